@@ -1,0 +1,89 @@
+/*
+ * ratrack_b200.h -- C ABI of libratrack_b200.so (hand-written sm_100a kernels for RaTrack's
+ * per-frame point-cloud hot path).
+ *
+ * Conventions (all entry points):
+ *   - plain C: device pointers + sizes, no torch / ATen types;
+ *   - every tensor is contiguous fp32 (float) or int32 (int) in DEVICE memory, laid out exactly
+ *     as the reference lays it out (shapes given per function);
+ *   - the caller owns every buffer; the library never allocates on behalf of these calls;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is
+ *     enqueued and the call returns immediately -- no synchronisation;
+ *   - return value: 0 on success, <0 for an argument/shape error, >0 = the cudaError_t of a
+ *     failed launch.  rt_last_error() returns a thread-local description.  The library never
+ *     calls exit() (the reference's launchers do: e.g. src/lib/src/ball_query_gpu.cu:62-65).
+ *
+ * Section 1 is the drop-in boundary for the reference's compiled module `pointnet2_cuda`
+ * (src/lib/src/pointnet2_api.cpp:11-24): one rt_* per pybind entry, same argument order.
+ * Section 2 is the fused inference engine for Track4D.backbone.
+ */
+#ifndef RATRACK_B200_H
+#define RATRACK_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int rt_abi_version(void);
+const char *rt_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Section 1 -- pointnet2 ops (Seam A)
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces ball_query_wrapper_fast       (reference: src/lib/src/ball_query.cpp:18-29,
+ *                                          kernel src/lib/src/ball_query_gpu.cu:9-45)
+ * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample).  First `nsample` points in index order with
+ * d2 < radius*radius; unused slots repeat the first hit; rows with no hit are left untouched
+ * (the reference's Python zero-fills idx first: src/lib/pointnet2_utils.py:246). */
+int rt_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx,
+                  void *stream);
+
+/* replaces group_points_wrapper_fast      (reference: src/lib/src/group_points.cpp:27-38)
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
+int rt_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out,
+                    void *stream);
+
+/* replaces group_points_grad_wrapper_fast (reference: src/lib/src/group_points.cpp:13-24)
+ * grad_out (b,c,npoints,nsample), idx -> grad_points (b,c,n) accumulated into (caller zero-fills) */
+int rt_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                         float *grad_points, void *stream);
+
+/* replaces gather_points_wrapper_fast     (reference: src/lib/src/sampling.cpp:12-21)
+ * points (b,c,n), idx (b,npoints) -> out (b,c,npoints) */
+int rt_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out, void *stream);
+
+/* replaces gather_points_grad_wrapper_fast (reference: src/lib/src/sampling.cpp:24-34) */
+int rt_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx, float *grad_points,
+                          void *stream);
+
+/* replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47,
+ *                                           kernel src/lib/src/sampling_gpu.cu:94-253)
+ * xyz (b,n,3), temp (b,n) [caller fills with 1e10; holds final min distances on return]
+ * -> idx (b,m), idx[:,0] = 0.  Bit-identical to the reference including arg-max ties. */
+int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream);
+
+/* replaces knn_wrapper_fast               (reference: src/lib/src/interpolate.cpp:27-36)
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,k) squared, idx (b,n,k), ascending, ties stable.
+ * k > 200 is rejected (the reference silently overflows its stack: interpolate_gpu.cu:30-31). */
+int rt_knn(int b, int n, int m, int k, const float *unknown, const float *known, float *dist2, int *idx,
+           void *stream);
+
+/* replaces three_nn_wrapper_fast          (reference: src/lib/src/interpolate.cpp:16-25)
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) squared, idx (b,n,3) */
+int rt_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *stream);
+
+/* replaces three_interpolate_wrapper_fast (reference: src/lib/src/interpolate.cpp:39-52)
+ * points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n) */
+int rt_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                         float *out, void *stream);
+
+/* replaces three_interpolate_grad_wrapper_fast (reference: src/lib/src/interpolate.cpp:54-67)
+ * grad_out (b,c,n), idx, weight -> grad_points (b,c,m) accumulated into (caller zero-fills) */
+int rt_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                              float *grad_points, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RATRACK_B200_H */

@@ -1,0 +1,61 @@
+"""ctypes binding of libratrack_b200.so (include/ratrack_b200.h).
+
+The library is the product: there is NO fallback.  If it is missing, or a call returns an
+error code, this module raises -- it never routes to torch ops or to oracle/.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libratrack_b200.so")
+
+_c_f = ctypes.c_void_p  # device pointers travel as raw addresses
+_I, _F, _P = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes (restype is always int); mirrors include/ratrack_b200.h
+SIGNATURES = {
+    "rt_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
+    "rt_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rt_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rt_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "rt_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "rt_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
+    "rt_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "rt_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "rt_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "rt_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+class RatrackError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RatrackError(
+                f"{SO_PATH} not found: build it with `python -m ratrack_b200.build` "
+                "(there is no CPU or torch fallback for these ops)")
+        L = ctypes.CDLL(SO_PATH)
+        L.rt_last_error.restype = ctypes.c_char_p
+        L.rt_abi_version.restype = ctypes.c_int
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, name: str):
+    if rc != 0:
+        msg = lib().rt_last_error().decode("utf-8", "replace")
+        raise RatrackError(f"{name} failed (code {rc}): {msg}")
+
+
+def call(name: str, *args):
+    check(getattr(lib(), name)(*args), name)

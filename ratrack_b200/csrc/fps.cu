@@ -1,0 +1,214 @@
+// Furthest point sampling for sm_100a.
+//
+// Replaces furthest_point_sampling_kernel / furthest_point_sampling_kernel_launcher
+// (reference: src/lib/src/sampling_gpu.cu:94-253) behind the same contract: idx[0] = 0, `temp`
+// holds the running min-distance (caller-initialised, 1e10 in src/lib/pointnet2_utils.py:26)
+// and is left holding the final values, results bit-identical to the reference including ties.
+//
+// Design (B200-first, not a translation):
+//   * one CTA per cloud, the whole cloud lives in REGISTERS (coordinates + running min
+//     distance), so a round touches no memory except one shared-memory exchange;
+//   * the reference's block-wide arg-max is a shared-memory tree with log2(bs)+1 barriers.
+//     Its tie-break is equivalent to "among maxima, minimise (bitrev(k mod bs), k div bs)"
+//     (bs = the reference's CTA size for this n).  Thread t here owns the residue class
+//     bitrev(t), and walks its points in that priority order, so plain "first strict maximum"
+//     scans plus "lowest lane / lowest warp wins" reproduce the reference bit for bit with
+//     ONE barrier per round: redux.sync.max + ballot inside a warp, one double-buffered
+//     shared-memory exchange across warps;
+//   * the cloud's xyz is staged once into shared memory by the bulk-copy engine (TMA, UBLKCP)
+//     for the broadcast read of the newly selected point each round.
+//   A generic kernel (any n) keeps the same ordering rule with 64-bit packed keys.
+#include "common.cuh"
+
+namespace {
+
+__host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
+    unsigned r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+// T threads; each thread owns PPT = Q*PH points.  bs = T*Q is the reference CTA size.
+// Slot s (priority order) = a*PH + ph  ->  point k = r + (bitrev_q(a) + Q*ph)*T,  r = bitrev_logT(t).
+template <int T, int Q, int PH>
+__global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all,
+                                                    float *__restrict__ temp_all, int *__restrict__ idx_all) {
+    constexpr int PPT = Q * PH;
+    constexpr int NW = (T + 31) / 32;
+    constexpr int LOGT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;
+    constexpr int LOGQ = (Q == 1) ? 0 : (Q == 2) ? 1 : (Q == 4) ? 2 : (Q == 8) ? 3 : (Q == 16) ? 4 : 5;
+
+    extern __shared__ __align__(16) float s_xyz[];  // n*3 floats
+    __shared__ uint2 s_red[2][NW];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int cloud = blockIdx.x;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    float *temp = temp_all + (size_t)cloud * n;
+    int *idx = idx_all + (size_t)cloud * m;
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+
+    if (t == 0) {
+        rt_mbar_init(&s_bar, 1);
+        rt_fence_mbar_init();
+    }
+    __syncthreads();
+    rt_stage_floats(s_xyz, xyz, n * 3, &s_bar, 0);
+
+    const int r = (int)bitrev_bits((unsigned)t, LOGT);
+    float px[PPT], py[PPT], pz[PPT], td[PPT];
+    int pk[PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) {
+        const int a = s / PH, ph = s % PH;
+        const int k = r + ((int)bitrev_bits((unsigned)a, LOGQ) + Q * ph) * T;
+        pk[s] = (k < n) ? k : -1;
+        const int kk = (k < n) ? k : 0;
+        px[s] = s_xyz[kk * 3 + 0];
+        py[s] = s_xyz[kk * 3 + 1];
+        pz[s] = s_xyz[kk * 3 + 2];
+        td[s] = (k < n) ? temp[k] : -2.0f;  // padding never beats the reference's initial best of -1
+    }
+
+    int old = 0;
+    if (t == 0) idx[0] = 0;
+
+    for (int j = 1; j < m; ++j) {
+        const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+        float best = -1.0f;
+        int besti = 0;
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float d = rt_sqdist(px[s], py[s], pz[s], x1, y1, z1);
+            // padding slots hold td = -2 and stay there (fminf keeps the smaller)
+            const float d2 = fminf(d, td[s]);
+            td[s] = d2;
+            const bool up = d2 > best;
+            besti = up ? pk[s] : besti;
+            best = up ? d2 : best;
+        }
+        const uint32_t key = rt_float_ordered(best);
+        const uint32_t wmax = rt_redux_max_u32(key);
+        const uint32_t vote = __ballot_sync(0xffffffffu, key == wmax);
+        const int src = __ffs(vote) - 1;
+        const int wi = __shfl_sync(0xffffffffu, besti, src);
+        int win;
+        if (NW == 1) {
+            win = wi;
+        } else {
+            const int buf = j & 1;
+            if (lane == 0) s_red[buf][warp] = make_uint2(wmax, (uint32_t)wi);
+            __syncthreads();
+            uint2 b = s_red[buf][0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) {
+                const uint2 c = s_red[buf][w];
+                if (c.x > b.x) b = c;
+            }
+            win = (int)b.y;
+        }
+        old = win;
+        if (t == 0) idx[j] = old;
+    }
+
+#pragma unroll
+    for (int s = 0; s < PPT; ++s)
+        if (pk[s] >= 0) temp[pk[s]] = td[s];
+}
+
+// Generic kernel: any n >= 1, temp kept in global memory (L1/L2 resident), 256 threads.
+// Candidate = (ordered(d2) << 32) | ~priority, priority = (bitrev_L(k mod bs) << 21) | (k div bs);
+// block-wide max of the 64-bit candidate gives the reference winner.
+__global__ void __launch_bounds__(256) fps_generic_kernel(int n, int m, int bs, int logbs,
+                                                          const float *__restrict__ xyz_all,
+                                                          float *__restrict__ temp_all, int *__restrict__ idx_all) {
+    __shared__ unsigned long long s_red[2][8];
+    const int cloud = blockIdx.x;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    float *temp = temp_all + (size_t)cloud * n;
+    int *idx = idx_all + (size_t)cloud * m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long none = ((unsigned long long)rt_float_ordered(-1.0f) << 32) | 0xffffffffull;
+
+    int old = 0;
+    if (t == 0) idx[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = __ldg(xyz + old * 3 + 0), y1 = __ldg(xyz + old * 3 + 1), z1 = __ldg(xyz + old * 3 + 2);
+        unsigned long long cand = none;
+        for (int k = t; k < n; k += 256) {
+            const float d = rt_sqdist(__ldg(xyz + k * 3 + 0), __ldg(xyz + k * 3 + 1), __ldg(xyz + k * 3 + 2), x1, y1, z1);
+            const float d2 = fminf(d, temp[k]);
+            temp[k] = d2;
+            if (d2 > -1.0f) {  // the reference's per-thread best starts at -1: anything <= -1 (or NaN) never wins
+                const unsigned pr = (bitrev_bits((unsigned)(k & (bs - 1)), logbs) << 21) | (unsigned)(k >> logbs);
+                const unsigned long long c = ((unsigned long long)rt_float_ordered(d2) << 32) | (unsigned)(~pr);
+                cand = c > cand ? c : cand;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long c = __shfl_xor_sync(0xffffffffu, cand, o);
+            cand = c > cand ? c : cand;
+        }
+        const int buf = j & 1;
+        if (lane == 0) s_red[buf][warp] = cand;
+        __syncthreads();
+        unsigned long long b = s_red[buf][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            const unsigned long long c = s_red[buf][w];
+            b = c > b ? c : b;
+        }
+        if (b == none) {
+            old = 0;
+        } else {
+            const unsigned pr = ~(unsigned)(b & 0xffffffffull);
+            old = (int)(((pr & 0x1fffffu) << logbs) | bitrev_bits(pr >> 21, logbs));
+        }
+        if (t == 0) idx[j] = old;
+    }
+}
+
+template <int T, int Q, int PH>
+int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t st) {
+    const size_t smem = (size_t)n * 3 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 40 * 1024) {
+        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    fps_reg_kernel<T, Q, PH><<<b, T, smem, st>>>(n, m, xyz, temp, idx);
+    return rt_check_launch("fps_reg_kernel");
+}
+
+}  // namespace
+
+// C-ABI.  replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47)
+RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream) {
+    RT_REQUIRE(b >= 0 && n >= 1 && xyz && temp && idx, "furthest_point_sampling: bad arguments (b=%d n=%d)", b, n);
+    if (m <= 0 || b == 0) return RT_OK;  // reference kernel returns early on m <= 0
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bs = rt_ref_block_size(n);
+    const int ph = (n + bs - 1) / bs;
+    // register-resident variants: T = 128 threads (4 warps = one per SM sub-partition), Q = bs/T
+    if (bs >= 128 && ph <= 4) {
+        const int q = bs / 128;
+#define RT_FPS_CASE(QQ, PP) \
+    if (q == QQ && ph == PP) return launch_reg<128, QQ, PP>(b, n, m, xyz, temp, idx, st);
+        RT_FPS_CASE(1, 1) RT_FPS_CASE(1, 2)
+        RT_FPS_CASE(2, 1) RT_FPS_CASE(2, 2)
+        RT_FPS_CASE(4, 1) RT_FPS_CASE(4, 2)
+        RT_FPS_CASE(8, 1) RT_FPS_CASE(8, 2)
+#undef RT_FPS_CASE
+        if (q == 8 && ph <= 4) {  // 2048 < n <= 4096: 256 threads x 16 points
+            if (ph == 3) return launch_reg<256, 4, 3>(b, n, m, xyz, temp, idx, st);
+            return launch_reg<256, 4, 4>(b, n, m, xyz, temp, idx, st);
+        }
+    }
+    int logbs = 0;
+    while ((1 << logbs) < bs) ++logbs;
+    RT_REQUIRE((n >> logbs) < (1 << 21), "furthest_point_sampling: n too large");
+    fps_generic_kernel<<<b, 256, 0, st>>>(n, m, bs, logbs, xyz, temp, idx);
+    return rt_check_launch("fps_generic_kernel");
+}

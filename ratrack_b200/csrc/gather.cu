@@ -1,0 +1,210 @@
+// Index-driven copy kernels for sm_100a: gather_points, group_points, three_interpolate and
+// their gradients.
+//
+// Replace gather_points_kernel_fast / gather_points_grad_kernel_fast
+// (reference: src/lib/src/sampling_gpu.cu:8-24, 46-63), group_points_kernel_fast /
+// group_points_grad_kernel_fast (src/lib/src/group_points_gpu.cu:47-66, 8-25) and
+// three_interpolate_kernel_fast / three_interpolate_grad_kernel_fast
+// (src/lib/src/interpolate_gpu.cu:149-169, 192-214).
+//
+// The reference launches one thread per OUTPUT ELEMENT PER CHANNEL, so every index (and
+// weight) is re-read C times.  Here a thread owns 4 consecutive output positions, loads its
+// indices / weights once as 128-bit vectors, then streams over a slab of channels writing
+// 128-bit coalesced stores; the gathers hit a (B,C,N) row that stays in L1/L2.
+// All base offsets are formed in 64 bits (the reference's int32 offsets overflow at large B).
+#include "common.cuh"
+
+namespace {
+
+constexpr int G_THREADS = 256;
+constexpr int G_CH_SLAB = 16;  // channels per CTA (grid.y = ceil(C / slab))
+
+// out[b,c,e] = points[b,c,idx[b,e]]   for e in [0, E): gather_points (E = npoints) and
+// group_points (E = npoints*nsample) are the same operation.
+__global__ void __launch_bounds__(G_THREADS) gather_rows_kernel(int c, int n, long long e_total,
+                                                                const float *__restrict__ points,
+                                                                const int *__restrict__ idx,
+                                                                float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * G_CH_SLAB;
+    const int c1 = min(c, c0 + G_CH_SLAB);
+    const long long e0 = ((long long)blockIdx.x * G_THREADS + threadIdx.x) * 4;
+    if (e0 >= e_total) return;
+    const int *ix = idx + (size_t)b * e_total + e0;
+    const float *src = points + ((size_t)b * c + c0) * n;
+    float *dst = out + ((size_t)b * c + c0) * e_total + e0;
+    const bool vec = (e0 + 3 < e_total) && ((e_total & 3) == 0);
+    if (vec) {
+        const int4 i4 = __ldg(reinterpret_cast<const int4 *>(ix));
+#pragma unroll 4
+        for (int ch = c0; ch < c1; ++ch) {
+            float4 v;
+            v.x = __ldg(src + i4.x);
+            v.y = __ldg(src + i4.y);
+            v.z = __ldg(src + i4.z);
+            v.w = __ldg(src + i4.w);
+            __stcs(reinterpret_cast<float4 *>(dst), v);
+            src += n;
+            dst += e_total;
+        }
+    } else {
+        const int cnt = (int)min(4ll, e_total - e0);
+        for (int ch = c0; ch < c1; ++ch) {
+            for (int q = 0; q < cnt; ++q) dst[q] = __ldg(src + __ldg(ix + q));
+            src += n;
+            dst += e_total;
+        }
+    }
+}
+
+// grad_points[b,c,idx[b,e]] += grad_out[b,c,e]  (same accumulation primitive as the reference:
+// fp32 atomic add, order not defined)
+__global__ void __launch_bounds__(G_THREADS) scatter_rows_kernel(int c, int n, long long e_total,
+                                                                 const float *__restrict__ grad_out,
+                                                                 const int *__restrict__ idx,
+                                                                 float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * G_CH_SLAB;
+    const int c1 = min(c, c0 + G_CH_SLAB);
+    const long long e = (long long)blockIdx.x * G_THREADS + threadIdx.x;
+    if (e >= e_total) return;
+    const int id = __ldg(idx + (size_t)b * e_total + e);
+    const float *g = grad_out + ((size_t)b * c + c0) * e_total + e;
+    float *dst = grad_points + ((size_t)b * c + c0) * n + id;
+    for (int ch = c0; ch < c1; ++ch) {
+        atomicAdd(dst, __ldg(g));
+        g += e_total;
+        dst += n;
+    }
+}
+
+// out[b,c,j] = fma(w2, p[i2], fma(w0, p[i0], w1*p[i1]))  -- the reference's sm_100 evaluation order
+__global__ void __launch_bounds__(G_THREADS) three_interpolate_kernel(int c, int m, int n,
+                                                                      const float *__restrict__ points,
+                                                                      const int *__restrict__ idx,
+                                                                      const float *__restrict__ weight,
+                                                                      float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * G_CH_SLAB;
+    const int c1 = min(c, c0 + G_CH_SLAB);
+    const int j = blockIdx.x * G_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const int *ix = idx + ((size_t)b * n + j) * 3;
+    const float *w = weight + ((size_t)b * n + j) * 3;
+    const int i0 = __ldg(ix + 0), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
+    const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const float *src = points + ((size_t)b * c + c0) * m;
+    float *dst = out + ((size_t)b * c + c0) * n + j;
+#pragma unroll 4
+    for (int ch = c0; ch < c1; ++ch) {
+        float t = __fmul_rn(w1, __ldg(src + i1));
+        t = __fmaf_rn(w0, __ldg(src + i0), t);
+        *dst = __fmaf_rn(w2, __ldg(src + i2), t);
+        src += m;
+        dst += n;
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS) three_interpolate_grad_kernel(int c, int n, int m,
+                                                                           const float *__restrict__ grad_out,
+                                                                           const int *__restrict__ idx,
+                                                                           const float *__restrict__ weight,
+                                                                           float *__restrict__ grad_points) {
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * G_CH_SLAB;
+    const int c1 = min(c, c0 + G_CH_SLAB);
+    const int j = blockIdx.x * G_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const int *ix = idx + ((size_t)b * n + j) * 3;
+    const float *w = weight + ((size_t)b * n + j) * 3;
+    const int i0 = __ldg(ix + 0), i1 = __ldg(ix + 1), i2 = __ldg(ix + 2);
+    const float w0 = __ldg(w + 0), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const float *g = grad_out + ((size_t)b * c + c0) * n + j;
+    float *dst = grad_points + ((size_t)b * c + c0) * m;
+    for (int ch = c0; ch < c1; ++ch) {
+        const float gv = __ldg(g);
+        atomicAdd(dst + i0, __fmul_rn(gv, w0));
+        atomicAdd(dst + i1, __fmul_rn(gv, w1));
+        atomicAdd(dst + i2, __fmul_rn(gv, w2));
+        g += n;
+        dst += m;
+    }
+}
+
+int launch_gather(int b, int c, int n, long long e_total, const float *points, const int *idx, float *out,
+                  cudaStream_t st, const char *what) {
+    if (b == 0 || c == 0 || e_total == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535, "%s: batch > 65535", what);
+    dim3 grid(rt_divup(e_total, (long long)G_THREADS * 4), rt_divup(c, G_CH_SLAB), b);
+    gather_rows_kernel<<<grid, G_THREADS, 0, st>>>(c, n, e_total, points, idx, out);
+    return rt_check_launch(what);
+}
+
+int launch_scatter(int b, int c, int n, long long e_total, const float *grad_out, const int *idx, float *grad_points,
+                   cudaStream_t st, const char *what) {
+    if (b == 0 || c == 0 || e_total == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535, "%s: batch > 65535", what);
+    dim3 grid(rt_divup(e_total, G_THREADS), rt_divup(c, G_CH_SLAB), b);
+    scatter_rows_kernel<<<grid, G_THREADS, 0, st>>>(c, n, e_total, grad_out, idx, grad_points);
+    return rt_check_launch(what);
+}
+
+}  // namespace
+
+// replaces gather_points_wrapper_fast (reference: src/lib/src/sampling.cpp:12-21)
+RT_API int rt_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                            void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && points && idx && out, "gather_points: bad arguments");
+    return launch_gather(b, c, n, npoints, points, idx, out, (cudaStream_t)stream, "gather_points");
+}
+
+// replaces gather_points_grad_wrapper_fast (reference: src/lib/src/sampling.cpp:24-34)
+RT_API int rt_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                 float *grad_points, void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && grad_out && idx && grad_points,
+               "gather_points_grad: bad arguments");
+    return launch_scatter(b, c, n, npoints, grad_out, idx, grad_points, (cudaStream_t)stream, "gather_points_grad");
+}
+
+// replaces group_points_wrapper_fast (reference: src/lib/src/group_points.cpp:27-38)
+RT_API int rt_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                           float *out, void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0 && points && idx && out,
+               "group_points: bad arguments");
+    return launch_gather(b, c, n, (long long)npoints * nsample, points, idx, out, (cudaStream_t)stream,
+                         "group_points");
+}
+
+// replaces group_points_grad_wrapper_fast (reference: src/lib/src/group_points.cpp:13-24)
+RT_API int rt_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                                float *grad_points, void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0 && grad_out && idx && grad_points,
+               "group_points_grad: bad arguments");
+    return launch_scatter(b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points, (cudaStream_t)stream,
+                          "group_points_grad");
+}
+
+// replaces three_interpolate_wrapper_fast (reference: src/lib/src/interpolate.cpp:39-52)
+RT_API int rt_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                                float *out, void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0 && points && idx && weight && out,
+               "three_interpolate: bad arguments");
+    if (b == 0 || c == 0 || n == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535, "three_interpolate: batch > 65535");
+    dim3 grid(rt_divup(n, G_THREADS), rt_divup(c, G_CH_SLAB), b);
+    three_interpolate_kernel<<<grid, G_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+    return rt_check_launch("three_interpolate");
+}
+
+// replaces three_interpolate_grad_wrapper_fast (reference: src/lib/src/interpolate.cpp:54-67)
+RT_API int rt_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                     const float *weight, float *grad_points, void *stream) {
+    RT_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0 && grad_out && idx && weight && grad_points,
+               "three_interpolate_grad: bad arguments");
+    if (b == 0 || c == 0 || n == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535, "three_interpolate_grad: batch > 65535");
+    dim3 grid(rt_divup(n, G_THREADS), rt_divup(c, G_CH_SLAB), b);
+    three_interpolate_grad_kernel<<<grid, G_THREADS, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight,
+                                                                                grad_points);
+    return rt_check_launch("three_interpolate_grad");
+}

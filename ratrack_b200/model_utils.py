@@ -1,0 +1,297 @@
+"""Seam C: the model blocks of RaTrack's hot path with the reference's names, constructor arguments,
+forward signatures, return shapes and state_dict keys
+(reference: src/utils/model_utils/model_utils.py:17-424 and src/models/track4d.py:13-106).
+
+Two execution paths share one set of parameters:
+  * modular path (this file): nn.Modules whose native ops are the sm_100a kernels behind
+    ratrack_b200.lib.pointnet2_utils -- supports train and eval, autograd, any batch size;
+  * fused path (ratrack_b200/engine.py): `Track4DBackbone.backbone` in eval mode without grad is
+    served by the fused CUDA engine (BN folded, grouping+MLP+max fused, cost volume fused).
+
+Differences from the reference that do not change results: no hard-coded `.cuda()` (tensors are
+created on the inputs' device), `h=None` creates zeros for the actual batch size
+(the reference hard-codes batch 1: model_utils.py:295), and the dead sub-module
+`FlowDecoder.pnnGru` (constructed but never called, model_utils.py:278) is not instantiated --
+reference checkpoints load with strict=False exactly as the reference itself loads them
+(src/models/model.py:24,37).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .lib.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+
+
+def square_distance(src, dst):
+    """Expanded-form squared distances, clamped at 0: (B,N,C),(B,M,C) -> (B,N,M).  reference :17-39"""
+    B, N, _ = src.shape
+    _, M, _ = dst.shape
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    return torch.clamp_min(dist, 0.0)
+
+
+def index_points(points, idx):
+    """points (B,N,C), idx (B,S[,K]) -> (B,S[,K],C).  reference :42-59"""
+    B = points.shape[0]
+    batch = torch.arange(B, dtype=torch.long, device=points.device).view(B, *([1] * (idx.dim() - 1))).expand_as(idx)
+    return points[batch, idx, :]
+
+
+def knn_point(nsample, xyz, new_xyz):
+    """(B,S,nsample) indices of the nsample nearest points of xyz to each new_xyz.  reference :85-99"""
+    sqrdists = square_distance(new_xyz, xyz)
+    _, group_idx = torch.topk(sqrdists, nsample, dim=-1, largest=False, sorted=False)
+    return group_idx
+
+
+class WeightNet(nn.Module):
+    """conv 3->8->8->out + ReLU each; the BN modules exist (state_dict) but are unused when bn=False.  reference :359-390"""
+
+    def __init__(self, in_channel, out_channel, hidden_unit=[8, 8], bn=False):
+        super().__init__()
+        self.bn = bn
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        widths = [in_channel] + list(hidden_unit or []) + [out_channel]
+        for cin, cout in zip(widths[:-1], widths[1:]):
+            self.mlp_convs.append(nn.Conv2d(cin, cout, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(cout))
+
+    def forward(self, localized_xyz):
+        weights = localized_xyz
+        for i, conv in enumerate(self.mlp_convs):
+            weights = conv(weights)
+            if self.bn:
+                weights = self.mlp_bns[i](weights)
+            weights = F.relu(weights)
+        return weights
+
+
+class FeatureCorrelator(nn.Module):
+    """Cost volume: point-to-patch (kNN in pc2) then patch-to-patch (kNN in pc1).  reference :166-250"""
+
+    def __init__(self, nsample, in_channel, mlp, bn=False, use_leaky=True):
+        super().__init__()
+        self.nsample = nsample
+        self.bn = bn
+        self.mlp_convs = nn.ModuleList()
+        self.mlp2 = nn.ModuleList()
+        if bn:
+            self.mlp_bns = nn.ModuleList()
+            self.mlp_bns2 = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            if bn:
+                self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last_channel = out_channel
+        self.cls_mlp = nn.Linear(16, 1)  # unused by forward; kept for checkpoint compatibility
+        self.weightnet1 = WeightNet(3, last_channel)
+        self.weightnet2 = WeightNet(3, last_channel)
+        self.relu = nn.ReLU(inplace=True) if not use_leaky else nn.LeakyReLU(0.1, inplace=True)
+        self.sig = nn.Sigmoid()
+
+    def forward(self, pc1, pc2, feature1, feature2):
+        """pc (B,3,N), feature (B,D,N) -> (B,mlp[-1],N1)"""
+        B, C, N1 = pc1.shape
+        pc1 = pc1.permute(0, 2, 1)
+        pc2 = pc2.permute(0, 2, 1)
+        feature1 = feature1.permute(0, 2, 1)
+        feature2 = feature2.permute(0, 2, 1)
+        D1 = feature1.shape[2]
+
+        knn_idx = knn_point(self.nsample, pc2, pc1)
+        direction_xyz = index_points(pc2, knn_idx) - pc1.reshape(B, N1, 1, C)
+        grouped_feature2 = index_points(feature2, knn_idx)
+        grouped_feature1 = feature1.reshape(B, N1, 1, D1).expand(-1, -1, self.nsample, -1)
+        x = torch.cat([grouped_feature1, grouped_feature2, direction_xyz], dim=-1).permute(0, 3, 2, 1)
+        for i, conv in enumerate(self.mlp_convs):
+            x = conv(x)
+            if self.bn:
+                x = self.mlp_bns[i](x)
+            x = self.relu(x)
+        weights = self.weightnet1(direction_xyz.permute(0, 3, 2, 1))
+        x = torch.sum(weights * x, dim=2)  # (B,C,N)
+
+        knn_idx = knn_point(self.nsample, pc1, pc1)
+        direction_xyz = index_points(pc1, knn_idx) - pc1.reshape(B, N1, 1, C)
+        weights = self.weightnet2(direction_xyz.permute(0, 3, 2, 1))
+        x = index_points(x.permute(0, 2, 1), knn_idx)
+        return torch.sum(weights * x.permute(0, 3, 2, 1), dim=2)
+
+
+class FlowPredictor(nn.Module):
+    """[conv1x1(no bias)+BN+ReLU] x3 -> conv1x1 -> (B,3,N).  reference :308-329"""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.sf_mlp = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.sf_mlp.append(nn.Sequential(nn.Conv2d(last_channel, out_channel, 1, bias=False),
+                                             nn.BatchNorm2d(out_channel), nn.ReLU(inplace=False)))
+            last_channel = out_channel
+        self.conv2 = nn.Conv2d(mlp[-1], 3, 1, bias=False)
+
+    def forward(self, feat):
+        feat = feat.unsqueeze(3)
+        for block in self.sf_mlp:
+            feat = block(feat)
+        return self.conv2(feat).squeeze(3)
+
+
+class ClsPredictor(nn.Module):
+    """FlowPredictor trunk -> Linear(3->1) -> sigmoid -> (B,N).  reference :332-357"""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.sf_mlp = nn.ModuleList()
+        last_channel = in_channel
+        for out_channel in mlp:
+            self.sf_mlp.append(nn.Sequential(nn.Conv2d(last_channel, out_channel, 1, bias=False),
+                                             nn.BatchNorm2d(out_channel), nn.ReLU(inplace=False)))
+            last_channel = out_channel
+        self.conv2 = nn.Conv2d(mlp[-1], 3, 1, bias=False)
+        self.linear = nn.Linear(3, 1)
+        self.sig = nn.Sigmoid()
+
+    def forward(self, feat):
+        feat = feat.unsqueeze(3)
+        for block in self.sf_mlp:
+            feat = block(feat)
+        out = self.conv2(feat)
+        out = self.linear(out.squeeze(3).permute(0, 2, 1))
+        return self.sig(out).squeeze(2)
+
+
+class PNHead(nn.Module):
+    """3 x SA-MSG + 3 x Linear + 3 x FP.  pc (B,N,3), features (B,C,N) -> (l3_xyz (B,S,3), (B,128,N)).  reference :393-424"""
+
+    def __init__(self, sample_point_num, in_channels):
+        super().__init__()
+        S = sample_point_num
+        self.sa1 = PointnetSAModuleMSG(npoint=S, radii=[2, 4], nsamples=[4, 8],
+                                       mlps=[[in_channels, 16, 16, 32], [in_channels, 16, 16, 32]])
+        self.sa2 = PointnetSAModuleMSG(npoint=S, radii=[4, 8], nsamples=[8, 16],
+                                       mlps=[[3 + 32, 32, 32], [3 + 32, 32, 64]])
+        self.sa3 = PointnetSAModuleMSG(npoint=S, radii=[8, 16], nsamples=[16, 32],
+                                       mlps=[[3 + 64, 64, 64], [3 + 64, 64, 64]])
+        self.fp3 = PointnetFPModule(mlp=[128, 128])
+        self.fp2 = PointnetFPModule(mlp=[160, 128])
+        self.fp1 = PointnetFPModule(mlp=[128, 128])
+        self.linear1 = nn.Linear(64, 32)
+        self.linear2 = nn.Linear(96, 64)
+        self.linear3 = nn.Linear(128, 64)
+
+    @staticmethod
+    def _lin(layer, x):
+        return layer(x.permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+
+    def forward(self, pc, features):
+        l0_points = features.contiguous()
+        l0_xyz = pc.contiguous()
+        l1_xyz, l1_points = self.sa1(l0_xyz, l0_points)
+        l1_points = self._lin(self.linear1, l1_points)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
+        l2_points = self._lin(self.linear2, l2_points)
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        l3_points = self._lin(self.linear3, l3_points)
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points)
+        return l3_xyz, l0_points
+
+
+class FlowDecoder(nn.Module):
+    """cls head, PNHead over [ft, feat, cost] embeddings, 5-layer GRU on the global feature, flow head.  reference :253-305"""
+
+    def __init__(self, fc_inch, args):
+        super().__init__()
+        ep_inch = fc_inch * 2 + 5
+        ep_mlp2s = [int(fc_inch / 8)] * 3
+        num_eps = 4
+        self.mse = PNHead(args.npoints, ep_inch)
+        sf_inch = num_eps * ep_mlp2s[-1] * 2
+        sf_mlps = [int(sf_inch / 2), int(sf_inch / 4), int(sf_inch / 8)]
+        self.fp = FlowPredictor(in_channel=sf_inch, mlp=sf_mlps)
+        self.cp = ClsPredictor(in_channel=sf_inch, mlp=sf_mlps)
+        self.mlp2 = nn.ModuleList([nn.Linear(3, 1)])                    # unused by forward (checkpoint compat)
+        self.gru2 = nn.GRU(input_size=fc_inch, hidden_size=fc_inch)     # unused by forward (checkpoint compat)
+        self.sig = nn.Sigmoid()
+        self.torchGRU = nn.GRU(fc_inch // 2, fc_inch // 2, 5)
+
+    def forward(self, pc1, feature1, pc1_features, cor_features, h):
+        cls = self.cp(cor_features)
+        if feature1 is not None:
+            embeddings = torch.cat((feature1, pc1_features, cor_features), dim=1)
+        else:
+            embeddings = torch.cat((pc1_features, cor_features), dim=1)
+        _, prop_features = self.mse(pc1.permute(0, 2, 1).contiguous(), embeddings)
+        gfeat = torch.max(prop_features, -1)[0].unsqueeze(2)
+        if h is None:
+            h = torch.zeros(5, pc1.size(0), 128, device=pc1.device, dtype=pc1.dtype)
+        gfeat, h = self.torchGRU(gfeat.permute(2, 0, 1), h)
+        gfeat = gfeat.permute(1, 2, 0).expand(prop_features.size(0), prop_features.size(1), pc1.size(2))
+        output = self.fp(torch.cat((prop_features, gfeat), dim=1))
+        return output, h, prop_features, cls
+
+
+class Track4DBackbone(nn.Module):
+    """The hot path of `Track4D` (reference: src/models/track4d.py:13-106): pn_head, fc_layer, fd_layer and
+    the methods backbone / flow_head / feature_extraction_head with the reference's signatures and
+    parameter names (`pn_head.*`, `fc_layer.*`, `fd_layer.*`), so a reference checkpoint loads with
+    strict=False.  Clustering / association (track4d.py:108-223) are out of this path's scope.
+
+    `args` needs `.npoints` (FPS sample count of all three SA levels, configs.yaml:25).
+    """
+
+    def __init__(self, args):
+        super().__init__()
+        self.npoints_cfg = args.npoints
+        self.pn_head = PNHead(args.npoints, 5)
+        fc_inch = 2 * 128
+        self.fc_layer = FeatureCorrelator(16, in_channel=fc_inch * 2 + 3, mlp=[fc_inch, fc_inch, fc_inch])
+        self.fd_layer = FlowDecoder(fc_inch=fc_inch, args=args)
+        self.use_fused = True   # eval + no_grad -> fused engine
+        self._engine = None
+
+    # -- reference-shaped methods ------------------------------------------------------------
+    def feature_extraction_head(self, feature1, feature2, pc1, pc2):
+        xyz1_new, pc1_features = self.pn_head(pc1.permute(0, 2, 1).contiguous(), feature1)
+        xyz2_new, pc2_features = self.pn_head(pc2.permute(0, 2, 1).contiguous(), feature2)
+        return feature1, pc1, pc1_features, pc2, pc2_features, xyz1_new, xyz2_new
+
+    def flow_head(self, feature1, h, pc1, pc1_features, pc2, pc2_features, xyz1_new, xyz2_new):
+        gfeat_1 = torch.max(pc1_features, -1)[0].unsqueeze(2).expand(-1, -1, pc1.size(2))
+        gfeat_2 = torch.max(pc2_features, -1)[0].unsqueeze(2).expand(-1, -1, pc2.size(2))
+        pc1_features = torch.cat((pc1_features, gfeat_1), dim=1)
+        pc2_features = torch.cat((pc2_features, gfeat_2), dim=1)
+        cor_features = self.fc_layer(pc1, pc2, pc1_features, pc2_features)
+        output, h, prop_features, cls = self.fd_layer(pc1, feature1, pc1_features, cor_features, h)
+        return cor_features, h, output, cls, pc1_features, pc2_features, prop_features
+
+    def backbone_modular(self, pc1, pc2, feature1, feature2, h):
+        feature1, pc1, pc1_features, pc2, pc2_features, xyz1_new, xyz2_new = \
+            self.feature_extraction_head(feature1, feature2, pc1, pc2)
+        cor_features, h, output, cls, pc1_features, pc2_features, prop_features = \
+            self.flow_head(feature1, h, pc1, pc1_features, pc2, pc2_features, xyz1_new, xyz2_new)
+        return output, h, cls, cor_features, pc1_features, pc2_features, prop_features
+
+    def backbone(self, pc1, pc2, feature1, feature2, h):
+        """pc (B,3,N), feature (B,2,N), h (5,B,128)|None ->
+        (output (B,3,N), h, cls (B,N), cor_features (B,256,N), pc1_features, pc2_features (B,256,N), prop_features (B,128,N))"""
+        if self.use_fused and not self.training and not torch.is_grad_enabled():
+            from .engine import FusedBackbone
+            if self._engine is None:
+                self._engine = FusedBackbone(self)
+            return self._engine(pc1, pc2, feature1, feature2, h)
+        return self.backbone_modular(pc1, pc2, feature1, feature2, h)
+
+    def forward(self, pc1, pc2, feature1, feature2, h=None):
+        return self.backbone(pc1, pc2, feature1, feature2, h)
+
+    def train(self, mode: bool = True):
+        self._engine = None  # parameters may change: re-fold on next eval call
+        return super().train(mode)
