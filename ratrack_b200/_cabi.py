@@ -57,5 +57,25 @@ def check(rc: int, name: str):
         raise RatrackError(f"{name} failed (code {rc}): {msg}")
 
 
+# launch accounting for bench.py: every successful call() is exactly one kernel launch of ours
+launch_count = 0
+# optional device timing of one entry point: set to {"name": "rt_...", "events": []} and every call
+# of that entry is bracketed by CUDA events on the stream it is launched on
+profile = None
+
+
 def call(name: str, *args):
-    check(getattr(lib(), name)(*args), name)
+    global launch_count
+    p = profile
+    if p is not None and p["name"] == name:
+        import torch
+
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.default_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        check(getattr(lib(), name)(*args), name)
+        e1.record(st)
+        p["events"].append((e0, e1))
+    else:
+        check(getattr(lib(), name)(*args), name)
+    launch_count += 1

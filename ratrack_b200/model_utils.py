@@ -254,7 +254,7 @@ class Track4DBackbone(nn.Module):
         fc_inch = 2 * 128
         self.fc_layer = FeatureCorrelator(16, in_channel=fc_inch * 2 + 3, mlp=[fc_inch, fc_inch, fc_inch])
         self.fd_layer = FlowDecoder(fc_inch=fc_inch, args=args)
-        self.use_fused = True   # eval + no_grad -> fused engine
+        self.use_fused = False  # eval + no_grad -> fused engine (enabled once ratrack_b200/engine.py is built)
         self._engine = None
 
     # -- reference-shaped methods ------------------------------------------------------------
@@ -291,6 +291,39 @@ class Track4DBackbone(nn.Module):
 
     def forward(self, pc1, pc2, feature1, feature2, h=None):
         return self.backbone(pc1, pc2, feature1, feature2, h)
+
+    @torch.no_grad()
+    def infer_host(self, pc1, pc2, feature1, feature2, h=None):
+        """Host-buffer entry: (B,3,N)/(B,2,N) fp32 host tensors (pinned for async copies) -> (flow (B,3,N),
+        cls (B,N)) as host tensors.  H2D copies, the backbone and the D2H result reads all happen here."""
+        dev = next(self.parameters()).device
+        args = [x.to(dev, non_blocking=True) for x in (pc1, pc2, feature1, feature2)]
+        if h is None:
+            h = torch.zeros(5, pc1.size(0), 128, device=dev)
+        out = self.backbone(args[0], args[1], args[2], args[3], h)
+        key = (tuple(out[0].shape), dev)
+        if getattr(self, "_host_out_key", None) != key:
+            self._host_out = (torch.empty(out[0].shape, dtype=torch.float32).pin_memory(),
+                              torch.empty(out[2].shape, dtype=torch.float32).pin_memory())
+            self._host_out_key = key
+        self._host_out[0].copy_(out[0], non_blocking=True)
+        self._host_out[1].copy_(out[2], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self._host_out
+
+    @staticmethod
+    def fused_available():
+        try:
+            from . import engine  # noqa: F401
+            return True
+        except ImportError:
+            return False
+
+    def cost_volume_neighbours(self, pc1, pc2):
+        """The two 16-NN index sets the cost volume uses (pc1->pc2, pc1->pc1), (B,N,16) each --
+        exposed so parity checks can be tie-aware (reference: model_utils.py:216,239)."""
+        a, b = pc1.permute(0, 2, 1), pc2.permute(0, 2, 1)
+        return knn_point(self.fc_layer.nsample, b, a), knn_point(self.fc_layer.nsample, a, a)
 
     def train(self, mode: bool = True):
         self._engine = None  # parameters may change: re-fold on next eval call

@@ -7,6 +7,8 @@ A record is the 7-column VoD row [x, y, z, RCS, v_r, v_r_comp, time]
 (src/vod/frame/data_loader.py:71,174); the model consumes pc = cols 0:3 as (B,3,N) and
 ft = cols 3:5 as (B,2,N) (src/main_utils.py:76-79).
 """
+import os
+
 import numpy as np
 
 
@@ -66,21 +68,39 @@ def make_batch(batch: int, n_points: int, seed: int = 1234):
     return dict(pc1=pc1, pc2=pc2, ft1=ft1, ft2=ft2)
 
 
-def make_state_dict(module, seed: int = 1234):
+BN_CALIB_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bn_calibration_seed1234.npz")
+
+
+def make_state_dict(module, seed: int = 1234, calibrated: bool = True):
     """Deterministic weights for any module exposing the reference's state_dict surface.
 
     There is no network for checkpoints, so benchmarks and parity fixtures use this recipe: every
     tensor is drawn from a numpy Generator seeded by (seed, crc32(key)) -- independent of module
     construction order, so the reference model and this package get identical values for
     identical keys.  Conv / Linear weights ~ N(0, 2/fan_in) (Kaiming-normal, as the reference
-    initialises its SharedMLP convs: src/lib/pytorch_utils.py:138,176), biases ~ N(0, 0.05),
-    BN weight ~ U(0.8, 1.2), BN bias ~ N(0, 0.1), running_mean ~ N(0, 0.2), running_var ~ U(0.6, 1.6).
+    initialises its SharedMLP convs: src/lib/pytorch_utils.py:138,176), GRU weights ~ N(0, 1/fan_in),
+    biases ~ N(0, 0.05), BN weight ~ U(0.8, 1.2), BN bias ~ N(0, 0.1).  The last WeightNet conv
+    (8 -> 256, no normalisation follows it) is scaled by 1/16 so the two sums over 16 neighbours in
+    the cost volume (src/utils/model_utils/model_utils.py:236,248) keep activations O(1), as a trained
+    network's would be.
+
+    BN running statistics: with `calibrated` (seed 1234 only) they come from
+    data/bn_calibration_seed1234.npz -- batch statistics of one train-mode pass (momentum 1) of the
+    reference model over synthetic.make_batch(4, 1024, seed=4321), written by oracle/gen_golden.py --
+    so eval-mode activations are normalised like a trained model's.  Otherwise
+    running_mean ~ N(0, 0.2), running_var ~ U(0.6, 1.6).
     Returns a dict of torch tensors (CPU, fp32 / int64) to pass to load_state_dict(strict=False).
     """
+    import os
     import zlib
 
     import torch
 
+    calib = None
+    if calibrated:
+        if seed != 1234 or not os.path.exists(BN_CALIB_FILE):
+            raise RuntimeError("BN calibration exists only for seed 1234 (ratrack_b200/data/); pass calibrated=False")
+        calib = np.load(BN_CALIB_FILE)
     out = {}
     for key, ref in module.state_dict().items():
         shape = tuple(ref.shape)
@@ -90,13 +110,21 @@ def make_state_dict(module, seed: int = 1234):
         if key.endswith("num_batches_tracked"):
             out[key] = torch.tensor(1, dtype=torch.int64)
             continue
-        if key.endswith("running_mean"):
-            v = rng.normal(0, 0.2, shape)
-        elif key.endswith("running_var"):
-            v = rng.uniform(0.6, 1.6, shape)
+        if key.endswith("running_mean") or key.endswith("running_var"):
+            if calib is not None and key in calib.files:
+                v = calib[key]
+            elif calib is not None:
+                v = np.zeros(shape) if key.endswith("running_mean") else np.ones(shape)
+            elif key.endswith("running_mean"):
+                v = rng.normal(0, 0.2, shape)
+            else:
+                v = rng.uniform(0.6, 1.6, shape)
         elif len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
-            v = rng.normal(0, np.sqrt(2.0 / fan_in), shape)
+            gain = 1.0 if "GRU" in key or "gru" in key else 2.0
+            v = rng.normal(0, np.sqrt(gain / fan_in), shape)
+            if "weightnet" in key and key.endswith("mlp_convs.2.weight"):
+                v = v / 16.0
         elif len(shape) == 1 and is_bn and key.endswith("weight"):
             v = rng.uniform(0.8, 1.2, shape)
         elif len(shape) == 1 and is_bn:
@@ -105,5 +133,7 @@ def make_state_dict(module, seed: int = 1234):
             v = np.asarray(1.0)
         else:
             v = rng.normal(0, 0.05, shape)
+            if "weightnet" in key and key.endswith("mlp_convs.2.bias"):
+                v = v / 16.0
         out[key] = torch.from_numpy(np.asarray(v, dtype=np.float32).reshape(shape))
     return out

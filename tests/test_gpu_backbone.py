@@ -1,0 +1,111 @@
+"""GPU parity of Track4D.backbone (PNHead x3 + cost volume + flow decoder) against the oracle and the
+golden outputs of the unmodified reference Python (tests/golden/backbone_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import backbone_oracle
+from ratrack_b200 import synthetic
+from ratrack_b200.model_utils import Track4DBackbone
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # of the tensor's scale: |d| <= TOL * max(1, max|ref|)   (DESIGN.md "Parity")
+
+
+class Args:
+    npoints = 512
+
+
+def _net(fused):
+    net = Track4DBackbone(Args())
+    sd = synthetic.make_state_dict(net, seed=1234)
+    net.load_state_dict(sd, strict=False)
+    net.use_fused = fused
+    return net.cuda().eval(), sd
+
+
+def _run(net, batch, n, seed=1234):
+    d = synthetic.make_batch(batch, n, seed=seed)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    with torch.no_grad():
+        out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128, device="cuda"))
+        knn = net.cost_volume_neighbours(t["pc1"], t["pc2"])
+    return d, [o.cpu() for o in out], [k.cpu().long() for k in knn]
+
+
+def knn_sets_equivalent(pc_q, pc_s, got, want, slack=8.0):
+    """Tie-aware kNN comparison.  Rows whose index sets differ are accepted only when every index in
+    the symmetric difference sits within `slack` ulps (of the expanded-form terms) of the k-th distance.
+    Returns (#rows that differ, #rows that differ without a tie excuse)."""
+    q = pc_q.transpose(0, 2, 1).astype(np.float64)
+    s = pc_s.transpose(0, 2, 1).astype(np.float64)
+    differ = bad = 0
+    for b in range(got.shape[0]):
+        for i in range(got.shape[1]):
+            a, w = set(got[b, i].tolist()), set(want[b, i].tolist())
+            if a == w:
+                continue
+            differ += 1
+            d2 = ((s[b] - q[b, i]) ** 2).sum(-1)
+            kth = np.sort(d2)[got.shape[2] - 1]
+            mag = (q[b, i] ** 2).sum() + (s[b] ** 2).sum(-1).max()
+            eps = slack * np.finfo(np.float32).eps * mag
+            if any(abs(d2[j] - kth) > eps for j in a ^ w):
+                bad += 1
+    return differ, bad
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name,batch,n", [("backbone_n256_b1.npz", 1, 256), ("backbone_n1024_b2.npz", 2, 1024)])
+def test_backbone_vs_reference_golden(fused, name, batch, n):
+    net, sd = _net(fused)
+    if fused and not net.fused_available():
+        pytest.skip("fused engine not built")
+    g = np.load(os.path.join(GOLDEN, name))
+    d, out, knn = _run(net, batch, n)
+    # 1. neighbour sets: equal to what the reference's torch.topk chose, up to genuine distance ties
+    diff12, bad12 = knn_sets_equivalent(d["pc1"], d["pc2"], knn[0].numpy(), g["knn12"])
+    diff11, bad11 = knn_sets_equivalent(d["pc1"], d["pc1"], knn[1].numpy(), g["knn11"])
+    assert bad12 == 0 and bad11 == 0, (diff12, bad12, diff11, bad11)
+    # 2. values: against the oracle replaying the product's neighbour choice
+    c = {k: torch.from_numpy(v) for k, v in d.items()}
+    ref = backbone_oracle.backbone(sd, c["pc1"], c["pc2"], c["ft1"], c["ft2"], torch.zeros(5, batch, 128),
+                                   knn_override=tuple(knn))
+    names = ["flow", "h", "cls", "cor", "f1", "f2", "prop"]
+    for nm, a, r in zip(names, out, ref):
+        scale = max(1.0, float(r.abs().max()))
+        err = float((a - r).abs().max())
+        assert err <= TOL * scale, (nm, err, scale)
+    # 3. and directly against the reference-generated golden flow when no neighbour set differed
+    if diff12 == 0 and diff11 == 0:
+        err = np.abs(out[0].numpy() - g["flow"]).max()
+        assert err <= TOL * max(1.0, np.abs(g["flow"]).max()), err
+
+
+def test_modules_keep_reference_state_dict_surface():
+    net, sd = _net(False)
+    keys = set(net.state_dict().keys())
+    for k in ["pn_head.sa1.mlps.0.layer0.conv.weight", "pn_head.sa1.mlps.1.layer2.bn.bn.running_var",
+              "pn_head.fp2.mlp.layer0.conv.weight", "pn_head.linear3.bias", "fc_layer.mlp_convs.0.weight",
+              "fc_layer.weightnet2.mlp_convs.2.bias", "fd_layer.mse.sa1.mlps.0.layer0.conv.weight",
+              "fd_layer.fp.sf_mlp.2.1.running_mean", "fd_layer.cp.linear.weight", "fd_layer.torchGRU.weight_hh_l4"]:
+        assert k in keys, k
+    assert net.state_dict()["fd_layer.mse.sa1.mlps.0.layer0.conv.weight"].shape == (16, 517, 1, 1)
+    assert net.state_dict()["fc_layer.mlp_convs.0.weight"].shape == (256, 515, 1, 1)
+
+
+def test_train_mode_backward_runs():
+    """forward+backward through the modular path (autograd over the CUDA grad kernels)."""
+    net, _ = _net(False)
+    net.train()
+    d = synthetic.make_batch(2, 256, seed=5)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, 2, 128, device="cuda"))
+    loss = out[0].square().mean() + out[2].mean()
+    loss.backward()
+    g = net.pn_head.sa1.mlps[0][0].conv.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0

@@ -1,0 +1,147 @@
+"""GPU parity of the ten pointnet2 ops: sm_100a kernels (through the C ABI) vs the CPU oracle,
+vs the committed golden vectors and -- when oracle/_ref is present -- vs the reference's own
+kernels on the same device.  Indices and copies bit-exact; atomics-based grads to 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import pointnet2_oracle as P
+from ratrack_b200 import synthetic
+from ratrack_b200.lib import pointnet2_utils as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(B, N, seed=1234):
+    d = synthetic.make_batch(B, N, seed=seed)
+    return np.ascontiguousarray(d["pc1"].transpose(0, 2, 1))
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("B,N,S", [(1, 256, 512), (3, 1024, 512), (2, 322, 512), (2, 3000, 512), (2, 5, 9),
+                                   (1, 64, 64), (2, 100, 37), (1, 2049, 128), (1, 4097, 64), (150, 512, 512)])
+def test_fps_bit_exact(B, N, S):
+    xyz = _cloud(B, N, seed=N)
+    got = U.furthest_point_sample(_cu(xyz), S).cpu().numpy()
+    assert np.array_equal(got, P.furthest_point_sample(xyz, S))
+
+
+def test_fps_massive_ties_and_temp():
+    rng = np.random.default_rng(3)
+    for N in (256, 300, 1024, 700):
+        xyz = rng.integers(0, 3, size=(2, N, 3)).astype(np.float32)
+        got = U.furthest_point_sample(_cu(xyz), 64).cpu().numpy()
+        assert np.array_equal(got, P.furthest_point_sample(xyz, 64)), N
+
+
+def test_vod_frames_golden():
+    g = np.load(os.path.join(GOLDEN, "pointnet2_vod_frames.npz"))
+    for tag in sorted(k[4:] for k in g.files if k.startswith("xyz_")):
+        xyz = _cu(g[f"xyz_{tag}"][None])
+        fps = U.furthest_point_sample(xyz, 512)
+        assert np.array_equal(fps.cpu().numpy()[0], g[f"fps_{tag}"])
+        new_xyz = U.gather_operation(xyz.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+        for r, ns in ((2.0, 4), (4.0, 8), (16.0, 32)):
+            assert np.array_equal(U.ball_query(r, ns, xyz, new_xyz).cpu().numpy()[0], g[f"bq_{tag}_{int(r)}_{ns}"])
+        d, i3 = U.three_nn(xyz, new_xyz)
+        assert np.array_equal(i3.cpu().numpy()[0], g[f"nn_idx_{tag}"])
+        assert np.array_equal(d.cpu().numpy()[0], np.sqrt(g[f"nn_d2_{tag}"]))
+
+
+@pytest.mark.parametrize("N,S", [(1024, 512), (512, 512), (333, 77), (3000, 512), (2050, 100)])
+@pytest.mark.parametrize("r,ns", [(2.0, 4), (4.0, 8), (8.0, 16), (16.0, 32), (0.01, 8), (1000.0, 64)])
+def test_ball_query_bit_exact(N, S, r, ns):
+    xyz = _cloud(2, N, seed=N + 1)
+    new_xyz = np.ascontiguousarray(xyz[:, np.random.default_rng(0).permutation(N)[:S] if S <= N else np.arange(S) % N])
+    got = U.ball_query(r, ns, _cu(xyz), _cu(new_xyz)).cpu().numpy()
+    assert np.array_equal(got, P.ball_query(r, ns, xyz, new_xyz))
+
+
+@pytest.mark.parametrize("n,m", [(512, 512), (1024, 512), (300, 2), (77, 1), (3000, 2500)])
+def test_three_nn_bit_exact(n, m):
+    u, k = _cloud(2, n, seed=5), _cloud(2, m, seed=6)
+    d, i = U.three_nn(_cu(u), _cu(k))
+    od, oi = P.three_nn(u, k)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert np.array_equal(d.cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("k", [1, 3, 16, 17, 32, 64, 200])
+def test_knn_bit_exact(k):
+    u, kn = _cloud(2, 300, seed=7), _cloud(2, 2100, seed=8)
+    d, i = U.knn(k, _cu(u), _cu(kn))
+    od, oi = P.knn(k, u, kn)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+
+
+def test_knn_k_over_200_raises():
+    u = _cu(_cloud(1, 32))
+    with pytest.raises(RuntimeError):
+        U.knn(201, u, u)
+
+
+@pytest.mark.parametrize("C,N,S,ns", [(3, 1024, 512, 8), (514, 1024, 512, 8), (64, 512, 512, 32), (5, 100, 33, 3)])
+def test_group_and_gather_bit_exact_and_grads(C, N, S, ns):
+    rng = np.random.default_rng(C)
+    feats = rng.normal(size=(2, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, size=(2, S, ns)).astype(np.int32)
+    f = _cu(feats).requires_grad_(True)
+    out = U.grouping_operation(f, _cu(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), P.grouping_operation(feats, idx))
+    go = rng.normal(size=out.shape).astype(np.float32)
+    out.backward(_cu(go))
+    ref = P.grouping_operation_grad(go, idx, N)
+    assert np.allclose(f.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    # gather = group with nsample 1
+    f2 = _cu(feats).requires_grad_(True)
+    o2 = U.gather_operation(f2, _cu(idx[:, :, 0].copy()))
+    assert np.array_equal(o2.detach().cpu().numpy(), P.gather_operation(feats, idx[:, :, 0]))
+    g2 = rng.normal(size=o2.shape).astype(np.float32)
+    o2.backward(_cu(g2))
+    assert np.allclose(f2.grad.cpu().numpy(), P.gather_operation_grad(g2, idx[:, :, 0], N), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,m,n", [(64, 512, 512), (128, 512, 1024), (7, 33, 101)])
+def test_three_interpolate_bit_exact_and_grad(C, m, n):
+    rng = np.random.default_rng(n)
+    feats = rng.normal(size=(2, C, m)).astype(np.float32)
+    idx = rng.integers(0, m, size=(2, n, 3)).astype(np.int32)
+    w = rng.uniform(size=(2, n, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    f = _cu(feats).requires_grad_(True)
+    out = U.three_interpolate(f, _cu(idx), _cu(w))
+    assert np.array_equal(out.detach().cpu().numpy(), P.three_interpolate(feats, idx, w))
+    go = rng.normal(size=out.shape).astype(np.float32)
+    out.backward(_cu(go))
+    assert np.allclose(f.grad.cpu().numpy(), P.three_interpolate_grad(go, idx, w, m), rtol=1e-5, atol=1e-5)
+
+
+def test_reference_kernels_agree_with_oracle_and_product():
+    """The pin: the reference's own kernels (oracle/_ref, compiled from /root/reference/src/lib/src)
+    on this GPU == C oracle == product kernels, bit for bit."""
+    from oracle import gen_golden_ref_gpu, ref_gpu
+
+    ref = ref_gpu.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/pointnet2_cuda.so not built")
+    for (B, N, S) in gen_golden_ref_gpu.CASES:
+        r = gen_golden_ref_gpu.run_case(ref, B, N, S)
+        xyz = _cloud(B, N)
+        fps = P.furthest_point_sample(xyz, S)
+        assert np.array_equal(r["fps"], fps), (B, N)
+        assert np.array_equal(U.furthest_point_sample(_cu(xyz), S).cpu().numpy(), r["fps"])
+        new_xyz = np.ascontiguousarray(np.take_along_axis(xyz, fps[..., None].astype(np.int64), 1))
+        for rad, ns in ((2.0, 4), (4.0, 8), (8.0, 16), (16.0, 32)):
+            assert np.array_equal(r[f"bq_{int(rad)}_{ns}"], P.ball_query(rad, ns, xyz, new_xyz)), (N, rad)
+        d2, i3 = P.three_nn_raw(xyz, new_xyz)
+        assert np.array_equal(r["nn_idx"], i3) and np.array_equal(r["nn_d2"], d2)
+        kd, ki = P.knn_raw(16, new_xyz, xyz)
+        assert np.array_equal(r["knn_idx"], ki) and np.array_equal(r["knn_d2"], kd)
+        feats = torch.randn((B, 8, S), generator=torch.Generator().manual_seed(1234)).numpy()
+        assert np.array_equal(r["interp"], P.three_interpolate(feats, i3, r["interp_w"]))
