@@ -13,6 +13,11 @@ from ratrack_b200.model_utils import Track4DBackbone
 
 pytestmark = pytest.mark.gpu
 
+# fp32 everywhere: torch's default cudnn.allow_tf32=True silently runs the 1x1 convs of the modular path in
+# TF32 (~1e-3 relative); the reference never sets these flags (SURVEY.md hard part 3), parity needs them off.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 TOL = 1e-5   # of the tensor's scale: |d| <= TOL * max(1, max|ref|)   (DESIGN.md "Parity")
 
 
