@@ -83,6 +83,45 @@ int rt_three_interpolate(int b, int c, int m, int n, const float *points, const 
 int rt_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
                               float *grad_points, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 2 -- fused inference engine for Track4D.backbone (Seam C)
+ *
+ * replaces, in eval mode, the whole of Track4D.backbone (reference: src/models/track4d.py:67-106):
+ * feature_extraction_head (two PNHead passes, src/utils/model_utils/model_utils.py:393-424),
+ * FeatureCorrelator.forward (:193-250) and FlowDecoder.forward (:281-305).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rt_engine rt_engine;
+
+/* number of entries of the weight-pointer table rt_engine_create expects */
+int rt_engine_num_weights(void);
+
+/* `weights`: table of DEVICE pointers to fp32 tensors, BatchNorm already folded, in the order documented in
+ * ratrack_b200/engine.py (WEIGHT_ORDER) == struct EngineW of csrc/engine.cu.  The engine keeps the
+ * pointers (no copy): the caller owns the tensors and must keep them alive.  npoint = FPS sample count of
+ * all three SA levels (reference: configs.yaml:25 `npoints`). */
+int rt_engine_create(rt_engine **out, int npoint, const void *const *weights, int nweights);
+void rt_engine_destroy(rt_engine *e);
+
+/* bytes of scratch device memory rt_backbone_forward needs for a batch of b pairs of n points (< 0 on error) */
+long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n);
+
+/* optional: two cudaEvent_t recorded on the launch stream around the dominant kernel (the dense
+ * cost-volume MLP) of every forward; pass NULL, NULL to disable */
+int rt_engine_set_profile_events(rt_engine *e, void *start_event, void *stop_event);
+
+/* kernels launched by this engine since creation */
+long long rt_engine_launch_count(const rt_engine *e);
+
+/* pc1, pc2 (b,3,n); ft1, ft2 (b,2,n); h_in (5,b,128)  ->  flow (b,3,n), h_out (5,b,128), cls (b,n),
+ * cor (b,256,n), f1, f2 (b,256,n), prop (b,128,n): the 7-tuple of Track4D.backbone (track4d.py:86).
+ * knn12 / knn11 (b,n,16) int32, optional (NULL to skip): the cost volume's neighbour sets pc1->pc2, pc1->pc1
+ * (model_utils.py:216,239), exposed for tie-aware parity checks.  All device pointers; workspace must be
+ * 256-byte aligned.  Asynchronous on `stream`. */
+int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                        const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                        float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                        long long workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

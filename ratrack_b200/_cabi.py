@@ -24,6 +24,16 @@ SIGNATURES = {
     "rt_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
     "rt_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "rt_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "rt_engine_create": [ctypes.POINTER(ctypes.c_void_p), _I, ctypes.POINTER(ctypes.c_void_p), _I],
+    "rt_engine_set_profile_events": [_P, _P, _P],
+    "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
+}
+# entries whose return value is not an error code
+OTHER = {
+    "rt_engine_num_weights": ([], ctypes.c_int),
+    "rt_engine_destroy": ([_P], None),
+    "rt_engine_workspace_bytes": ([_P, _I, _I], ctypes.c_longlong),
+    "rt_engine_launch_count": ([_P], ctypes.c_longlong),
 }
 
 _lib = None
@@ -47,6 +57,10 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        for name, (args, res) in OTHER.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
         _lib = L
     return _lib
 

@@ -1,0 +1,453 @@
+// Fused inference engine for Track4D.backbone (reference: src/models/track4d.py:67-106 and
+// src/utils/model_utils/model_utils.py:166-424), eval mode: BatchNorm folded into the preceding 1x1
+// convolutions by the host side (ratrack_b200/engine.py), every stage a CUDA kernel of this library.
+//
+// What is different from the reference's dataflow (same results up to fp32 re-association):
+//   * geometry once: FPS / ball-query / three_nn / kNN depend only on xyz, so pc1's index structures are
+//     computed once and shared by pn_head(pc1) and the FlowDecoder's second PNHead (`mse`);
+//   * project-then-gather: the first 1x1 conv of every SA scale and of the cost volume is linear in the
+//     gathered features, W.[dxyz; f_j] = Wx.dxyz + Wf.f_j, so Wf.f is evaluated once per POINT and the
+//     grouped (B,C,S,ns) / (B,515,16,N) tensors of the reference are never built;
+//   * channels that are constant over a cloud (global max-pool features, the GRU output) enter the next
+//     layer as a per-cloud bias instead of being broadcast and concatenated.
+#include <new>
+#include <string.h>
+
+#include "../../include/ratrack_b200.h"
+#include "engine_kernels.cuh"
+
+int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
+                          float *xa, float *xb, cudaStream_t st);  // engine-internal, below
+
+namespace {
+
+struct SaScaleW { const float *wx, *b1, *w2, *b2, *w3, *b3; };
+struct HeadW {
+    const float *wf_ft, *wf_loc, *wf_glob, *wf_cor;
+    SaScaleW l1[2];
+    const float *lin1_w, *lin1_b;
+    const float *wf2;
+    SaScaleW l2[2];
+    const float *lin2_w, *lin2_b;
+    const float *wf3;
+    SaScaleW l3[2];
+    const float *lin3_w, *lin3_b;
+    const float *fp3_wi, *fp3_ws, *fp3_b, *fp2_wi, *fp2_ws, *fp2_b, *fp1_wi, *fp1_b;
+};
+struct WeightNetW { const float *wa, *ba, *wb, *bb, *wc, *bc; };
+struct CvW {
+    const float *w1_l1, *w1_g1, *w1_l2, *w1_g2, *w1_x, *b1, *w2, *b2, *w3, *b3;
+    WeightNetW wn1, wn2;
+};
+struct ClsW { const float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *lin_w, *lin_b; };
+struct FlowW { const float *w1_l, *w1_g, *b1, *w2, *b2, *w3, *b3, *w4; };
+struct GruW { const float *wih, *whh, *bih, *bhh; };
+struct EngineW {
+    HeadW pn, mse;
+    CvW cv;
+    ClsW cp;
+    FlowW fp;
+    GruW gru;
+};
+constexpr int kNumWeights = sizeof(EngineW) / sizeof(const float *);
+static_assert(sizeof(EngineW) == kNumWeights * sizeof(const float *), "EngineW must be a plain pointer table");
+static_assert(kNumWeights == 155, "weight table order is mirrored by ratrack_b200/engine.py");
+
+// PNHead geometry, hard-coded in the reference (utils/model_utils/model_utils.py:397-399)
+struct LevelCfg { float radius[2]; int ns[2]; int c1[2], c2[2], c3[2]; int lin_out; };
+const LevelCfg kLevels[3] = {
+    {{2.f, 4.f}, {4, 8}, {16, 16}, {16, 16}, {32, 32}, 32},
+    {{4.f, 8.f}, {8, 16}, {32, 32}, {32, 64}, {0, 0}, 64},
+    {{8.f, 16.f}, {16, 32}, {64, 64}, {64, 64}, {0, 0}, 64},
+};
+constexpr int kKnn = 16;
+
+// bump allocator over the caller's workspace; run with base == nullptr to size it
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <typename T>
+    T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Ws {
+    float *xyz0, *ft0, *xyz[3], *temp;
+    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11;
+    float *nn_w[3];
+    float *proj, *xa, *xb, *pooled, *l1, *l2, *l3, *l2p, *l1p, *interp, *feat, *prop;
+    float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h;
+};
+
+void carve(Carver &c, Ws &w, int b, int n, int S) {
+    const size_t B2 = 2 * (size_t)b;
+    w.xyz0 = c.take<float>(B2 * n * 3);
+    w.ft0 = c.take<float>(B2 * n * 2);
+    for (int l = 0; l < 3; ++l) w.xyz[l] = c.take<float>(B2 * S * 3);
+    w.temp = c.take<float>(B2 * (size_t)max(n, S));
+    for (int l = 0; l < 3; ++l) w.fps[l] = c.take<int>(B2 * S);
+    for (int l = 0; l < 3; ++l)
+        for (int s = 0; s < 2; ++s) w.bq[l][s] = c.take<int>(B2 * S * kLevels[l].ns[s]);
+    // three_nn of FP3 (xyz2 <- xyz3), FP2 (xyz1 <- xyz2), FP1 (xyz0 <- xyz1)
+    const size_t nn_rows[3] = {B2 * S, B2 * S, B2 * (size_t)n};
+    for (int l = 0; l < 3; ++l) {
+        w.nn_idx[l] = c.take<int>(nn_rows[l] * 3);
+        w.nn_w[l] = c.take<float>(nn_rows[l] * 3);
+    }
+    w.knn12 = c.take<int>((size_t)b * n * kKnn);
+    w.knn11 = c.take<int>((size_t)b * n * kKnn);
+    const size_t head_rows = B2 * S * 32 * 64;  // widest SA activation: ns=32 x 64 channels
+    const size_t cv_rows = (size_t)b * n * kKnn * 256;
+    const size_t xbuf = head_rows > cv_rows ? head_rows : cv_rows;
+    w.proj = c.take<float>(B2 * (size_t)max(n * 32, S * 128));
+    w.xa = c.take<float>(xbuf);
+    w.xb = c.take<float>(xbuf);
+    w.pooled = c.take<float>(B2 * S * 128);
+    w.l1 = c.take<float>(B2 * S * 32);
+    w.l2 = c.take<float>(B2 * S * 64);
+    w.l3 = c.take<float>(B2 * S * 64);
+    w.l2p = c.take<float>(B2 * S * 128);
+    w.l1p = c.take<float>(B2 * S * 128);
+    w.interp = c.take<float>(B2 * (size_t)max(n, S) * 128);
+    w.feat = c.take<float>(B2 * n * 128);
+    w.prop = c.take<float>((size_t)b * n * 128);
+    w.gmax = c.take<float>(B2 * 128);
+    w.gprop = c.take<float>((size_t)b * 128);
+    w.cb_a = c.take<float>((size_t)b * 256);
+    w.cb_b = c.take<float>((size_t)b * 256);
+    w.p1 = c.take<float>((size_t)b * n * 256);
+    w.p2 = c.take<float>((size_t)b * n * 256);
+    w.cost1 = c.take<float>((size_t)b * n * 256);
+    w.cor = c.take<float>((size_t)b * n * 256);
+    w.h1 = c.take<float>((size_t)b * n * 128);
+    w.h2 = c.take<float>((size_t)b * n * 64);
+    w.h3 = c.take<float>((size_t)b * n * 32);
+    w.flow_rows = c.take<float>((size_t)b * n * 3);
+    w.gru_h = c.take<float>((size_t)5 * b * 128);
+}
+
+#define RT_TRY(expr)              \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != RT_OK) return rc_; \
+    } while (0)
+
+RtRowGemm gemm1(long long rows, int nout, const float *x, int ldx, int k, const float *w, const float *bias, int act, float *y,
+                int ldy) {
+    RtRowGemm g{};
+    g.rows = (int)rows;
+    g.nout = nout;
+    g.nseg = 1;
+    g.seg[0] = RtSeg{x, ldx, k, w, k};
+    g.bias = bias;
+    g.rows_per_cloud = 1;
+    g.act = act;
+    g.y = y;
+    g.ldy = ldy;
+    return g;
+}
+
+}  // namespace
+
+struct rt_engine {
+    EngineW w;
+    int npoint;
+    cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
+    long long launches = 0;
+};
+
+namespace {
+
+// geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN
+int run_geometry(rt_engine *e, Ws &w, int b, int n, cudaStream_t st) {
+    const int B2 = 2 * b, S = e->npoint;
+    const float *lvl_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
+    const int lvl_n[3] = {n, S, S};
+    for (int l = 0; l < 3; ++l) {
+        RT_TRY(rt_launch_fill(w.temp, (long long)B2 * lvl_n[l], 1e10f, st));
+        RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp, w.fps[l], st));
+        RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], st));
+        for (int s = 0; s < 2; ++s) {
+            const int ns = kLevels[l].ns[s];
+            cudaMemsetAsync(w.bq[l][s], 0, sizeof(int) * (size_t)B2 * S * ns, st);
+            RT_TRY(rt_ball_query(B2, lvl_n[l], S, kLevels[l].radius[s], ns, w.xyz[l], lvl_in[l], w.bq[l][s], st));
+        }
+        e->launches += 7;
+    }
+    // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
+    const float *unk[3] = {w.xyz[1], w.xyz[0], w.xyz0};
+    const float *kn[3] = {w.xyz[2], w.xyz[1], w.xyz[0]};
+    const int un[3] = {S, S, n};
+    for (int l = 0; l < 3; ++l) {
+        RT_TRY(rt_three_nn(B2, un[l], S, unk[l], kn[l], w.nn_w[l], w.nn_idx[l], st));
+        RT_TRY(rt_launch_nn_weights((long long)B2 * un[l], w.nn_w[l], st));
+        e->launches += 2;
+    }
+    const float *pc1 = w.xyz0, *pc2 = w.xyz0 + (size_t)b * n * 3;
+    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, st));
+    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, st));
+    e->launches += 2;
+    return RT_OK;
+}
+
+// One PNHead (utils/model_utils/model_utils.py:409-424) over the first `clouds` clouds of the geometry.
+// Level-1 input features arrive as row segments; `cloud_bias1` carries cloud-constant channels.
+int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSeg *segs, int nseg, const float *cloud_bias1,
+             float *out, cudaStream_t st) {
+    const int S = e->npoint;
+    const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
+    const int lvl_n[3] = {n, S, S};
+    float *lvl_out[3] = {w.l1, w.l2, w.l3};
+    const float *lvl_feat_in[3] = {nullptr, w.l1, w.l2};
+    const int lvl_cin[3] = {0, 32, 64};
+    const float *wf[3] = {nullptr, hw.wf2, hw.wf3};
+    const SaScaleW *sw[3] = {hw.l1, hw.l2, hw.l3};
+    const float *lin_w[3] = {hw.lin1_w, hw.lin2_w, hw.lin3_w};
+    const float *lin_b[3] = {hw.lin1_b, hw.lin2_b, hw.lin3_b};
+    for (int l = 0; l < 3; ++l) {
+        const LevelCfg &cfg = kLevels[l];
+        const int c1tot = cfg.c1[0] + cfg.c1[1];
+        // projection of every input point's features through the feature columns of both scales' first conv
+        RtRowGemm pg{};
+        pg.rows = clouds * lvl_n[l];
+        pg.nout = c1tot;
+        if (l == 0) {
+            pg.nseg = nseg;
+            for (int i = 0; i < nseg; ++i) pg.seg[i] = segs[i];
+            pg.cloud_bias = cloud_bias1;
+            pg.rows_per_cloud = n;
+        } else {
+            pg.nseg = 1;
+            pg.seg[0] = RtSeg{lvl_feat_in[l], lvl_cin[l], lvl_cin[l], wf[l], lvl_cin[l]};
+            pg.rows_per_cloud = 1;
+        }
+        pg.act = RT_ACT_NONE;
+        pg.y = w.proj;
+        pg.ldy = c1tot;
+        RT_TRY(rt_launch_rowgemm(pg, st));
+        e->launches += 1;
+        const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
+        int coff = 0;
+        for (int s = 0; s < 2; ++s) {
+            const int ns = cfg.ns[s];
+            const long long rows = (long long)clouds * S * ns;
+            RtGatherCombine gc{};
+            gc.clouds = clouds; gc.npts = S; gc.ns = ns; gc.c = cfg.c1[s];
+            gc.y = w.proj; gc.ldy = c1tot; gc.yoff = s ? cfg.c1[0] : 0; gc.n_in = lvl_n[l];
+            gc.idx = w.bq[l][s]; gc.xyz_in = lvl_xyz_in[l]; gc.xyz_c = w.xyz[l];
+            gc.wx = sw[l][s].wx; gc.bias = sw[l][s].b1; gc.q = nullptr; gc.act = RT_ACT_RELU; gc.out = w.xa;
+            RT_TRY(rt_launch_gather_combine(gc, st));
+            RT_TRY(rt_launch_rowgemm(gemm1(rows, cfg.c2[s], w.xa, cfg.c1[s], cfg.c1[s], sw[l][s].w2, sw[l][s].b2, RT_ACT_RELU, w.xb, cfg.c2[s]), st));
+            const float *last = w.xb;
+            int clast = cfg.c2[s];
+            e->launches += 2;
+            if (cfg.c3[s]) {
+                RT_TRY(rt_launch_rowgemm(gemm1(rows, cfg.c3[s], w.xb, cfg.c2[s], cfg.c2[s], sw[l][s].w3, sw[l][s].b3, RT_ACT_RELU, w.xa, cfg.c3[s]), st));
+                last = w.xa;
+                clast = cfg.c3[s];
+                e->launches += 1;
+            }
+            RT_TRY(rt_launch_maxpool_rows(clouds * S, ns, clast, last, w.pooled, pooled_c, coff, st));
+            e->launches += 1;
+            coff += clast;
+        }
+        RT_TRY(rt_launch_rowgemm(gemm1((long long)clouds * S, cfg.lin_out, w.pooled, pooled_c, pooled_c, lin_w[l], lin_b[l], RT_ACT_NONE, lvl_out[l], cfg.lin_out), st));
+        e->launches += 1;
+    }
+    // feature propagation (lib/pointnet2_modules.py:129-158): interpolate, concat skip, 1-layer SharedMLP
+    {   // FP3: l2 <- l3
+        RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
+        RtRowGemm g{};
+        g.rows = clouds * S; g.nout = 128; g.nseg = 2;
+        g.seg[0] = RtSeg{w.interp, 64, 64, hw.fp3_wi, 64};
+        g.seg[1] = RtSeg{w.l2, 64, 64, hw.fp3_ws, 64};
+        g.bias = hw.fp3_b; g.rows_per_cloud = 1; g.act = RT_ACT_RELU; g.y = w.l2p; g.ldy = 128;
+        RT_TRY(rt_launch_rowgemm(g, st));
+    }
+    {   // FP2: l1 <- l2'
+        RT_TRY(rt_launch_interp3(clouds, S, S, 128, w.l2p, 128, w.nn_idx[1], w.nn_w[1], w.interp, 128, st));
+        RtRowGemm g{};
+        g.rows = clouds * S; g.nout = 128; g.nseg = 2;
+        g.seg[0] = RtSeg{w.interp, 128, 128, hw.fp2_wi, 128};
+        g.seg[1] = RtSeg{w.l1, 32, 32, hw.fp2_ws, 32};
+        g.bias = hw.fp2_b; g.rows_per_cloud = 1; g.act = RT_ACT_RELU; g.y = w.l1p; g.ldy = 128;
+        RT_TRY(rt_launch_rowgemm(g, st));
+    }
+    {   // FP1: l0 <- l1' (no skip features)
+        RT_TRY(rt_launch_interp3(clouds, n, S, 128, w.l1p, 128, w.nn_idx[2], w.nn_w[2], w.interp, 128, st));
+        RT_TRY(rt_launch_rowgemm(gemm1((long long)clouds * n, 128, w.interp, 128, 128, hw.fp1_wi, hw.fp1_b, RT_ACT_RELU, out, 128), st));
+    }
+    e->launches += 6;
+    return RT_OK;
+}
+
+}  // namespace
+
+// v0 of the dense cost-volume MLP (two 256x256 layers with LeakyReLU over b*n*16 rows): two row GEMMs.
+int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
+                          float *xa, float *xb, cudaStream_t st) {
+    RT_TRY(rt_launch_rowgemm(gemm1(rows, 256, x1, 256, 256, w2, b2, RT_ACT_LEAKY01, xb, 256), st));
+    RT_TRY(rt_launch_rowgemm(gemm1(rows, 256, xb, 256, 256, w3, b3, RT_ACT_LEAKY01, xa, 256), st));
+    return RT_OK;
+}
+
+RT_API int rt_engine_num_weights(void) { return kNumWeights; }
+
+RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weights, int nweights) {
+    RT_REQUIRE(out && weights, "engine_create: null argument");
+    RT_REQUIRE(nweights == kNumWeights, "engine_create: expected %d weight pointers, got %d", kNumWeights, nweights);
+    RT_REQUIRE(npoint >= 1, "engine_create: npoint=%d", npoint);
+    rt_engine *e = new (std::nothrow) rt_engine();
+    RT_REQUIRE(e, "engine_create: out of host memory");
+    memcpy(&e->w, weights, sizeof(EngineW));
+    e->npoint = npoint;
+    // pointers that may legitimately be null: pn_head has only the `ft` feature segment; levels 2-3 have no third conv
+    const float *const *tab = reinterpret_cast<const float *const *>(&e->w);
+    const int head = sizeof(HeadW) / sizeof(const float *);
+    for (int i = 0; i < kNumWeights; ++i) {
+        if (tab[i]) continue;
+        const int in_head = i < 2 * head ? i % head : -1;
+        const bool opt = (i < head && in_head >= 1 && in_head <= 3) ||              // pn.wf_loc/glob/cor
+                         (in_head >= 0 && (in_head == 23 || in_head == 24 || in_head == 29 || in_head == 30 ||  // l2 w3/b3
+                                           in_head == 38 || in_head == 39 || in_head == 44 || in_head == 45));  // l3 w3/b3
+        if (!opt) {
+            delete e;
+            rt_set_error("engine_create: weight pointer %d is null", i);
+            return RT_ERR_INVALID;
+        }
+    }
+    *out = e;
+    return RT_OK;
+}
+
+RT_API void rt_engine_destroy(rt_engine *e) { delete e; }
+
+RT_API long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n) {
+    if (!e || b < 1 || n < 1) return -1;
+    Carver c(nullptr);
+    Ws w;
+    carve(c, w, b, n, e->npoint);
+    return (long long)c.off + 256;
+}
+
+RT_API int rt_engine_set_profile_events(rt_engine *e, void *start, void *stop) {
+    RT_REQUIRE(e, "engine_set_profile_events: null engine");
+    e->prof_start = (cudaEvent_t)start;
+    e->prof_stop = (cudaEvent_t)stop;
+    return RT_OK;
+}
+
+RT_API long long rt_engine_launch_count(const rt_engine *e) { return e ? e->launches : -1; }
+
+RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                               const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                               float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                               long long workspace_bytes, void *stream) {
+    RT_REQUIRE(e && pc1 && pc2 && ft1 && ft2 && h_in && flow && h_out && cls && cor && f1 && f2 && prop && workspace,
+               "backbone_forward: null argument");
+    RT_REQUIRE(b >= 1 && n >= 1, "backbone_forward: b=%d n=%d", b, n);
+    RT_REQUIRE(2 * b <= 65535, "backbone_forward: batch > 32767");
+    RT_REQUIRE(workspace_bytes >= rt_engine_workspace_bytes(e, b, n), "backbone_forward: workspace too small");
+    RT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "backbone_forward: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver c(workspace);
+    Ws w;
+    carve(c, w, b, n, e->npoint);
+    const int B2 = 2 * b;
+    const size_t half3 = (size_t)b * n * 3, half2 = (size_t)b * n * 2, half128 = (size_t)b * n * 128;
+
+    // inputs (B,3,N)/(B,2,N) channel-major -> row-major, pc1 clouds first then pc2
+    RT_TRY(rt_launch_cm_to_rows(b, 3, n, pc1, w.xyz0, 3, 0, st));
+    RT_TRY(rt_launch_cm_to_rows(b, 3, n, pc2, w.xyz0 + half3, 3, 0, st));
+    RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft1, w.ft0, 2, 0, st));
+    RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft2, w.ft0 + half2, 2, 0, st));
+    e->launches += 4;
+    RT_TRY(run_geometry(e, w, b, n, st));
+
+    // feature_extraction_head: pn_head over both clouds of every pair at once (track4d.py:102-106)
+    RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
+    RT_TRY(run_head(e, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+    RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
+    // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95)
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat, 128, 0, f1, 256, 0, st));
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat + half128, 128, 0, f2, 256, 0, st));
+    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax, f1, 256, 128, st));
+    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax + (size_t)b * 128, f2, 256, 128, st));
+    e->launches += 5;
+
+    // FeatureCorrelator (model_utils.py:193-250)
+    const CvW &cv = e->w.cv;
+    const float *x1 = w.xyz0, *x2 = w.xyz0 + half3;
+    RT_TRY(rt_launch_cloud_matvec(b, 256, 128, cv.w1_g1, 128, w.gmax, 128, cv.b1, w.cb_a, st));
+    RT_TRY(rt_launch_cloud_matvec(b, 256, 128, cv.w1_g2, 128, w.gmax + (size_t)b * 128, 128, nullptr, w.cb_b, st));
+    {
+        RtRowGemm g = gemm1((long long)b * n, 256, w.feat, 128, 128, cv.w1_l1, nullptr, RT_ACT_NONE, w.p1, 256);
+        g.cloud_bias = w.cb_a; g.rows_per_cloud = n;
+        RT_TRY(rt_launch_rowgemm(g, st));
+        g = gemm1((long long)b * n, 256, w.feat + half128, 128, 128, cv.w1_l2, nullptr, RT_ACT_NONE, w.p2, 256);
+        g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
+        RT_TRY(rt_launch_rowgemm(g, st));
+    }
+    {
+        RtGatherCombine gc{};
+        gc.clouds = b; gc.npts = n; gc.ns = kKnn; gc.c = 256;
+        gc.y = w.p2; gc.ldy = 256; gc.yoff = 0; gc.n_in = n; gc.idx = w.knn12; gc.xyz_in = x2; gc.xyz_c = x1;
+        gc.wx = cv.w1_x; gc.bias = nullptr; gc.q = w.p1; gc.act = RT_ACT_LEAKY01; gc.out = w.xa;
+        RT_TRY(rt_launch_gather_combine(gc, st));
+    }
+    if (e->prof_start) cudaEventRecord(e->prof_start, st);
+    RT_TRY(rt_launch_costvol_mlp(b * n * kKnn, w.xa, cv.w2, cv.b2, cv.w3, cv.b3, w.xa, w.xb, st));
+    if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
+    {
+        RtWeightedSum ws{};
+        ws.clouds = b; ws.npts = n; ws.ns = kKnn; ws.c = 256; ws.n_in = n; ws.gather_v = 0;
+        ws.idx = w.knn12; ws.xyz_in = x2; ws.xyz_c = x1;
+        ws.wa = cv.wn1.wa; ws.ba = cv.wn1.ba; ws.wb = cv.wn1.wb; ws.bb = cv.wn1.bb; ws.wc = cv.wn1.wc; ws.bc = cv.wn1.bc;
+        ws.v = w.xa; ws.out = w.cost1;
+        RT_TRY(rt_launch_weighted_sum(ws, st));
+        ws.gather_v = 1; ws.idx = w.knn11; ws.xyz_in = x1;
+        ws.wa = cv.wn2.wa; ws.ba = cv.wn2.ba; ws.wb = cv.wn2.wb; ws.bb = cv.wn2.bb; ws.wc = cv.wn2.wc; ws.bc = cv.wn2.bc;
+        ws.v = w.cost1; ws.out = w.cor;
+        RT_TRY(rt_launch_weighted_sum(ws, st));
+    }
+    RT_TRY(rt_launch_rows_to_cm(b, 256, n, w.cor, 256, 0, cor, 256, 0, st));
+    e->launches += 10;
+
+    // FlowDecoder (model_utils.py:281-305): cls head on the cost volume
+    const ClsW &cp = e->w.cp;
+    const long long pts = (long long)b * n;
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 128, w.cor, 256, 256, cp.w1, cp.b1, RT_ACT_RELU, w.h1, 128), st));
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, cp.w2, cp.b2, RT_ACT_RELU, w.h2, 64), st));
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, cp.w3, cp.b3, RT_ACT_RELU, w.h3, 32), st));
+    RT_TRY(rt_launch_cls_tail(pts, w.h3, cp.w4, cp.lin_w, cp.lin_b, cls, st));
+    // second PNHead over embeddings = cat(feature1, pc1_features, cor_features) on pc1's geometry
+    const HeadW &mse = e->w.mse;
+    RT_TRY(rt_launch_cloud_matvec(b, 32, 128, mse.wf_glob, 128, w.gmax, 128, nullptr, w.cb_a, st));
+    RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},
+                     RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
+    RT_TRY(run_head(e, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, st));
+    RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
+    RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, st));
+    // FlowPredictor on cat(prop_features, broadcast GRU output)
+    const FlowW &fp = e->w.fp;
+    RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + (size_t)4 * b * 128, 128, fp.b1, w.cb_b, st));
+    {
+        RtRowGemm g = gemm1(pts, 128, w.prop, 128, 128, fp.w1_l, nullptr, RT_ACT_RELU, w.h1, 128);
+        g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
+        RT_TRY(rt_launch_rowgemm(g, st));
+    }
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, fp.w2, fp.b2, RT_ACT_RELU, w.h2, 64), st));
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, fp.w3, fp.b3, RT_ACT_RELU, w.h3, 32), st));
+    RT_TRY(rt_launch_rowgemm(gemm1(pts, 3, w.h3, 32, 32, fp.w4, nullptr, RT_ACT_NONE, w.flow_rows, 3), st));
+    RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
+    e->launches += 14;
+    if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
+    if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
+    return rt_check_launch("backbone_forward");
+}

@@ -1,0 +1,518 @@
+// Building-block kernels of the fused Track4D.backbone engine (sm_100a).  See engine_kernels.cuh for the
+// contracts and engine.cu for how they are chained.  Everything here is fp32 SIMT; the dense 256-wide
+// cost-volume MLP has its own tensor-core kernel (costvol_tc.cu).
+#include <math.h>
+
+#include "engine_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == RT_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == RT_ACT_LEAKY01) return v > 0.0f ? v : 0.1f * v;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row GEMM: CTA tile 64 rows x 64 outputs, 256 threads, 4x4 register tile, K staged 16 at a time.
+constexpr int RG_T = 64, RG_K = 16, RG_LD = RG_T + 4;
+
+__global__ void __launch_bounds__(256) rowgemm_kernel(RtRowGemm a) {
+    __shared__ __align__(16) float sX[RG_K][RG_LD];
+    __shared__ __align__(16) float sW[RG_K][RG_LD];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long row0 = (long long)blockIdx.x * RG_T;
+    const int out0 = blockIdx.y * RG_T;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int s = 0; s < a.nseg; ++s) {
+        const RtSeg sg = a.seg[s];
+        for (int k0 = 0; k0 < sg.k; k0 += RG_K) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + 256 * i;
+                const int r = e >> 4, kk = e & 15;
+                const long long gr = row0 + r;
+                const int gk = k0 + kk;
+                float xv = 0.0f, wv = 0.0f;
+                if (gk < sg.k) {
+                    if (gr < a.rows) xv = __ldg(sg.x + gr * sg.ldx + gk);
+                    if (out0 + r < a.nout) wv = __ldg(sg.w + (long long)(out0 + r) * sg.ldw + gk);
+                }
+                sX[kk][r] = xv;
+                sW[kk][r] = wv;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < RG_K; ++kk) {
+                const float4 xa = *reinterpret_cast<const float4 *>(&sX[kk][4 * ty]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&sW[kk][4 * tx]);
+                const float xr[4] = {xa.x, xa.y, xa.z, xa.w};
+                const float wr[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long gr = row0 + 4 * ty + i;
+        if (gr >= a.rows) continue;
+        const float *cb = a.cloud_bias ? a.cloud_bias + (gr / a.rows_per_cloud) * a.nout : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = out0 + 4 * tx + j;
+            if (o >= a.nout) continue;
+            float v = acc[i][j];
+            if (a.bias) v += __ldg(a.bias + o);
+            if (cb) v += __ldg(cb + o);
+            a.y[gr * a.ldy + o] = apply_act(v, a.act);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_combine_kernel(RtGatherCombine a) {
+    const long long total = (long long)a.clouds * a.npts * a.ns * a.c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(e % a.c);
+        const long long row = e / a.c;              // (cloud, p, s)
+        const long long cp = row / a.ns;            // (cloud, p)
+        const int cloud = (int)(cp / a.npts);
+        const int j = __ldg(a.idx + row);
+        const float *pi = a.xyz_in + ((long long)cloud * a.n_in + j) * 3;
+        const float *pc = a.xyz_c + cp * 3;
+        const float dx = __ldg(pi + 0) - __ldg(pc + 0), dy = __ldg(pi + 1) - __ldg(pc + 1), dz = __ldg(pi + 2) - __ldg(pc + 2);
+        float v = __ldg(a.y + ((long long)cloud * a.n_in + j) * a.ldy + a.yoff + ch);
+        const float *w = a.wx + ch * 3;
+        v += fmaf(__ldg(w + 2), dz, fmaf(__ldg(w + 1), dy, __ldg(w + 0) * dx));
+        if (a.bias) v += __ldg(a.bias + ch);
+        if (a.q) v += __ldg(a.q + cp * a.c + ch);
+        a.out[e] = apply_act(v, a.act);
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_rows_kernel(long long groups, int ns, int c, const float *__restrict__ x,
+                                                           float *__restrict__ pooled, int ldp, int coff) {
+    const long long total = groups * c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(e % c);
+        const long long g = e / c;
+        const float *src = x + g * ns * c + ch;
+        float m = __ldg(src);
+        for (int s = 1; s < ns; ++s) m = fmaxf(m, __ldg(src + (long long)s * c));
+        pooled[g * ldp + coff + ch] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WeightNet-weighted neighbour sum.  CTA = 8 points, 256 threads.  Phase 1: one thread per (point,
+// neighbour) evaluates the 3->8->8 trunk into shared memory; phase 2: one thread per channel.
+constexpr int WS_PTS = 8;
+
+__global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
+    extern __shared__ float s_h2[];  // WS_PTS * ns * 8
+    __shared__ int s_idx[WS_PTS * 32];
+    const long long cp0 = (long long)blockIdx.x * WS_PTS;
+    const long long ncp = (long long)a.clouds * a.npts;
+    const int pairs = WS_PTS * a.ns;
+    for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+        const long long cp = cp0 + t / a.ns;
+        float h2[8];
+        int j = 0;
+        if (cp < ncp) {
+            const int cloud = (int)(cp / a.npts);
+            j = __ldg(a.idx + cp * a.ns + (t % a.ns));
+            const float *pi = a.xyz_in + ((long long)cloud * a.n_in + j) * 3;
+            const float *pc = a.xyz_c + cp * 3;
+            const float d[3] = {__ldg(pi + 0) - __ldg(pc + 0), __ldg(pi + 1) - __ldg(pc + 1), __ldg(pi + 2) - __ldg(pc + 2)};
+            float h1[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float v = __ldg(a.ba + o);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v = fmaf(__ldg(a.wa + o * 3 + k), d[k], v);
+                h1[o] = fmaxf(v, 0.0f);
+            }
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float v = __ldg(a.bb + o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v = fmaf(__ldg(a.wb + o * 8 + k), h1[k], v);
+                h2[o] = fmaxf(v, 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) h2[o] = 0.0f;
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) s_h2[t * 8 + o] = h2[o];
+        s_idx[t] = j;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < a.c; ch += blockDim.x) {
+        float wc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wc[k] = __ldg(a.wc + ch * 8 + k);
+        const float bc = __ldg(a.bc + ch);
+        for (int p = 0; p < WS_PTS; ++p) {
+            const long long cp = cp0 + p;
+            if (cp >= ncp) break;
+            const int cloud = (int)(cp / a.npts);
+            float acc = 0.0f;
+            for (int s = 0; s < a.ns; ++s) {
+                const float *h2 = s_h2 + (p * a.ns + s) * 8;
+                float w = bc;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
+                w = fmaxf(w, 0.0f);
+                const float v = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
+                                           : __ldg(a.v + (cp * a.ns + s) * a.c + ch);
+                acc = fmaf(w, v, acc);
+            }
+            a.out[cp * a.c + ch] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expanded-form kNN: one thread per query, search cloud staged as (x, y, z, |p|^2) in shared memory.
+constexpr int KX_THREADS = 128, KX_TILE = 1024;
+
+template <int KMAX>
+__global__ void __launch_bounds__(KX_THREADS) knn_expanded_kernel(int n, int m, int k, const float *__restrict__ q,
+                                                                  const float *__restrict__ s, int *__restrict__ idx) {
+    __shared__ float4 s_pts[KX_TILE];
+    const int cloud = blockIdx.y;
+    const int i = blockIdx.x * KX_THREADS + threadIdx.x;
+    const bool ok = i < n;
+    const float *qp = q + ((long long)cloud * n + (ok ? i : 0)) * 3;
+    const float qx = __ldg(qp + 0), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    // torch.sum(src ** 2, -1) on the permuted view: (x*x + y*y) + z*z, every op rounded (no contraction)
+    const float q2 = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+    const float inf = __int_as_float(0x7f800000);
+    float best[KMAX];
+    int besti[KMAX];
+#pragma unroll
+    for (int l = 0; l < KMAX; ++l) {
+        best[l] = inf;
+        besti[l] = 0;
+    }
+    float worst = inf;
+    for (int base = 0; base < m; base += KX_TILE) {
+        const int tn = min(KX_TILE, m - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < tn; t += KX_THREADS) {
+            const float *p = s + ((long long)cloud * m + base + t) * 3;
+            const float x = __ldg(p + 0), y = __ldg(p + 1), z = __ldg(p + 2);
+            s_pts[t] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        }
+        __syncthreads();
+        for (int t = 0; t < tn; ++t) {
+            const float4 p = s_pts[t];
+            // matmul with K = 3 (cuBLAS and MKL agree): fma(z,z', fma(y,y', x*x'))
+            const float dot = __fmaf_rn(qz, p.z, __fmaf_rn(qy, p.y, __fmul_rn(qx, p.x)));
+            float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), q2), p.w);
+            d = fmaxf(d, 0.0f);
+            if (d < worst) {
+                int pos = k - 1;
+#pragma unroll
+                for (int l = KMAX - 1; l > 0; --l) {
+                    if (l < k && best[l - 1] > d) {
+                        best[l] = best[l - 1];
+                        besti[l] = besti[l - 1];
+                        pos = l - 1;
+                    }
+                }
+#pragma unroll
+                for (int l = 0; l < KMAX; ++l)
+                    if (l == pos) {
+                        best[l] = d;
+                        besti[l] = base + t;
+                    }
+#pragma unroll
+                for (int l = 0; l < KMAX; ++l)
+                    if (l == k - 1) worst = best[l];
+            }
+        }
+    }
+    if (ok) {
+        int *o = idx + ((long long)cloud * n + i) * k;
+#pragma unroll
+        for (int l = 0; l < KMAX; ++l)
+            if (l < k) o[l] = besti[l];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nn_weights_kernel(long long rows, float *__restrict__ d) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float *p = d + r * 3;
+    // dist = sqrt(d2); recip = 1/(dist + 1e-8); w = recip / (r0 + r1 + r2)   (lib/pointnet2_modules.py:141-144)
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(p[0]), 1e-8f));
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(p[1]), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(p[2]), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    p[0] = __fdiv_rn(r0, norm);
+    p[1] = __fdiv_rn(r1, norm);
+    p[2] = __fdiv_rn(r2, norm);
+}
+
+__global__ void __launch_bounds__(256) interp3_kernel(int clouds, int n, int m, int c, const float *__restrict__ f, int ldf,
+                                                      const int *__restrict__ idx, const float *__restrict__ w,
+                                                      float *__restrict__ out, int ldo) {
+    const long long total = (long long)clouds * n * c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(e % c);
+        const long long row = e / c;
+        const int cloud = (int)(row / n);
+        const int *ix = idx + row * 3;
+        const float *ww = w + row * 3;
+        const float *base = f + (long long)cloud * m * ldf + ch;
+        float t = __fmul_rn(__ldg(ww + 1), __ldg(base + (long long)__ldg(ix + 1) * ldf));
+        t = __fmaf_rn(__ldg(ww + 0), __ldg(base + (long long)__ldg(ix + 0) * ldf), t);
+        out[row * ldo + ch] = __fmaf_rn(__ldg(ww + 2), __ldg(base + (long long)__ldg(ix + 2) * ldf), t);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_rows3_kernel(int clouds, int npts_out, int n_in, int c,
+                                                           const float *__restrict__ src, const int *__restrict__ idx,
+                                                           float *__restrict__ dst) {
+    const long long total = (long long)clouds * npts_out * c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(e % c);
+        const long long row = e / c;
+        const int cloud = (int)(row / npts_out);
+        dst[e] = __ldg(src + ((long long)cloud * n_in + __ldg(idx + row)) * c + ch);
+    }
+}
+
+__global__ void __launch_bounds__(256) cloud_max_kernel(int npts, int c, const float *__restrict__ f, int ldf, float *__restrict__ g) {
+    // grid (cloud, channel-block of 32); 256 threads = 8 point-lanes x 32 channels
+    __shared__ float s[8][33];
+    const int cloud = blockIdx.x, ch = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+    float m = -__int_as_float(0x7f800000);
+    if (ch < c)
+        for (int p = pl; p < npts; p += 8) m = fmaxf(m, __ldg(f + ((long long)cloud * npts + p) * ldf + ch));
+    s[pl][threadIdx.x & 31] = m;
+    __syncthreads();
+    if (pl == 0 && ch < c) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, s[i][threadIdx.x & 31]);
+        g[(long long)cloud * c + ch] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) cloud_matvec_kernel(int nout, int k, const float *__restrict__ w, int ldw,
+                                                           const float *__restrict__ g, int ldg, const float *__restrict__ bias,
+                                                           float *__restrict__ cb) {
+    // grid (cloud); one warp per output, lanes stride over k
+    const int cloud = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = warp; o < nout; o += 8) {
+        float acc = 0.0f;
+        for (int kk = lane; kk < k; kk += 32) acc = fmaf(__ldg(w + (long long)o * ldw + kk), __ldg(g + (long long)cloud * ldg + kk), acc);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) cb[(long long)cloud * nout + o] = acc + (bias ? __ldg(bias + o) : 0.0f);
+    }
+}
+
+// (b, c, n) <-> (b*n, ld) transposes through a 32x33 tile
+__global__ void __launch_bounds__(256) cm_to_rows_kernel(int c, int n, const float *__restrict__ src, float *__restrict__ dst, int ldd, int coff) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < c && n0 + tx < n) t[i][tx] = __ldg(src + ((long long)b * c + c0 + i) * n + n0 + tx);
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (n0 + i < n && c0 + tx < c) dst[((long long)b * n + n0 + i) * ldd + coff + c0 + tx] = t[tx][i];
+}
+__global__ void __launch_bounds__(256) rows_to_cm_kernel(int c, int n, const float *__restrict__ src, int lds, int soff,
+                                                         float *__restrict__ dst, int dst_c, int dst_coff) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (n0 + i < n && c0 + tx < c) t[i][tx] = __ldg(src + ((long long)b * n + n0 + i) * lds + soff + c0 + tx);
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < c && n0 + tx < n) dst[((long long)b * dst_c + dst_coff + c0 + i) * n + n0 + tx] = t[tx][i];
+}
+__global__ void __launch_bounds__(256) broadcast_cm_kernel(int c, int n, const float *__restrict__ g, float *__restrict__ dst,
+                                                           int dst_c, int dst_coff) {
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const float v = __ldg(g + (long long)b * c + ch);
+    float *row = dst + ((long long)b * dst_c + dst_coff + ch) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = v;
+}
+
+// 5-layer GRU, sequence length 1 (torch.nn.GRU equations): CTA per batch element, 384 threads (one per gate row)
+__global__ void __launch_bounds__(384) gru_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
+                                                  const float *__restrict__ wih, const float *__restrict__ whh,
+                                                  const float *__restrict__ bih, const float *__restrict__ bhh,
+                                                  float *__restrict__ h_out) {
+    __shared__ float s_in[128], s_h[128], s_gi[384], s_gh[384];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 128) s_in[t] = x[(long long)b * 128 + t];
+    for (int l = 0; l < 5; ++l) {
+        if (t < 128) s_h[t] = h_in[((long long)l * bsz + b) * 128 + t];
+        __syncthreads();
+        const float *wi = wih + ((long long)l * 384 + t) * 128;
+        const float *wh = whh + ((long long)l * 384 + t) * 128;
+        float gi = 0.0f, gh = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < 128; ++k) {
+            gi = fmaf(__ldg(wi + k), s_in[k], gi);
+            gh = fmaf(__ldg(wh + k), s_h[k], gh);
+        }
+        s_gi[t] = gi + __ldg(bih + l * 384 + t);
+        s_gh[t] = gh + __ldg(bhh + l * 384 + t);
+        __syncthreads();
+        if (t < 128) {
+            const float r = 1.0f / (1.0f + expf(-(s_gi[t] + s_gh[t])));
+            const float z = 1.0f / (1.0f + expf(-(s_gi[128 + t] + s_gh[128 + t])));
+            const float nn = tanhf(s_gi[256 + t] + r * s_gh[256 + t]);
+            const float hn = (1.0f - z) * nn + z * s_h[t];
+            h_out[((long long)l * bsz + b) * 128 + t] = hn;
+            s_in[t] = hn;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) cls_tail_kernel(long long rows, const float *__restrict__ h3, const float *__restrict__ w4,
+                                                       const float *__restrict__ lin_w, const float *__restrict__ lin_b,
+                                                       float *__restrict__ cls) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *h = h3 + r * 32;
+    float o[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float v = __ldg(h + k);
+        o[0] = fmaf(__ldg(w4 + k), v, o[0]);
+        o[1] = fmaf(__ldg(w4 + 32 + k), v, o[1]);
+        o[2] = fmaf(__ldg(w4 + 64 + k), v, o[2]);
+    }
+    const float y = fmaf(__ldg(lin_w + 2), o[2], fmaf(__ldg(lin_w + 1), o[1], __ldg(lin_w + 0) * o[0])) + __ldg(lin_b);
+    cls[r] = 1.0f / (1.0f + expf(-y));
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float *p, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+inline int grid_for(long long total, int threads, int cap = 148 * 16) {
+    long long g = (total + threads - 1) / threads;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int rt_launch_rowgemm(const RtRowGemm &a, cudaStream_t st) {
+    if (a.rows <= 0 || a.nout <= 0) return RT_OK;
+    dim3 grid(rt_divup(a.rows, RG_T), rt_divup(a.nout, RG_T));
+    rowgemm_kernel<<<grid, 256, 0, st>>>(a);
+    return rt_check_launch("rowgemm_kernel");
+}
+int rt_launch_gather_combine(const RtGatherCombine &a, cudaStream_t st) {
+    const long long total = (long long)a.clouds * a.npts * a.ns * a.c;
+    if (total <= 0) return RT_OK;
+    gather_combine_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(a);
+    return rt_check_launch("gather_combine_kernel");
+}
+int rt_launch_maxpool_rows(int groups, int ns, int c, const float *x, float *pooled, int ldp, int coff, cudaStream_t st) {
+    if (groups <= 0) return RT_OK;
+    maxpool_rows_kernel<<<grid_for((long long)groups * c, 256), 256, 0, st>>>(groups, ns, c, x, pooled, ldp, coff);
+    return rt_check_launch("maxpool_rows_kernel");
+}
+int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st) {
+    const long long ncp = (long long)a.clouds * a.npts;
+    if (ncp <= 0) return RT_OK;
+    RT_REQUIRE(a.ns <= 32, "weighted_sum: nsample > 32");
+    weighted_sum_kernel<<<rt_divup(ncp, WS_PTS), 256, WS_PTS * a.ns * 8 * sizeof(float), st>>>(a);
+    return rt_check_launch("weighted_sum_kernel");
+}
+int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st) {
+    if (clouds <= 0 || n <= 0) return RT_OK;
+    RT_REQUIRE(k >= 1 && k <= 32 && m >= 1, "knn_expanded: k=%d outside [1,32] or empty search cloud", k);
+    dim3 grid(rt_divup(n, KX_THREADS), clouds);
+    if (k <= 16) knn_expanded_kernel<16><<<grid, KX_THREADS, 0, st>>>(n, m, k, q, s, idx);
+    else knn_expanded_kernel<32><<<grid, KX_THREADS, 0, st>>>(n, m, k, q, s, idx);
+    return rt_check_launch("knn_expanded_kernel");
+}
+int rt_launch_nn_weights(long long rows, float *d, cudaStream_t st) {
+    if (rows <= 0) return RT_OK;
+    nn_weights_kernel<<<rt_divup(rows, 256), 256, 0, st>>>(rows, d);
+    return rt_check_launch("nn_weights_kernel");
+}
+int rt_launch_interp3(int clouds, int n, int m, int c, const float *f, int ldf, const int *idx, const float *w, float *out,
+                      int ldo, cudaStream_t st) {
+    const long long total = (long long)clouds * n * c;
+    if (total <= 0) return RT_OK;
+    interp3_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(clouds, n, m, c, f, ldf, idx, w, out, ldo);
+    return rt_check_launch("interp3_kernel");
+}
+int rt_launch_gather_rows(int clouds, int npts_out, int n_in, int c, const float *src, const int *idx, float *dst, cudaStream_t st) {
+    const long long total = (long long)clouds * npts_out * c;
+    if (total <= 0) return RT_OK;
+    gather_rows3_kernel<<<grid_for(total, 256), 256, 0, st>>>(clouds, npts_out, n_in, c, src, idx, dst);
+    return rt_check_launch("gather_rows3_kernel");
+}
+int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, float *g, cudaStream_t st) {
+    if (clouds <= 0) return RT_OK;
+    dim3 grid(clouds, rt_divup(c, 32));
+    cloud_max_kernel<<<grid, 256, 0, st>>>(npts, c, f, ldf, g);
+    return rt_check_launch("cloud_max_kernel");
+}
+int rt_launch_cloud_matvec(int clouds, int nout, int k, const float *w, int ldw, const float *g, int ldg, const float *bias,
+                           float *cb, cudaStream_t st) {
+    if (clouds <= 0) return RT_OK;
+    cloud_matvec_kernel<<<clouds, 256, 0, st>>>(nout, k, w, ldw, g, ldg, bias, cb);
+    return rt_check_launch("cloud_matvec_kernel");
+}
+int rt_launch_cm_to_rows(int b, int c, int n, const float *src, float *dst, int ldd, int coff, cudaStream_t st) {
+    if (b <= 0) return RT_OK;
+    dim3 grid(rt_divup(n, 32), rt_divup(c, 32), b);
+    cm_to_rows_kernel<<<grid, 256, 0, st>>>(c, n, src, dst, ldd, coff);
+    return rt_check_launch("cm_to_rows_kernel");
+}
+int rt_launch_rows_to_cm(int b, int c, int n, const float *src, int lds, int soff, float *dst, int dst_c, int dst_coff,
+                         cudaStream_t st) {
+    if (b <= 0) return RT_OK;
+    dim3 grid(rt_divup(n, 32), rt_divup(c, 32), b);
+    rows_to_cm_kernel<<<grid, 256, 0, st>>>(c, n, src, lds, soff, dst, dst_c, dst_coff);
+    return rt_check_launch("rows_to_cm_kernel");
+}
+int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int dst_c, int dst_coff, cudaStream_t st) {
+    if (b <= 0) return RT_OK;
+    dim3 grid(rt_divup(n, 256), c, b);
+    broadcast_cm_kernel<<<grid, 256, 0, st>>>(c, n, g, dst, dst_c, dst_coff);
+    return rt_check_launch("broadcast_cm_kernel");
+}
+int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
+                  const float *bhh, float *h_out, cudaStream_t st) {
+    if (b <= 0) return RT_OK;
+    gru_kernel<<<b, 384, 0, st>>>(b, x, h_in, wih, whh, bih, bhh, h_out);
+    return rt_check_launch("gru_kernel");
+}
+int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b, float *cls,
+                       cudaStream_t st) {
+    if (rows <= 0) return RT_OK;
+    cls_tail_kernel<<<rt_divup(rows, 256), 256, 0, st>>>(rows, h3, w4, lin_w, lin_b, cls);
+    return rt_check_launch("cls_tail_kernel");
+}
+int rt_launch_fill(float *p, long long n, float v, cudaStream_t st) {
+    if (n <= 0) return RT_OK;
+    fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);
+    return rt_check_launch("fill_kernel");
+}

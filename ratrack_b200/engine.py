@@ -1,0 +1,200 @@
+"""Host side of the fused inference engine (include/ratrack_b200.h, section 2).
+
+`FusedBackbone(module)` reads the parameters of a `Track4DBackbone` (state_dict surface of the reference's
+Track4D: pn_head.*, fc_layer.*, fd_layer.*), folds every eval-mode BatchNorm into the 1x1 convolution in
+front of it, splits first-layer weights into their xyz / feature / cloud-constant column blocks, and hands
+the resulting device tensors to the C-ABI engine as one pointer table.  Calling it runs
+`rt_backbone_forward` on torch's current stream and returns the 7-tuple of `Track4D.backbone`
+(reference: src/models/track4d.py:67-86).  There is no fallback: a missing library or a failed launch raises.
+
+Folding (reference layer -> engine tensor):
+  SharedMLP layer  conv(no bias) -> BN(eval, eps 1e-5) -> ReLU   (src/lib/pytorch_utils.py:5-32)
+      W' = W * gamma / sqrt(var + eps),  b' = beta - mean * gamma / sqrt(var + eps)
+  first SA conv (C1 x (3 + Cin)):  WX = W'[:, :3]  (applied to xyz_j - centre),  WF = W'[:, 3:]  (applied per point)
+  cost-volume conv 0 (256 x 515):  columns [f1 local 128 | f1 global 128 | f2 local 128 | f2 global 128 | dxyz 3]
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+
+def _fold(conv_w, bn):
+    """conv weight (Cout,Cin,1,1) + BatchNorm2d -> (W' (Cout,Cin), b' (Cout,)) in float64 then fp32."""
+    w = conv_w.detach().double().flatten(1)
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    return (w * scale[:, None]).float(), (bn.bias.detach().double() - bn.running_mean.detach().double() * scale).float()
+
+
+def _shared_mlp_layers(mlp):
+    """SharedMLP -> list of folded (W', b')."""
+    out = []
+    for layer in mlp:
+        out.append(_fold(layer.conv.weight, layer.bn.bn))
+    return out
+
+
+def _head_weights(head, first_feature_split):
+    """Weight list of one PNHead in the order of struct HeadW (csrc/engine.cu)."""
+    ws = []
+    for lvl, sa in enumerate((head.sa1, head.sa2, head.sa3)):
+        scales = [_shared_mlp_layers(m) for m in sa.mlps]
+        wf = torch.cat([s[0][0][:, 3:] for s in scales], dim=0)  # feature columns of both scales' first conv
+        if lvl == 0:
+            cols = 0
+            for width in first_feature_split:
+                ws.append(wf[:, cols:cols + width] if width else None)
+                cols += width
+            assert cols == wf.shape[1], (cols, wf.shape)
+        else:
+            ws.append(wf)
+        for s in scales:
+            ws += [s[0][0][:, :3], s[0][1], s[1][0], s[1][1]]
+            ws += [s[2][0], s[2][1]] if len(s) > 2 else [None, None]
+        lin = (head.linear1, head.linear2, head.linear3)[lvl]
+        ws += [lin.weight.detach(), lin.bias.detach()]
+    w3, b3 = _shared_mlp_layers(head.fp3.mlp)[0]
+    w2, b2 = _shared_mlp_layers(head.fp2.mlp)[0]
+    w1, b1 = _shared_mlp_layers(head.fp1.mlp)[0]
+    ws += [w3[:, :64], w3[:, 64:], b3, w2[:, :128], w2[:, 128:], b2, w1, b1]
+    assert len(ws) == 56, len(ws)
+    return ws
+
+
+def _weightnet(wn):
+    c = wn.mlp_convs
+    assert not wn.bn and len(c) == 3
+    out = []
+    for conv in c:
+        out += [conv.weight.detach().flatten(1), conv.bias.detach()]
+    return out
+
+
+def _predictor(p):
+    """FlowPredictor / ClsPredictor trunk: three folded conv+BN layers and the final bias-free conv."""
+    out = []
+    for block in p.sf_mlp:
+        out.append(_fold(block[0].weight, block[1]))
+    return out, p.conv2.weight.detach().flatten(1)
+
+
+def build_weight_table(net):
+    """-> list of 155 fp32 tensors / None, ordered as struct EngineW."""
+    fc, fd = net.fc_layer, net.fd_layer
+    assert not fc.bn and fc.nsample == 16, "engine is built for the reference configuration (bn=False, nsample=16)"
+    ws = _head_weights(net.pn_head, (2, 0, 0, 0))
+    ws += _head_weights(fd.mse, (2, 128, 128, 256))
+    w1 = fc.mlp_convs[0].weight.detach().flatten(1)
+    assert w1.shape == (256, 515)
+    ws += [w1[:, 0:128], w1[:, 128:256], w1[:, 256:384], w1[:, 384:512], w1[:, 512:515], fc.mlp_convs[0].bias.detach(),
+           fc.mlp_convs[1].weight.detach().flatten(1), fc.mlp_convs[1].bias.detach(),
+           fc.mlp_convs[2].weight.detach().flatten(1), fc.mlp_convs[2].bias.detach()]
+    ws += _weightnet(fc.weightnet1) + _weightnet(fc.weightnet2)
+    (c1, c2, c3), c4 = _predictor(fd.cp)
+    ws += [c1[0], c1[1], c2[0], c2[1], c3[0], c3[1], c4, fd.cp.linear.weight.detach(), fd.cp.linear.bias.detach()]
+    (f1, f2, f3), f4 = _predictor(fd.fp)
+    ws += [f1[0][:, :128], f1[0][:, 128:], f1[1], f2[0], f2[1], f3[0], f3[1], f4]
+    g = fd.torchGRU
+    assert g.num_layers == 5 and g.input_size == 128 and g.hidden_size == 128
+    ws += [torch.stack([getattr(g, f"weight_ih_l{l}").detach() for l in range(5)]),
+           torch.stack([getattr(g, f"weight_hh_l{l}").detach() for l in range(5)]),
+           torch.stack([getattr(g, f"bias_ih_l{l}").detach() for l in range(5)]),
+           torch.stack([getattr(g, f"bias_hh_l{l}").detach() for l in range(5)])]
+    return ws
+
+
+class FusedBackbone:
+    def __init__(self, net):
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise _cabi.RatrackError("FusedBackbone needs the module on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.npoint = int(net.npoints_cfg)
+        table = build_weight_table(net)
+        lib = _cabi.lib()
+        assert len(table) == lib.rt_engine_num_weights(), (len(table), lib.rt_engine_num_weights())
+        # keep the folded tensors alive: the engine stores raw pointers
+        self._weights = [None if t is None else t.to(device=dev, dtype=torch.float32).contiguous().clone() for t in table]
+        ptrs = (ctypes.c_void_p * len(table))(*[None if t is None else t.data_ptr() for t in self._weights])
+        self._handle = ctypes.c_void_p()
+        _cabi.call("rt_engine_create", ctypes.byref(self._handle), self.npoint, ptrs, len(table))
+        self._workspace = None
+        self._ws_key = None
+        self.last_knn = None
+        self._prof = None
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                _cabi.lib().rt_engine_destroy(h)
+            except Exception:
+                pass
+
+    def launch_count(self):
+        return int(_cabi.lib().rt_engine_launch_count(self._handle))
+
+    def set_profile_events(self, start, stop):
+        """torch.cuda.Event pair (enable_timing=True) recorded around the dominant kernel of every forward."""
+        if start is None:
+            _cabi.call("rt_engine_set_profile_events", self._handle, None, None)
+            self._prof = None
+            return
+        # events must exist on the device before their handle can be taken
+        start.record()
+        stop.record()
+        self._prof = (start, stop)
+        _cabi.call("rt_engine_set_profile_events", self._handle, start.cuda_event, stop.cuda_event)
+
+    def _ws(self, b, n):
+        if self._ws_key != (b, n):
+            nbytes = int(_cabi.lib().rt_engine_workspace_bytes(self._handle, b, n))
+            if nbytes < 0:
+                raise _cabi.RatrackError("rt_engine_workspace_bytes failed")
+            self._workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._ws_key = (b, n)
+        base = self._workspace.data_ptr()
+        return (base + 255) // 256 * 256, self._workspace.numel() - 256
+
+    def __call__(self, pc1, pc2, feature1, feature2, h=None, want_knn=False):
+        b, _, n = pc1.shape
+        f32 = dict(dtype=torch.float32, device=self.device)
+        args = [t.to(**f32).contiguous() for t in (pc1, pc2, feature1, feature2)]
+        if h is None:
+            h = torch.zeros(5, b, 128, **f32)
+        h = h.to(**f32).contiguous()
+        flow = torch.empty(b, 3, n, **f32)
+        h_out = torch.empty(5, b, 128, **f32)
+        cls = torch.empty(b, n, **f32)
+        cor = torch.empty(b, 256, n, **f32)
+        f1 = torch.empty(b, 256, n, **f32)
+        f2 = torch.empty(b, 256, n, **f32)
+        prop = torch.empty(b, 128, n, **f32)
+        knn = (torch.empty(b, n, 16, dtype=torch.int32, device=self.device),
+               torch.empty(b, n, 16, dtype=torch.int32, device=self.device)) if want_knn else (None, None)
+        ws_ptr, ws_bytes = self._ws(b, n)
+        with torch.cuda.device(self.device):
+            _cabi.call("rt_backbone_forward", self._handle, b, n, args[0].data_ptr(), args[1].data_ptr(),
+                       args[2].data_ptr(), args[3].data_ptr(), h.data_ptr(), flow.data_ptr(), h_out.data_ptr(),
+                       cls.data_ptr(), cor.data_ptr(), f1.data_ptr(), f2.data_ptr(), prop.data_ptr(),
+                       knn[0].data_ptr() if want_knn else None, knn[1].data_ptr() if want_knn else None,
+                       ws_ptr, ws_bytes, torch.cuda.current_stream(self.device).cuda_stream)
+        if want_knn:
+            self.last_knn = knn
+        return flow, h_out, cls, cor, f1, f2, prop
+
+
+def roofline_of_dominant(batch, points, dom_ms, peaks):
+    """Roofline entry of bench.py for the dominant kernel: the dense cost-volume MLP
+    (two 256 -> 256 layers over batch*points*16 rows; DESIGN.md "Kernels and rooflines").
+    Algorithmic work = the fp32-accurate useful FLOPs, 2 layers x 2*rows*256*256; the denominator is the
+    measured dense bf16 tensor throughput (sustained figure: the kernel is timed inside a long step)."""
+    rows = batch * points * 16
+    flops = 2 * 2.0 * rows * 256 * 256
+    avg_ms = sum(dom_ms) / max(1, len(dom_ms))
+    ach = flops / (avg_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_sustained") or peaks["bf16"]
+    return {"kernel": "cost-volume MLP (2 x [rows x 256 x 256], LeakyReLU)", "bound": "tensor", "achieved": ach,
+            "peak": peak, "peak_source": peaks["src"] + " dense bf16 (sustained)", "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None, "avg_launch_ms": avg_ms, "flops_per_launch": flops}

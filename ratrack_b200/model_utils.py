@@ -254,7 +254,8 @@ class Track4DBackbone(nn.Module):
         fc_inch = 2 * 128
         self.fc_layer = FeatureCorrelator(16, in_channel=fc_inch * 2 + 3, mlp=[fc_inch, fc_inch, fc_inch])
         self.fd_layer = FlowDecoder(fc_inch=fc_inch, args=args)
-        self.use_fused = False  # eval + no_grad -> fused engine (enabled once ratrack_b200/engine.py is built)
+        self.use_fused = True   # eval + no_grad -> fused engine (ratrack_b200/engine.py)
+        self.capture_knn = False  # fused path: also return the cost volume's neighbour sets (tie-aware parity checks)
         self._engine = None
 
     # -- reference-shaped methods ------------------------------------------------------------
@@ -286,7 +287,7 @@ class Track4DBackbone(nn.Module):
             from .engine import FusedBackbone
             if self._engine is None:
                 self._engine = FusedBackbone(self)
-            return self._engine(pc1, pc2, feature1, feature2, h)
+            return self._engine(pc1, pc2, feature1, feature2, h, want_knn=self.capture_knn)
         return self.backbone_modular(pc1, pc2, feature1, feature2, h)
 
     def forward(self, pc1, pc2, feature1, feature2, h=None):
@@ -322,6 +323,8 @@ class Track4DBackbone(nn.Module):
     def cost_volume_neighbours(self, pc1, pc2):
         """The two 16-NN index sets the cost volume uses (pc1->pc2, pc1->pc1), (B,N,16) each --
         exposed so parity checks can be tie-aware (reference: model_utils.py:216,239)."""
+        if self.use_fused and not self.training and self._engine is not None and self._engine.last_knn is not None:
+            return tuple(k.long() for k in self._engine.last_knn)   # what the fused forward actually used
         a, b = pc1.permute(0, 2, 1), pc2.permute(0, 2, 1)
         return knn_point(self.fc_layer.nsample, b, a), knn_point(self.fc_layer.nsample, a, a)
 

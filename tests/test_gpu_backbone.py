@@ -30,6 +30,7 @@ def _net(fused):
     sd = synthetic.make_state_dict(net, seed=1234)
     net.load_state_dict(sd, strict=False)
     net.use_fused = fused
+    net.capture_knn = True
     return net.cuda().eval(), sd
 
 

@@ -236,6 +236,7 @@ int main() {
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CK(cudaFuncSetAttribute(throughput_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     for (int mode = 0; mode < 4; ++mode) {
+        if (mode == 1) continue;  // swapped LBO/SBO: faults (illegal address) on hardware -- convention settled by mode 0
         CK(cudaMemset(dD, 0xff, M * N * 4)); CK(cudaMemset(dD2, 0xff, M * N * 4)); CK(cudaMemset(dErr, 0, 4));
         probe_kernel<<<1, 192, 49152>>>(mode, dA, dB, dD, dD2, dErr);
         cudaError_t e = cudaDeviceSynchronize();
