@@ -109,6 +109,14 @@ long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n);
  * cost-volume MLP) of every forward; pass NULL, NULL to disable */
 int rt_engine_set_profile_events(rt_engine *e, void *start_event, void *stop_event);
 
+/* flags: bit 0 (default on) = cost volume on the tcgen05 tensor-core kernel; off = the SIMT fp32 chain with the
+ * same dataflow (kept for A/B parity checks of the fp16x3 split arithmetic) */
+int rt_engine_set_flags(rt_engine *e, int flags);
+
+/* blocking: device status word of the last rt_backbone_forward.  0 = ok; bit 1 = an activation of the cost-volume
+ * MLP left the fp16 hi/lo range (|x| >= 65000): that call's outputs are invalid */
+int rt_engine_last_status(rt_engine *e, int *status_out);
+
 /* kernels launched by this engine since creation */
 long long rt_engine_launch_count(const rt_engine *e);
 

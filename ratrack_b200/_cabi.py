@@ -26,6 +26,8 @@ SIGNATURES = {
     "rt_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "rt_engine_create": [ctypes.POINTER(ctypes.c_void_p), _I, ctypes.POINTER(ctypes.c_void_p), _I],
     "rt_engine_set_profile_events": [_P, _P, _P],
+    "rt_engine_set_flags": [_P, _I],
+    "rt_engine_last_status": [_P, ctypes.POINTER(ctypes.c_int)],
     "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
 }
 # entries whose return value is not an error code

@@ -18,6 +18,11 @@
 
 int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
                           float *xa, float *xb, cudaStream_t st);  // engine-internal, below
+// costvol_tc.cu: gather + 3-layer MLP + WeightNet-weighted neighbour sum on tcgen05
+int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2, const float *xyz1, const float *xyz2,
+                         const int *knn, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
+                         const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
+                         float *out, int *status, cudaStream_t st);
 
 namespace {
 
@@ -38,6 +43,7 @@ struct WeightNetW { const float *wa, *ba, *wb, *bb, *wc, *bc; };
 struct CvW {
     const float *w1_l1, *w1_g1, *w1_l2, *w1_g2, *w1_x, *b1, *w2, *b2, *w3, *b3;
     WeightNetW wn1, wn2;
+    const float *w23_pack, *wc1_pack;  // fp16 hi/lo planes in UMMA core-matrix layout (costvol_tc.cu), made by engine.py
 };
 struct ClsW { const float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *lin_w, *lin_b; };
 struct FlowW { const float *w1_l, *w1_g, *b1, *w2, *b2, *w3, *b3, *w4; };
@@ -51,7 +57,7 @@ struct EngineW {
 };
 constexpr int kNumWeights = sizeof(EngineW) / sizeof(const float *);
 static_assert(sizeof(EngineW) == kNumWeights * sizeof(const float *), "EngineW must be a plain pointer table");
-static_assert(kNumWeights == 155, "weight table order is mirrored by ratrack_b200/engine.py");
+static_assert(kNumWeights == 157, "weight table order is mirrored by ratrack_b200/engine.py");
 
 // PNHead geometry, hard-coded in the reference (utils/model_utils/model_utils.py:397-399)
 struct LevelCfg { float radius[2]; int ns[2]; int c1[2], c2[2], c3[2]; int lin_out; };
@@ -82,6 +88,7 @@ struct Ws {
     float *nn_w[3];
     float *proj, *xa, *xb, *pooled, *l1, *l2, *l3, *l2p, *l1p, *interp, *feat, *prop;
     float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h;
+    int *status;
 };
 
 void carve(Carver &c, Ws &w, int b, int n, int S) {
@@ -129,6 +136,7 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     w.h3 = c.take<float>((size_t)b * n * 32);
     w.flow_rows = c.take<float>((size_t)b * n * 3);
     w.gru_h = c.take<float>((size_t)5 * b * 128);
+    w.status = c.take<int>(64);
 }
 
 #define RT_TRY(expr)              \
@@ -159,6 +167,8 @@ struct rt_engine {
     int npoint;
     cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
     long long launches = 0;
+    int flags = 1;                 // bit 0: tensor-core cost volume (costvol_tc.cu); 0 = SIMT reference chain
+    const int *last_status = nullptr;
 };
 
 namespace {
@@ -344,6 +354,26 @@ RT_API int rt_engine_set_profile_events(rt_engine *e, void *start, void *stop) {
 
 RT_API long long rt_engine_launch_count(const rt_engine *e) { return e ? e->launches : -1; }
 
+RT_API int rt_engine_set_flags(rt_engine *e, int flags) {
+    RT_REQUIRE(e, "engine_set_flags: null engine");
+    e->flags = flags;
+    return RT_OK;
+}
+
+// blocking read of the device status word of the last forward: 0 = ok, bit 1 = an activation left the fp16x2
+// range of the tensor-core cost volume (|x| >= 65000) -- results of that call must not be used
+RT_API int rt_engine_last_status(rt_engine *e, int *status_out) {
+    RT_REQUIRE(e && status_out, "engine_last_status: null argument");
+    *status_out = 0;
+    if (!e->last_status) return RT_OK;
+    cudaError_t err = cudaMemcpy(status_out, e->last_status, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) {
+        rt_set_error("engine_last_status: %s", cudaGetErrorString(err));
+        return (int)err;
+    }
+    return RT_OK;
+}
+
 RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
                                const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
                                float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
@@ -393,23 +423,30 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
     }
-    {
+    cudaMemsetAsync(w.status, 0, 64 * sizeof(int), st);
+    e->last_status = w.status;
+    if (e->flags & 1) {
+        if (e->prof_start) cudaEventRecord(e->prof_start, st);
+        RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
+                                    cv.wn1.bc, cv.wn1.wa, cv.wn1.ba, cv.wn1.wb, cv.wn1.bb, w.cost1, w.status, st));
+        if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
+    } else {
         RtGatherCombine gc{};
         gc.clouds = b; gc.npts = n; gc.ns = kKnn; gc.c = 256;
         gc.y = w.p2; gc.ldy = 256; gc.yoff = 0; gc.n_in = n; gc.idx = w.knn12; gc.xyz_in = x2; gc.xyz_c = x1;
         gc.wx = cv.w1_x; gc.bias = nullptr; gc.q = w.p1; gc.act = RT_ACT_LEAKY01; gc.out = w.xa;
         RT_TRY(rt_launch_gather_combine(gc, st));
+        if (e->prof_start) cudaEventRecord(e->prof_start, st);
+        RT_TRY(rt_launch_costvol_mlp(b * n * kKnn, w.xa, cv.w2, cv.b2, cv.w3, cv.b3, w.xa, w.xb, st));
+        if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
     }
-    if (e->prof_start) cudaEventRecord(e->prof_start, st);
-    RT_TRY(rt_launch_costvol_mlp(b * n * kKnn, w.xa, cv.w2, cv.b2, cv.w3, cv.b3, w.xa, w.xb, st));
-    if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
     {
         RtWeightedSum ws{};
         ws.clouds = b; ws.npts = n; ws.ns = kKnn; ws.c = 256; ws.n_in = n; ws.gather_v = 0;
         ws.idx = w.knn12; ws.xyz_in = x2; ws.xyz_c = x1;
         ws.wa = cv.wn1.wa; ws.ba = cv.wn1.ba; ws.wb = cv.wn1.wb; ws.bb = cv.wn1.bb; ws.wc = cv.wn1.wc; ws.bc = cv.wn1.bc;
         ws.v = w.xa; ws.out = w.cost1;
-        RT_TRY(rt_launch_weighted_sum(ws, st));
+        if (!(e->flags & 1)) RT_TRY(rt_launch_weighted_sum(ws, st));
         ws.gather_v = 1; ws.idx = w.knn11; ws.xyz_in = x1;
         ws.wa = cv.wn2.wa; ws.ba = cv.wn2.ba; ws.wb = cv.wn2.wb; ws.bb = cv.wn2.bb; ws.wc = cv.wn2.wc; ws.bc = cv.wn2.bc;
         ws.v = w.cost1; ws.out = w.cor;

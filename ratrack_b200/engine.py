@@ -79,8 +79,37 @@ def _predictor(p):
     return out, p.conv2.weight.detach().flatten(1)
 
 
+W_SCALE = 1024.0  # costvol_tc.cu: weights enter the tensor core as 2^10 * W (keeps the fp16 `lo` plane normal)
+
+
+def _umma_planes(w, k_chunk):
+    """(N, K) fp32 -> fp16 hi/lo planes in the K-major core-matrix layout of tcgen05 shared-memory operands:
+    [chunk = K / k_chunk][plane hi, lo][kc = k_chunk / 8][row group = N / 8][8 rows][8 halfs]."""
+    n, k = w.shape
+    assert n % 8 == 0 and k % k_chunk == 0 and k_chunk % 8 == 0
+    w = w.float() * W_SCALE
+    hi = w.half()
+    lo = (w - hi.float()).half()
+
+    def lay(x):
+        return x.reshape(n // 8, 8, k // k_chunk, k_chunk // 8, 8).permute(2, 3, 0, 1, 4)
+
+    return torch.stack([lay(hi), lay(lo)], dim=1).contiguous()
+
+
+def pack_costvol_weights(w2, w3):
+    """conv 256->256 weights of cost-volume layers 2 and 3 -> one fp16 tensor streamed chunk by chunk (K = 32)."""
+    return torch.cat([_umma_planes(w2, 32), _umma_planes(w3, 32)], dim=0)
+
+
+def pack_weightnet_last(wc):
+    """WeightNet last conv (256 x 8) -> K padded to 16, planes [hi, lo][kc 2][32][8][8]."""
+    wc16 = torch.cat([wc.float(), torch.zeros(wc.shape[0], 8, dtype=torch.float32, device=wc.device)], dim=1)
+    return _umma_planes(wc16, 16)[0]
+
+
 def build_weight_table(net):
-    """-> list of 155 fp32 tensors / None, ordered as struct EngineW."""
+    """-> list of 157 tensors / None, ordered as struct EngineW (fp32, except the two fp16 packs of CvW)."""
     fc, fd = net.fc_layer, net.fd_layer
     assert not fc.bn and fc.nsample == 16, "engine is built for the reference configuration (bn=False, nsample=16)"
     ws = _head_weights(net.pn_head, (2, 0, 0, 0))
@@ -91,6 +120,8 @@ def build_weight_table(net):
            fc.mlp_convs[1].weight.detach().flatten(1), fc.mlp_convs[1].bias.detach(),
            fc.mlp_convs[2].weight.detach().flatten(1), fc.mlp_convs[2].bias.detach()]
     ws += _weightnet(fc.weightnet1) + _weightnet(fc.weightnet2)
+    ws += [pack_costvol_weights(fc.mlp_convs[1].weight.detach().flatten(1), fc.mlp_convs[2].weight.detach().flatten(1)),
+           pack_weightnet_last(fc.weightnet1.mlp_convs[2].weight.detach().flatten(1))]
     (c1, c2, c3), c4 = _predictor(fd.cp)
     ws += [c1[0], c1[1], c2[0], c2[1], c3[0], c3[1], c4, fd.cp.linear.weight.detach(), fd.cp.linear.bias.detach()]
     (f1, f2, f3), f4 = _predictor(fd.fp)
@@ -115,7 +146,9 @@ class FusedBackbone:
         lib = _cabi.lib()
         assert len(table) == lib.rt_engine_num_weights(), (len(table), lib.rt_engine_num_weights())
         # keep the folded tensors alive: the engine stores raw pointers
-        self._weights = [None if t is None else t.to(device=dev, dtype=torch.float32).contiguous().clone() for t in table]
+        self._weights = [None if t is None else
+                         t.to(device=dev, dtype=torch.float16 if t.dtype == torch.float16 else torch.float32).contiguous().clone()
+                         for t in table]
         ptrs = (ctypes.c_void_p * len(table))(*[None if t is None else t.data_ptr() for t in self._weights])
         self._handle = ctypes.c_void_p()
         _cabi.call("rt_engine_create", ctypes.byref(self._handle), self.npoint, ptrs, len(table))
@@ -131,6 +164,17 @@ class FusedBackbone:
                 _cabi.lib().rt_engine_destroy(h)
             except Exception:
                 pass
+
+    def set_tensor_core_costvol(self, on: bool):
+        """A/B switch: tcgen05 cost-volume kernel (default) vs the SIMT fp32 chain of the same dataflow."""
+        _cabi.call("rt_engine_set_flags", self._handle, 1 if on else 0)
+
+    def check_status(self):
+        """Blocking.  Raises if the last forward flagged an fp16-range overflow in the tensor-core cost volume."""
+        st = ctypes.c_int(0)
+        _cabi.call("rt_engine_last_status", self._handle, ctypes.byref(st))
+        if st.value:
+            raise _cabi.RatrackError(f"fused backbone: device status {st.value} (cost-volume activation outside fp16 hi/lo range)")
 
     def launch_count(self):
         return int(_cabi.lib().rt_engine_launch_count(self._handle))

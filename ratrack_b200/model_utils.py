@@ -310,6 +310,8 @@ class Track4DBackbone(nn.Module):
         self._host_out[0].copy_(out[0], non_blocking=True)
         self._host_out[1].copy_(out[2], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        if self._engine is not None and self.use_fused and not self.training:
+            self._engine.check_status()
         return self._host_out
 
     @staticmethod

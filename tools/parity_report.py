@@ -23,20 +23,27 @@ lines = []
 for batch, n in ((1, 256), (2, 1024), (4, 1024)):
     d = synthetic.make_batch(batch, n, seed=1234)
     c = {k: torch.from_numpy(v) for k, v in d.items()}
-    for fused in (False, True):
+    for fused in (False, 'simt', 'tc'):
         net = Track4DBackbone(Args())
         sd = synthetic.make_state_dict(net, seed=1234)
         net.load_state_dict(sd, strict=False)
-        net.use_fused, net.capture_knn = fused, True
+        net.use_fused, net.capture_knn = bool(fused), True
         net = net.cuda().eval()
         t = {k: v.cuda() for k, v in c.items()}
+        if fused:
+            from ratrack_b200.engine import FusedBackbone
+            net._engine = FusedBackbone(net)
+            net._engine.set_tensor_core_costvol(fused == 'tc')
         with torch.no_grad():
             out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128, device="cuda"))
             knn = net.cost_volume_neighbours(t["pc1"], t["pc2"])
         ref = backbone_oracle.backbone(sd, c["pc1"], c["pc2"], c["ft1"], c["ft2"], torch.zeros(5, batch, 128),
                                        knn_override=tuple(k.cpu().long() for k in knn))
         ref_free = backbone_oracle.backbone(sd, c["pc1"], c["pc2"], c["ft1"], c["ft2"], torch.zeros(5, batch, 128))
-        row = [f"B={batch} N={n} {'fused  ' if fused else 'modular'}"]
+        if fused:
+            torch.cuda.synchronize()
+            net._engine.check_status()
+        row = [f"B={batch} N={n} {('fused-' + fused) if fused else 'modular'}"]
         for nm, a, r in zip(["flow", "h", "cls", "cor", "f1", "f2", "prop"], out, ref):
             err = float((a.cpu() - r).abs().max())
             scale = max(1.0, float(r.abs().max()))
