@@ -83,6 +83,12 @@ int rt_three_interpolate(int b, int c, int m, int n, const float *points, const 
 int rt_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
                               float *grad_points, void *stream);
 
+/* replaces square_distance + knn_point   (reference: src/utils/model_utils/model_utils.py:17-39, 85-99)
+ * query (b,n,3), search (b,m,3) row-major -> idx (b,n,k) int32, k <= 32: the k smallest expanded-form distances
+ * max((-2 q.s + |q|^2) + |s|^2, 0), evaluated in the fp32 rounding order of torch.matmul / torch.sum on both CPU
+ * and B200 (fma(z,z',fma(y,y',x*x')), (x^2+y^2)+z^2); ascending, ties -> lower index. */
+int rt_knn_expanded(int b, int n, int m, int k, const float *query, const float *search, int *idx, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Section 2 -- fused inference engine for Track4D.backbone (Seam C)
  *

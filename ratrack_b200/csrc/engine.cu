@@ -15,6 +15,7 @@
 
 #include "../../include/ratrack_b200.h"
 #include "engine_kernels.cuh"
+#include "mlp_tc.cuh"
 
 int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
                           float *xa, float *xb, cudaStream_t st);  // engine-internal, below
@@ -162,12 +163,19 @@ RtRowGemm gemm1(long long rows, int nout, const float *x, int ldx, int k, const 
 
 }  // namespace
 
+// tensor-core weight packs (fp16 hi/lo planes, mlp_tc.cuh layout), built on the device at engine creation
+struct HeadPacks { void *proj[3], *w2[3][2], *w3[2], *lin[3], *fp3, *fp2, *fp1; };
+struct Packs { HeadPacks pn, mse; void *p1, *p2, *cp[3], *fw[4]; };
+
 struct rt_engine {
     EngineW w;
+    Packs packs;
+    void *arena = nullptr;
     int npoint;
     cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
     long long launches = 0;
-    int flags = 1;                 // bit 0: tensor-core cost volume (costvol_tc.cu); 0 = SIMT reference chain
+    int flags = 3;                 // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
+                                   // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow
     const int *last_status = nullptr;
 };
 
@@ -298,6 +306,182 @@ int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSe
 
 }  // namespace
 
+namespace {
+
+RtMlpTc mlp_rows(long long rows, const float *x, int ldx, int k) {
+    RtMlpTc m{};
+    m.rows = rows;
+    m.load_mode = RT_MLP_LOAD_ROWS;
+    m.out_mode = RT_MLP_OUT_ROWS;
+    m.nseg = 1;
+    m.seg[0] = RtMlpSeg{x, ldx, k};
+    m.rows_per_cloud = 1;
+    return m;
+}
+void mlp_layer(RtMlpTc &m, const void *pack, const float *bias, int k, int n, int act) {
+    m.layer[m.nlayers++] = RtMlpLayer{pack, bias, (k + 15) / 16 * 16, (n + 15) / 16 * 16, act};
+}
+void mlp_out(RtMlpTc &m, float *out, int ldo, int ooff, int n_out) {
+    m.out = out; m.ldo = ldo; m.ooff = ooff; m.n_out = n_out;
+}
+
+// PNHead on the tensor cores: per level  projection GEMM -> 2 x [gather + conv chain + max-pool] -> linear
+int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int clouds, int n, const RtMlpSeg *segs, int nseg,
+                const float *cloud_bias1, float *out, cudaStream_t st) {
+    const int S = e->npoint;
+    const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
+    const int lvl_n[3] = {n, S, S};
+    float *lvl_out[3] = {w.l1, w.l2, w.l3};
+    const float *lvl_feat_in[3] = {nullptr, w.l1, w.l2};
+    const int lvl_cin[3] = {0, 32, 64};
+    const SaScaleW *sw[3] = {hw.l1, hw.l2, hw.l3};
+    const float *lin_b[3] = {hw.lin1_b, hw.lin2_b, hw.lin3_b};
+    for (int l = 0; l < 3; ++l) {
+        const LevelCfg &cfg = kLevels[l];
+        const int c1tot = cfg.c1[0] + cfg.c1[1];
+        RtMlpTc pg{};
+        int k0 = 0;
+        if (l == 0) {
+            pg = mlp_rows((long long)clouds * n, nullptr, 0, 0);
+            pg.nseg = nseg;
+            for (int i = 0; i < nseg; ++i) { pg.seg[i] = segs[i]; k0 += (segs[i].k + 15) / 16 * 16; }
+            pg.cloud_bias = cloud_bias1; pg.rows_per_cloud = n; pg.cloud_bias_ld = c1tot;
+        } else {
+            pg = mlp_rows((long long)clouds * lvl_n[l], lvl_feat_in[l], lvl_cin[l], lvl_cin[l]);
+            k0 = lvl_cin[l];
+        }
+        mlp_layer(pg, pk.proj[l], nullptr, k0, c1tot, RT_ACT_NONE);
+        mlp_out(pg, w.proj, c1tot, 0, c1tot);
+        pg.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(pg, st));
+        const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
+        int coff = 0;
+        for (int s = 0; s < 2; ++s) {
+            RtMlpTc m{};
+            m.rows = (long long)clouds * S * cfg.ns[s];
+            m.load_mode = RT_MLP_LOAD_GATHER; m.out_mode = RT_MLP_OUT_MAXPOOL;
+            m.y = w.proj; m.ldy = c1tot; m.yoff = s ? cfg.c1[0] : 0; m.n_in = lvl_n[l];
+            m.idx = w.bq[l][s]; m.xyz_in = lvl_xyz_in[l]; m.xyz_c = w.xyz[l]; m.wx = sw[l][s].wx; m.b1 = sw[l][s].b1;
+            m.npts = S; m.ns = cfg.ns[s]; m.c1 = cfg.c1[s]; m.rows_per_cloud = 1;
+            mlp_layer(m, pk.w2[l][s], sw[l][s].b2, cfg.c1[s], cfg.c2[s], RT_ACT_RELU);
+            int clast = cfg.c2[s];
+            if (cfg.c3[s]) { mlp_layer(m, pk.w3[s], sw[l][s].b3, cfg.c2[s], cfg.c3[s], RT_ACT_RELU); clast = cfg.c3[s]; }
+            mlp_out(m, w.pooled, pooled_c, coff, clast);
+            m.status = w.status;
+            RT_TRY(rt_launch_mlp_tc(m, st));
+            coff += clast;
+        }
+        RtMlpTc lg = mlp_rows((long long)clouds * S, w.pooled, pooled_c, pooled_c);
+        mlp_layer(lg, pk.lin[l], lin_b[l], pooled_c, cfg.lin_out, RT_ACT_NONE);
+        mlp_out(lg, lvl_out[l], cfg.lin_out, 0, cfg.lin_out);
+        lg.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(lg, st));
+        e->launches += 4;
+    }
+    {   // FP3: l2 <- l3
+        RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
+        RtMlpTc m = mlp_rows((long long)clouds * S, w.interp, 64, 64);
+        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l2, 64, 64};
+        mlp_layer(m, pk.fp3, hw.fp3_b, 128, 128, RT_ACT_RELU);
+        mlp_out(m, w.l2p, 128, 0, 128); m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    }
+    {   // FP2: l1 <- l2'
+        RT_TRY(rt_launch_interp3(clouds, S, S, 128, w.l2p, 128, w.nn_idx[1], w.nn_w[1], w.interp, 128, st));
+        RtMlpTc m = mlp_rows((long long)clouds * S, w.interp, 128, 128);
+        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l1, 32, 32};
+        mlp_layer(m, pk.fp2, hw.fp2_b, 160, 128, RT_ACT_RELU);
+        mlp_out(m, w.l1p, 128, 0, 128); m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    }
+    {   // FP1: l0 <- l1'
+        RT_TRY(rt_launch_interp3(clouds, n, S, 128, w.l1p, 128, w.nn_idx[2], w.nn_w[2], w.interp, 128, st));
+        RtMlpTc m = mlp_rows((long long)clouds * n, w.interp, 128, 128);
+        mlp_layer(m, pk.fp1, hw.fp1_b, 128, 128, RT_ACT_RELU);
+        mlp_out(m, out, 128, 0, 128); m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    }
+    e->launches += 6;
+    return RT_OK;
+}
+
+// ---- weight packing at engine creation -----------------------------------------------------------
+struct PackJob { void **dst; int n; int nseg; RtPackSeg seg[4]; };
+
+void add_job(PackJob *jobs, int &nj, void **dst, int n, const float *w, int k) {
+    jobs[nj] = PackJob{dst, n, 1, {RtPackSeg{w, k, k}}};
+    ++nj;
+}
+
+int head_jobs(PackJob *jobs, int &nj, const HeadW &hw, HeadPacks &pk, bool mse) {
+    // level-1 projection: both scales' feature columns, segment by segment (ft | local | cor; the cloud-constant
+    // `glob` block is applied as a per-cloud bias)
+    PackJob j{&pk.proj[0], 32, 1, {RtPackSeg{hw.wf_ft, 2, 2}}};
+    if (mse) {
+        j.nseg = 3;
+        j.seg[1] = RtPackSeg{hw.wf_loc, 128, 128};
+        j.seg[2] = RtPackSeg{hw.wf_cor, 256, 256};
+    }
+    jobs[nj++] = j;
+    add_job(jobs, nj, &pk.proj[1], 64, hw.wf2, 32);
+    add_job(jobs, nj, &pk.proj[2], 128, hw.wf3, 64);
+    const SaScaleW *sw[3] = {hw.l1, hw.l2, hw.l3};
+    for (int l = 0; l < 3; ++l)
+        for (int s = 0; s < 2; ++s) {
+            add_job(jobs, nj, &pk.w2[l][s], kLevels[l].c2[s], sw[l][s].w2, kLevels[l].c1[s]);
+            if (l == 0) add_job(jobs, nj, &pk.w3[s], kLevels[0].c3[s], sw[0][s].w3, kLevels[0].c2[s]);
+        }
+    add_job(jobs, nj, &pk.lin[0], 32, hw.lin1_w, 64);
+    add_job(jobs, nj, &pk.lin[1], 64, hw.lin2_w, 96);
+    add_job(jobs, nj, &pk.lin[2], 64, hw.lin3_w, 128);
+    jobs[nj++] = PackJob{&pk.fp3, 128, 2, {RtPackSeg{hw.fp3_wi, 64, 64}, RtPackSeg{hw.fp3_ws, 64, 64}}};
+    jobs[nj++] = PackJob{&pk.fp2, 128, 2, {RtPackSeg{hw.fp2_wi, 128, 128}, RtPackSeg{hw.fp2_ws, 32, 32}}};
+    add_job(jobs, nj, &pk.fp1, 128, hw.fp1_wi, 128);
+    return RT_OK;
+}
+
+int build_packs(rt_engine *e) {
+    PackJob jobs[64];
+    int nj = 0;
+    head_jobs(jobs, nj, e->w.pn, e->packs.pn, false);
+    head_jobs(jobs, nj, e->w.mse, e->packs.mse, true);
+    add_job(jobs, nj, &e->packs.p1, 256, e->w.cv.w1_l1, 128);
+    add_job(jobs, nj, &e->packs.p2, 256, e->w.cv.w1_l2, 128);
+    add_job(jobs, nj, &e->packs.cp[0], 128, e->w.cp.w1, 256);
+    add_job(jobs, nj, &e->packs.cp[1], 64, e->w.cp.w2, 128);
+    add_job(jobs, nj, &e->packs.cp[2], 32, e->w.cp.w3, 64);
+    add_job(jobs, nj, &e->packs.fw[0], 128, e->w.fp.w1_l, 128);
+    add_job(jobs, nj, &e->packs.fw[1], 64, e->w.fp.w2, 128);
+    add_job(jobs, nj, &e->packs.fw[2], 32, e->w.fp.w3, 64);
+    add_job(jobs, nj, &e->packs.fw[3], 3, e->w.fp.w4, 32);
+    size_t total = 0;
+    size_t offs[64];
+    for (int i = 0; i < nj; ++i) {
+        int kp = 0;
+        for (int s = 0; s < jobs[i].nseg; ++s) kp += (jobs[i].seg[s].k + 15) / 16 * 16;
+        const int np = (jobs[i].n + 15) / 16 * 16;
+        offs[i] = total;
+        total += ((size_t)4 * np * kp + 255) & ~(size_t)255;
+    }
+    cudaError_t err = cudaMalloc(&e->arena, total);
+    if (err != cudaSuccess) {
+        rt_set_error("engine_create: cudaMalloc(%zu) for weight packs: %s", total, cudaGetErrorString(err));
+        return (int)err;
+    }
+    for (int i = 0; i < nj; ++i) {
+        *jobs[i].dst = (char *)e->arena + offs[i];
+        RT_TRY(rt_launch_pack_umma(*jobs[i].dst, jobs[i].n, (jobs[i].n + 15) / 16 * 16, jobs[i].seg, jobs[i].nseg, nullptr));
+    }
+    err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        rt_set_error("engine_create: packing weights: %s", cudaGetErrorString(err));
+        return (int)err;
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
 // v0 of the dense cost-volume MLP (two 256x256 layers with LeakyReLU over b*n*16 rows): two row GEMMs.
 int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
                           float *xa, float *xb, cudaStream_t st) {
@@ -331,11 +515,21 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
             return RT_ERR_INVALID;
         }
     }
+    const int rc = build_packs(e);
+    if (rc != RT_OK) {
+        if (e->arena) cudaFree(e->arena);
+        delete e;
+        return rc;
+    }
     *out = e;
     return RT_OK;
 }
 
-RT_API void rt_engine_destroy(rt_engine *e) { delete e; }
+RT_API void rt_engine_destroy(rt_engine *e) {
+    if (!e) return;
+    if (e->arena) cudaFree(e->arena);
+    delete e;
+}
 
 RT_API long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n) {
     if (!e || b < 1 || n < 1) return -1;
@@ -400,8 +594,16 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     RT_TRY(run_geometry(e, w, b, n, st));
 
     // feature_extraction_head: pn_head over both clouds of every pair at once (track4d.py:102-106)
-    RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
-    RT_TRY(run_head(e, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+    const bool tc_mlp = (e->flags & 2) != 0;
+    cudaMemsetAsync(w.status, 0, 64 * sizeof(int), st);
+    e->last_status = w.status;
+    if (tc_mlp) {
+        RtMlpSeg seg_ft{w.ft0, 2, 2};
+        RT_TRY(run_head_tc(e, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+    } else {
+        RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
+        RT_TRY(run_head(e, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+    }
     RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
     // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95)
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat, 128, 0, f1, 256, 0, st));
@@ -415,7 +617,18 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     const float *x1 = w.xyz0, *x2 = w.xyz0 + half3;
     RT_TRY(rt_launch_cloud_matvec(b, 256, 128, cv.w1_g1, 128, w.gmax, 128, cv.b1, w.cb_a, st));
     RT_TRY(rt_launch_cloud_matvec(b, 256, 128, cv.w1_g2, 128, w.gmax + (size_t)b * 128, 128, nullptr, w.cb_b, st));
-    {
+    if (tc_mlp) {
+        RtMlpTc m = mlp_rows((long long)b * n, w.feat, 128, 128);
+        mlp_layer(m, e->packs.p1, nullptr, 128, 256, RT_ACT_NONE);
+        mlp_out(m, w.p1, 256, 0, 256);
+        m.cloud_bias = w.cb_a; m.rows_per_cloud = n; m.cloud_bias_ld = 256; m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+        m = mlp_rows((long long)b * n, w.feat + half128, 128, 128);
+        mlp_layer(m, e->packs.p2, nullptr, 128, 256, RT_ACT_NONE);
+        mlp_out(m, w.p2, 256, 0, 256);
+        m.cloud_bias = w.cb_b; m.rows_per_cloud = n; m.cloud_bias_ld = 256; m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    } else {
         RtRowGemm g = gemm1((long long)b * n, 256, w.feat, 128, 128, cv.w1_l1, nullptr, RT_ACT_NONE, w.p1, 256);
         g.cloud_bias = w.cb_a; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
@@ -423,8 +636,6 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
     }
-    cudaMemsetAsync(w.status, 0, 64 * sizeof(int), st);
-    e->last_status = w.status;
     if (e->flags & 1) {
         if (e->prof_start) cudaEventRecord(e->prof_start, st);
         RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
@@ -458,30 +669,54 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     // FlowDecoder (model_utils.py:281-305): cls head on the cost volume
     const ClsW &cp = e->w.cp;
     const long long pts = (long long)b * n;
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 128, w.cor, 256, 256, cp.w1, cp.b1, RT_ACT_RELU, w.h1, 128), st));
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, cp.w2, cp.b2, RT_ACT_RELU, w.h2, 64), st));
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, cp.w3, cp.b3, RT_ACT_RELU, w.h3, 32), st));
+    if (tc_mlp) {
+        RtMlpTc m = mlp_rows(pts, w.cor, 256, 256);
+        mlp_layer(m, e->packs.cp[0], cp.b1, 256, 128, RT_ACT_RELU);
+        mlp_layer(m, e->packs.cp[1], cp.b2, 128, 64, RT_ACT_RELU);
+        mlp_layer(m, e->packs.cp[2], cp.b3, 64, 32, RT_ACT_RELU);
+        mlp_out(m, w.h3, 32, 0, 32);
+        m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    } else {
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 128, w.cor, 256, 256, cp.w1, cp.b1, RT_ACT_RELU, w.h1, 128), st));
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, cp.w2, cp.b2, RT_ACT_RELU, w.h2, 64), st));
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, cp.w3, cp.b3, RT_ACT_RELU, w.h3, 32), st));
+    }
     RT_TRY(rt_launch_cls_tail(pts, w.h3, cp.w4, cp.lin_w, cp.lin_b, cls, st));
     // second PNHead over embeddings = cat(feature1, pc1_features, cor_features) on pc1's geometry
     const HeadW &mse = e->w.mse;
     RT_TRY(rt_launch_cloud_matvec(b, 32, 128, mse.wf_glob, 128, w.gmax, 128, nullptr, w.cb_a, st));
-    RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},
-                     RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
-    RT_TRY(run_head(e, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+    if (tc_mlp) {
+        RtMlpSeg segs[3] = {RtMlpSeg{w.ft0, 2, 2}, RtMlpSeg{w.feat, 128, 128}, RtMlpSeg{w.cor, 256, 256}};
+        RT_TRY(run_head_tc(e, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+    } else {
+        RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},
+                         RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
+        RT_TRY(run_head(e, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+    }
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, st));
     RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
     RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, st));
     // FlowPredictor on cat(prop_features, broadcast GRU output)
     const FlowW &fp = e->w.fp;
     RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + (size_t)4 * b * 128, 128, fp.b1, w.cb_b, st));
-    {
+    if (tc_mlp) {
+        RtMlpTc m = mlp_rows(pts, w.prop, 128, 128);
+        mlp_layer(m, e->packs.fw[0], nullptr, 128, 128, RT_ACT_RELU);
+        mlp_layer(m, e->packs.fw[1], fp.b2, 128, 64, RT_ACT_RELU);
+        mlp_layer(m, e->packs.fw[2], fp.b3, 64, 32, RT_ACT_RELU);
+        mlp_layer(m, e->packs.fw[3], nullptr, 32, 3, RT_ACT_NONE);
+        mlp_out(m, w.flow_rows, 3, 0, 3);
+        m.cloud_bias = w.cb_b; m.rows_per_cloud = n; m.cloud_bias_ld = 128; m.status = w.status;
+        RT_TRY(rt_launch_mlp_tc(m, st));
+    } else {
         RtRowGemm g = gemm1(pts, 128, w.prop, 128, 128, fp.w1_l, nullptr, RT_ACT_RELU, w.h1, 128);
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, fp.w2, fp.b2, RT_ACT_RELU, w.h2, 64), st));
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, fp.w3, fp.b3, RT_ACT_RELU, w.h3, 32), st));
+        RT_TRY(rt_launch_rowgemm(gemm1(pts, 3, w.h3, 32, 32, fp.w4, nullptr, RT_ACT_NONE, w.flow_rows, 3), st));
     }
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, fp.w2, fp.b2, RT_ACT_RELU, w.h2, 64), st));
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, fp.w3, fp.b3, RT_ACT_RELU, w.h3, 32), st));
-    RT_TRY(rt_launch_rowgemm(gemm1(pts, 3, w.h3, 32, 32, fp.w4, nullptr, RT_ACT_NONE, w.flow_rows, 3), st));
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
     e->launches += 14;
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);

@@ -251,6 +251,78 @@ __global__ void __launch_bounds__(KX_THREADS) knn_expanded_kernel(int n, int m, 
     }
 }
 
+// Warp-cooperative variant (k <= 32): one warp per query, 16 queries per CTA.  The search cloud is staged
+// in tiles of 1024 points; lane L holds candidates L, L+32, ... of the tile in registers plus one carried
+// winner of the previous tiles.  The k smallest are then extracted one by one with redux.sync.min
+// (distance bits first, then index: ties -> lower index).  No divergent per-thread insertion lists.
+constexpr int KW_WARPS = 8, KW_QPW = 2, KW_TILE = 1024;
+
+__global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n, int m, int k, const float *__restrict__ q,
+                                                                           const float *__restrict__ s, int *__restrict__ idx) {
+    __shared__ float4 s_pts[KW_TILE];
+    const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = (blockIdx.x * KW_WARPS + warp) * KW_QPW;
+    float qx[KW_QPW], qy[KW_QPW], qz[KW_QPW], q2[KW_QPW];
+    uint32_t car_d[KW_QPW], car_i[KW_QPW];   // carried best list: lane l < k holds the l-th smallest so far
+#pragma unroll
+    for (int u = 0; u < KW_QPW; ++u) {
+        const int qi = min(q0 + u, n - 1);
+        const float *qp = q + ((long long)cloud * n + qi) * 3;
+        qx[u] = __ldg(qp + 0); qy[u] = __ldg(qp + 1); qz[u] = __ldg(qp + 2);
+        q2[u] = __fadd_rn(__fadd_rn(__fmul_rn(qx[u], qx[u]), __fmul_rn(qy[u], qy[u])), __fmul_rn(qz[u], qz[u]));
+        car_d[u] = 0x7f800000u;
+        car_i[u] = 0xffffffffu;
+    }
+    for (int base = 0; base < m; base += KW_TILE) {
+        const int tn = min(KW_TILE, m - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < tn; t += 32 * KW_WARPS) {
+            const float *p = s + ((long long)cloud * m + base + t) * 3;
+            const float x = __ldg(p + 0), y = __ldg(p + 1), z = __ldg(p + 2);
+            s_pts[t] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < KW_QPW; ++u) {
+            uint32_t d[32];   // distance bits (d >= 0, so uint order == float order); +inf marks "absent / taken"
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int t = lane + 32 * i;
+                if (t < tn) {
+                    const float4 p = s_pts[t];
+                    const float dot = __fmaf_rn(qz[u], p.z, __fmaf_rn(qy[u], p.y, __fmul_rn(qx[u], p.x)));
+                    d[i] = __float_as_uint(fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), q2[u]), p.w), 0.0f));
+                } else {
+                    d[i] = 0x7f800000u;
+                }
+            }
+            uint32_t cd = car_d[u], ci = car_i[u], nd = 0x7f800000u, ni = 0xffffffffu;
+            for (int r = 0; r < k; ++r) {
+                // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
+                uint32_t ld = cd, li = ci;
+                int lslot = -1;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (d[i] < ld) { ld = d[i]; li = (uint32_t)(base + lane + 32 * i); lslot = i; }
+                const uint32_t md = rt_redux_min_u32(ld);
+                const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
+                if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
+                    if (lslot < 0) cd = 0x7f800000u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i == lslot) d[i] = 0x7f800000u;
+                }
+                if (lane == r) { nd = md; ni = mi; }
+            }
+            car_d[u] = nd;
+            car_i[u] = ni;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < KW_QPW; ++u)
+        if (q0 + u < n && lane < k) idx[((long long)cloud * n + q0 + u) * k + lane] = (int)car_i[u];
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nn_weights_kernel(long long rows, float *__restrict__ d) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,9 +427,10 @@ __global__ void __launch_bounds__(256) broadcast_cm_kernel(int c, int n, const f
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = v;
 }
 
-// 5-layer GRU, sequence length 1 (torch.nn.GRU equations): CTA per batch element, 384 threads (one per gate row)
+// 5-layer GRU, sequence length 1 (torch.nn.GRU equations): CTA per batch element, 384 threads (one per gate row).
+// Weights arrive TRANSPOSED, (5, 128, 384): thread t reads column t -> every load is coalesced.
 __global__ void __launch_bounds__(384) gru_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
-                                                  const float *__restrict__ wih, const float *__restrict__ whh,
+                                                  const float *__restrict__ wih_t, const float *__restrict__ whh_t,
                                                   const float *__restrict__ bih, const float *__restrict__ bhh,
                                                   float *__restrict__ h_out) {
     __shared__ float s_in[128], s_h[128], s_gi[384], s_gh[384];
@@ -366,13 +439,13 @@ __global__ void __launch_bounds__(384) gru_kernel(int bsz, const float *__restri
     for (int l = 0; l < 5; ++l) {
         if (t < 128) s_h[t] = h_in[((long long)l * bsz + b) * 128 + t];
         __syncthreads();
-        const float *wi = wih + ((long long)l * 384 + t) * 128;
-        const float *wh = whh + ((long long)l * 384 + t) * 128;
+        const float *wi = wih_t + (long long)l * 128 * 384 + t;
+        const float *wh = whh_t + (long long)l * 128 * 384 + t;
         float gi = 0.0f, gh = 0.0f;
 #pragma unroll 8
         for (int k = 0; k < 128; ++k) {
-            gi = fmaf(__ldg(wi + k), s_in[k], gi);
-            gh = fmaf(__ldg(wh + k), s_h[k], gh);
+            gi = fmaf(__ldg(wi + k * 384), s_in[k], gi);
+            gh = fmaf(__ldg(wh + k * 384), s_h[k], gh);
         }
         s_gi[t] = gi + __ldg(bih + l * 384 + t);
         s_gh[t] = gh + __ldg(bhh + l * 384 + t);
@@ -445,10 +518,10 @@ int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st) {
 int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st) {
     if (clouds <= 0 || n <= 0) return RT_OK;
     RT_REQUIRE(k >= 1 && k <= 32 && m >= 1, "knn_expanded: k=%d outside [1,32] or empty search cloud", k);
-    dim3 grid(rt_divup(n, KX_THREADS), clouds);
-    if (k <= 16) knn_expanded_kernel<16><<<grid, KX_THREADS, 0, st>>>(n, m, k, q, s, idx);
-    else knn_expanded_kernel<32><<<grid, KX_THREADS, 0, st>>>(n, m, k, q, s, idx);
-    return rt_check_launch("knn_expanded_kernel");
+    RT_REQUIRE(k <= m, "knn_expanded: k=%d > search points %d", k, m);
+    dim3 grid(rt_divup(n, KW_WARPS * KW_QPW), clouds);
+    knn_expanded_warp_kernel<<<grid, 32 * KW_WARPS, 0, st>>>(n, m, k, q, s, idx);
+    return rt_check_launch("knn_expanded_warp_kernel");
 }
 int rt_launch_nn_weights(long long rows, float *d, cudaStream_t st) {
     if (rows <= 0) return RT_OK;
@@ -515,4 +588,15 @@ int rt_launch_fill(float *p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return RT_OK;
     fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);
     return rt_check_launch("fill_kernel");
+}
+
+// C ABI: cost-volume neighbour search.  replaces square_distance + knn_point
+// (reference: src/utils/model_utils/model_utils.py:17-39, 85-99): expanded-form fp32 distances in torch's own
+// rounding order, clamp at 0, the k smallest per query (ascending, ties -> lower index; torch.topk leaves
+// both the order and the tie choice undefined).
+RT_API int rt_knn_expanded(int b, int n, int m, int k, const float *query, const float *search, int *idx, void *stream) {
+    RT_REQUIRE(b >= 0 && n >= 0 && m >= 0 && query && search && idx, "knn_expanded: bad arguments");
+    RT_REQUIRE(b <= 65535, "knn_expanded: batch > 65535");
+    RT_REQUIRE(k <= m, "knn_expanded: k=%d > number of search points %d", k, m);
+    return rt_launch_knn_expanded(b, n, m, k, query, search, idx, (cudaStream_t)stream);
 }

@@ -1,0 +1,376 @@
+// Row-tile MLP chains on the tcgen05 tensor cores (sm_100a): the workhorse behind every dense layer of the
+// fused engine except the streamed 256x256 cost-volume layers (costvol_tc.cu).
+//
+//   tile      = 128 rows (row = TMEM lane);  persistent CTAs loop over tiles;
+//   input     = MT_LOAD_ROWS:   concatenation of up to 4 row-major fp32 segments (each padded to 16 columns), or
+//               MT_LOAD_GATHER: the first set-abstraction layer evaluated on the fly from per-point projections,
+//                               relu(Y[idx] + Wx.(xyz[idx] - centre) + b1)   (reference: QueryAndGroup + first conv,
+//                               src/lib/pointnet2_utils.py:269-292, src/lib/pytorch_utils.py:5-32) -- the grouped
+//                               (B,C,S,ns) tensor is never built;
+//   layers    = 1..4 x [tcgen05.mma kind::f16 M128 N<=256, A from TMEM, weights resident in shared memory in the
+//               K-major core-matrix layout, fp16 hi/lo split with 3 MMAs per product (fp32-class accuracy)]
+//               with bias / ReLU / LeakyReLU epilogues that write the next layer's A operand straight back to TMEM;
+//   output    = MT_OUT_ROWS: fp32 rows, or MT_OUT_MAXPOOL: max over the ns consecutive rows of a centre
+//               (reference: F.max_pool2d over nsample, src/lib/pointnet2_modules.py:42-44) by warp shuffles.
+#include <cuda_fp16.h>
+
+#include "engine_kernels.cuh"
+#include "mlp_tc.cuh"
+
+namespace {
+
+constexpr int MT_WORKER_WARPS = 4;
+constexpr int MT_THREADS = 32 * (MT_WORKER_WARPS + 1);
+constexpr float MT_WINV = 1.0f / 1024.0f;
+
+__device__ __forceinline__ void mt_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = rt_smem_u32(bar);
+    for (uint32_t it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (it > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mt_tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mt_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mt_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mt_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mt_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mt_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mt_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mt_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void mt_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t mt_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t mt_idesc(int n) {  // F16 x F16 -> F32, K-major, M = 128
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ float mt_act(float v, int act) {
+    if (act == RT_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == RT_ACT_LEAKY01) return v > 0.0f ? v : 0.1f * v;
+    return v;
+}
+__device__ __forceinline__ void mt_split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
+    amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// 16 fp32 values -> hi/lo fp16 planes, 8 TMEM columns each
+__device__ __forceinline__ void mt_store16(const float *v, uint32_t t_hi, uint32_t t_lo, float &amax) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mt_split2(v[2 * i], v[2 * i + 1], hi[i], lo[i], amax);
+    mt_st8(t_hi, hi);
+    mt_st8(t_lo, lo);
+}
+
+__global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_a, bar_d;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = (a.rows + 127) / 128;
+
+    // weights of all layers -> shared memory (already in core-matrix layout); layer l starts at w_off[l]
+    int w_off[RT_MLP_MAX_LAYERS + 1];
+    w_off[0] = 0;
+#pragma unroll
+    for (int l = 0; l < RT_MLP_MAX_LAYERS; ++l) w_off[l + 1] = w_off[l] + (l < a.nlayers ? 4 * a.layer[l].k * a.layer[l].n : 0);
+    for (int l = 0; l < a.nlayers; ++l) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.layer[l].wpack);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + w_off[l]);
+        const int n16 = (w_off[l + 1] - w_off[l]) / 16;
+        for (int i = threadIdx.x; i < n16; i += MT_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x == 0) {
+        rt_mbar_init(&bar_a, MT_WORKER_WARPS);
+        rt_mbar_init(&bar_d, 1);
+        rt_fence_mbar_init();
+    }
+    rt_fence_proxy_async();
+    if (warp == MT_WORKER_WARPS) mt_tmem_alloc(&tmem_slot, a.tmem_cols);
+    mt_fence_before();
+    __syncthreads();
+    mt_fence_after();
+    const uint32_t tm = tmem_slot;
+    const uint32_t tD = tm, tAhi = tm + a.d_cols, tAlo = tAhi + a.a_cols;
+
+    if (warp == MT_WORKER_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t a_phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int l = 0; l < a.nlayers; ++l) {
+                    mt_mbar_wait(&bar_a, a_phase);
+                    a_phase ^= 1;
+                    mt_fence_after();
+                    const int k = a.layer[l].k, n = a.layer[l].n;
+                    const uint32_t lbo = (uint32_t)(n / 8) * 128;
+                    const uint32_t hi_base = rt_smem_u32(smem + w_off[l]), lo_base = hi_base + 2 * k * n;
+                    const uint32_t idesc = mt_idesc(n);
+                    for (int kk = 0; kk < k / 16; ++kk) {
+                        const uint64_t bhi = mt_desc(hi_base + kk * 2 * lbo, lbo, 128);
+                        const uint64_t blo = mt_desc(lo_base + kk * 2 * lbo, lbo, 128);
+                        mt_mma_ts(tD, tAhi + 8 * kk, bhi, idesc, kk > 0);
+                        mt_mma_ts(tD, tAlo + 8 * kk, bhi, idesc, 1);
+                        mt_mma_ts(tD, tAhi + 8 * kk, blo, idesc, 1);
+                    }
+                    mt_commit(&bar_d);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== worker warps: one thread per row =====
+        const int row_in_tile = 32 * warp + lane;
+        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        uint32_t d_phase = 0;
+        float amax = 0.0f;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long row = tile * 128 + row_in_tile;
+            const bool valid = row < a.rows;
+            const long long rc = valid ? row : a.rows - 1;
+            // ---------- layer-0 input ----------
+            if (a.load_mode == RT_MLP_LOAD_ROWS) {
+                int c0 = 0;
+                for (int s = 0; s < a.nseg; ++s) {
+                    const float *x = a.seg[s].x + rc * a.seg[s].ldx;
+                    const int ks = a.seg[s].k;
+                    const bool vec = (a.seg[s].ldx & 3) == 0;
+                    for (int o = 0; o < ks; o += 16, c0 += 16) {
+                        float v[16];
+                        if (vec && o + 16 <= ks) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(x + o) + g);
+                                v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = (o + i < ks) ? __ldg(x + o + i) : 0.0f;
+                        }
+                        mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
+                    }
+                }
+            } else {
+                const long long cp = rc / a.ns;                 // (cloud, centre)
+                const int cloud = (int)(cp / a.npts);
+                const int j = __ldg(a.idx + rc);
+                const long long g = (long long)cloud * a.n_in + j;
+                const float dx = __ldg(a.xyz_in + g * 3 + 0) - __ldg(a.xyz_c + cp * 3 + 0);
+                const float dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(a.xyz_c + cp * 3 + 1);
+                const float dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(a.xyz_c + cp * 3 + 2);
+                const float *yrow = a.y + g * a.ldy + a.yoff;
+                for (int c0 = 0; c0 < a.c1; c0 += 16) {
+                    float v[16];
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(yrow + c0) + gq);
+                        v[4 * gq] = t.x; v[4 * gq + 1] = t.y; v[4 * gq + 2] = t.z; v[4 * gq + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float *w = a.wx + (c0 + i) * 3;
+                        float t = v[i] + fmaf(__ldg(w + 2), dz, fmaf(__ldg(w + 1), dy, __ldg(w + 0) * dx));
+                        t += __ldg(a.b1 + c0 + i);
+                        v[i] = fmaxf(t, 0.0f);
+                    }
+                    mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
+                }
+            }
+            mt_st_wait();
+            mt_fence_before();
+            __syncwarp();
+            if (lane == 0) rt_mbar_arrive(&bar_a);
+
+            for (int l = 0; l < a.nlayers; ++l) {
+                mt_mbar_wait(&bar_d, d_phase);
+                d_phase ^= 1;
+                mt_fence_after();
+                const int n = a.layer[l].n, act = a.layer[l].act;
+                const float *bias = a.layer[l].bias;
+                const float *cb = (l == 0 && a.cloud_bias) ? a.cloud_bias + (rc / a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
+                const bool last = l == a.nlayers - 1;
+                for (int c0 = 0; c0 < n; c0 += 16) {
+                    uint32_t r[16];
+                    mt_ld16(tD + lane_base + c0, r);
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float t = __uint_as_float(r[i]) * MT_WINV;
+                        if (bias) t += __ldg(bias + c0 + i);
+                        if (cb) t += __ldg(cb + c0 + i);
+                        v[i] = mt_act(t, act);
+                    }
+                    if (!last) {
+                        mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
+                    } else if (a.out_mode == RT_MLP_OUT_ROWS) {
+                        if (valid) {
+                            float *o = a.out + row * a.ldo + a.ooff + c0;
+                            if (c0 + 16 <= a.n_out && (a.ldo & 3) == 0 && (a.ooff & 3) == 0) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    reinterpret_cast<float4 *>(o)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < a.n_out) o[i] = v[i];
+                            }
+                        }
+                    } else {
+                        // max over the ns consecutive rows (= lanes) of a centre; 128 % ns == 0 so groups never straddle tiles
+                        for (int off = a.ns >> 1; off >= 1; off >>= 1) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], off));
+                        }
+                        if (valid && (lane & (a.ns - 1)) == 0) {
+                            float *o = a.out + (row / a.ns) * a.ldo + a.ooff + c0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < a.n_out) o[i] = v[i];
+                        }
+                    }
+                }
+                if (!last) {
+                    mt_st_wait();
+                    mt_fence_before();
+                    __syncwarp();
+                    if (lane == 0) rt_mbar_arrive(&bar_a);
+                }
+            }
+            mt_fence_before();
+        }
+        if (!(amax < 65000.0f) && a.status) atomicOr(a.status, 2);
+    }
+    mt_fence_before();
+    __syncthreads();
+    if (warp == MT_WORKER_WARPS) mt_tmem_dealloc(tm, a.tmem_cols);
+}
+
+}  // namespace
+
+int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
+    if (a.rows <= 0) return RT_OK;
+    RT_REQUIRE(a.nlayers >= 1 && a.nlayers <= RT_MLP_MAX_LAYERS, "mlp_tc: nlayers=%d", a.nlayers);
+    int dmax = 0, kmax = 0, wbytes = 0;
+    for (int l = 0; l < a.nlayers; ++l) {
+        const int k = a.layer[l].k, n = a.layer[l].n;
+        RT_REQUIRE(k >= 16 && k % 16 == 0 && n >= 16 && n % 16 == 0 && n <= 256, "mlp_tc: layer %d has k=%d n=%d", l, k, n);
+        RT_REQUIRE(l == 0 || k == a.layer[l - 1].n, "mlp_tc: layer %d k=%d does not chain", l, k);
+        dmax = n > dmax ? n : dmax;
+        kmax = k > kmax ? k : kmax;
+        wbytes += 4 * k * n;
+    }
+    if (a.load_mode == RT_MLP_LOAD_ROWS) {
+        int ktot = 0;
+        for (int s = 0; s < a.nseg; ++s) ktot += (a.seg[s].k + 15) / 16 * 16;
+        RT_REQUIRE(ktot == a.layer[0].k, "mlp_tc: segments cover %d columns, layer 0 expects %d", ktot, a.layer[0].k);
+    } else {
+        RT_REQUIRE(a.c1 == a.layer[0].k && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
+    }
+    if (a.out_mode == RT_MLP_OUT_MAXPOOL || a.load_mode == RT_MLP_LOAD_GATHER)
+        RT_REQUIRE(a.ns >= 1 && a.ns <= 32 && (a.ns & (a.ns - 1)) == 0, "mlp_tc: ns=%d must be a power of two <= 32", a.ns);
+    const int need = dmax + kmax;  // accumulator columns + two A planes of kmax/2 columns
+    RT_REQUIRE(need <= 512, "mlp_tc: %d TMEM columns needed", need);
+    int cols = 32;
+    while (cols < need) cols *= 2;
+    a.tmem_cols = cols;
+    a.d_cols = dmax;
+    a.a_cols = kmax / 2;
+    RT_REQUIRE(wbytes <= 200 * 1024, "mlp_tc: %d bytes of weights do not fit in shared memory", wbytes);
+    static int smem_set = 0;
+    if (wbytes > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            rt_set_error("mlp_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        smem_set = 200 * 1024;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // resident CTAs per SM: bounded by TMEM columns, shared memory and (to keep tail effects small) 4
+    int per_sm = 512 / cols;
+    const int by_smem = (220 * 1024) / (wbytes + 2048);
+    per_sm = per_sm < by_smem ? per_sm : by_smem;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    const long long ntiles = (a.rows + 127) / 128;
+    long long grid = (long long)sms * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    mlp_tc_kernel<<<(int)grid, MT_THREADS, wbytes, st>>>(a);
+    return rt_check_launch("mlp_tc_kernel");
+}
+
+namespace {
+struct PackArgs { __half *dst; int n_real, n_pad, k_pad, nseg; RtPackSeg seg[4]; };
+
+__global__ void __launch_bounds__(256) pack_umma_kernel(PackArgs a) {
+    const int total = a.n_pad * a.k_pad;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int n = e / a.k_pad, k = e % a.k_pad;
+        float w = 0.0f;
+        if (n < a.n_real) {
+            int c0 = 0;
+            for (int s = 0; s < a.nseg; ++s) {
+                const int kp = (a.seg[s].k + 15) / 16 * 16;
+                if (k >= c0 && k < c0 + kp) {
+                    if (k - c0 < a.seg[s].k) w = a.seg[s].w[(long long)n * a.seg[s].ldw + (k - c0)];
+                    break;
+                }
+                c0 += kp;
+            }
+        }
+        w *= 1024.0f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        // [plane][kc = k/8][rg = n/8][n%8][k%8]
+        const size_t off = ((size_t)(k / 8) * (a.n_pad / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
+        a.dst[off] = hi;
+        a.dst[(size_t)a.n_pad * a.k_pad + off] = lo;
+    }
+}
+}  // namespace
+
+int rt_launch_pack_umma(void *dst, int n_real, int n_pad, const RtPackSeg *segs, int nseg, cudaStream_t st) {
+    RT_REQUIRE(dst && nseg >= 1 && nseg <= 4 && n_pad % 16 == 0 && n_real <= n_pad, "pack_umma: bad arguments");
+    PackArgs a{};
+    a.dst = (__half *)dst;
+    a.n_real = n_real;
+    a.n_pad = n_pad;
+    a.nseg = nseg;
+    a.k_pad = 0;
+    for (int s = 0; s < nseg; ++s) {
+        a.seg[s] = segs[s];
+        a.k_pad += (segs[s].k + 15) / 16 * 16;
+    }
+    pack_umma_kernel<<<rt_divup((long long)a.n_pad * a.k_pad, 256), 256, 0, st>>>(a);
+    return rt_check_launch("pack_umma_kernel");
+}

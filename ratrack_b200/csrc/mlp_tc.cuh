@@ -1,0 +1,46 @@
+// Launcher contract of the tensor-core row-tile MLP kernel (mlp_tc.cu).
+#pragma once
+#include "common.cuh"
+
+enum { RT_MLP_LOAD_ROWS = 0, RT_MLP_LOAD_GATHER = 1 };
+enum { RT_MLP_OUT_ROWS = 0, RT_MLP_OUT_MAXPOOL = 1 };
+constexpr int RT_MLP_MAX_LAYERS = 4;
+
+// weights of one layer: fp16 hi/lo planes of 2^10 * W in the K-major core-matrix layout
+// [plane hi, lo][kc = k/8][row group = n/8][8 rows][8 halfs]   (k, n already padded to multiples of 16)
+struct RtMlpLayer {
+    const void *wpack;
+    const float *bias;  // n entries (padded) or null
+    int k, n, act;
+};
+struct RtMlpSeg {
+    const float *x;
+    int ldx, k;         // k real columns; occupies ceil16(k) columns of layer 0's K
+};
+struct RtMlpTc {
+    long long rows;
+    int load_mode, out_mode;
+    // RT_MLP_LOAD_ROWS
+    int nseg;
+    RtMlpSeg seg[4];
+    // RT_MLP_LOAD_GATHER: relu(y[cloud, idx[row], yoff + c] + wx[c,:].(xyz_in[idx] - xyz_c[row / ns]) + b1[c]), c < c1
+    const float *y;
+    int ldy, yoff, n_in;
+    const int *idx;
+    const float *xyz_in, *xyz_c, *wx, *b1;
+    int npts, ns, c1;
+    int nlayers;
+    RtMlpLayer layer[RT_MLP_MAX_LAYERS];
+    const float *cloud_bias;   // added to layer 0's output: cloud_bias[row / rows_per_cloud, c]
+    int rows_per_cloud, cloud_bias_ld;
+    float *out;                // rows: out[row * ldo + ooff + c]; maxpool: out[(row / ns) * ldo + ooff + c], c < n_out
+    int ldo, ooff, n_out;
+    int *status;               // optional device status word (bit 1: fp16 range exceeded)
+    int tmem_cols, d_cols, a_cols;  // filled by the launcher
+};
+int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st);
+
+// device-side weight packing: W (n_real x sum k_s, given as column segments of row-major fp32 matrices) ->
+// the layout above with every segment padded to 16 columns and n padded to n_pad rows (zeros)
+struct RtPackSeg { const float *w; int ldw, k; };
+int rt_launch_pack_umma(void *dst, int n_real, int n_pad, const RtPackSeg *segs, int nseg, cudaStream_t st);

@@ -128,8 +128,9 @@ def build_weight_table(net):
     ws += [f1[0][:, :128], f1[0][:, 128:], f1[1], f2[0], f2[1], f3[0], f3[1], f4]
     g = fd.torchGRU
     assert g.num_layers == 5 and g.input_size == 128 and g.hidden_size == 128
-    ws += [torch.stack([getattr(g, f"weight_ih_l{l}").detach() for l in range(5)]),
-           torch.stack([getattr(g, f"weight_hh_l{l}").detach() for l in range(5)]),
+    # transposed to (5, 128, 384) so the GRU kernel's per-gate-row threads read coalesced columns
+    ws += [torch.stack([getattr(g, f"weight_ih_l{l}").detach().t() for l in range(5)]),
+           torch.stack([getattr(g, f"weight_hh_l{l}").detach().t() for l in range(5)]),
            torch.stack([getattr(g, f"bias_ih_l{l}").detach() for l in range(5)]),
            torch.stack([getattr(g, f"bias_hh_l{l}").detach() for l in range(5)])]
     return ws
@@ -165,9 +166,10 @@ class FusedBackbone:
             except Exception:
                 pass
 
-    def set_tensor_core_costvol(self, on: bool):
-        """A/B switch: tcgen05 cost-volume kernel (default) vs the SIMT fp32 chain of the same dataflow."""
-        _cabi.call("rt_engine_set_flags", self._handle, 1 if on else 0)
+    def set_flags(self, costvol_tc: bool = True, mlp_tc: bool = True):
+        """A/B switches: tcgen05 kernels (default) vs the fp32 SIMT kernels of the same dataflow, separately for the
+        cost-volume core (costvol_tc.cu) and for every other dense layer (mlp_tc.cu)."""
+        _cabi.call("rt_engine_set_flags", self._handle, (1 if costvol_tc else 0) | (2 if mlp_tc else 0))
 
     def check_status(self):
         """Blocking.  Raises if the last forward flagged an fp16-range overflow in the tensor-core cost volume."""

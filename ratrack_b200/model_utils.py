@@ -40,10 +40,22 @@ def index_points(points, idx):
 
 
 def knn_point(nsample, xyz, new_xyz):
-    """(B,S,nsample) indices of the nsample nearest points of xyz to each new_xyz.  reference :85-99"""
-    sqrdists = square_distance(new_xyz, xyz)
-    _, group_idx = torch.topk(sqrdists, nsample, dim=-1, largest=False, sorted=False)
-    return group_idx
+    """(B,S,nsample) int64 indices of the nsample nearest points of xyz (B,N,3) to each new_xyz (B,S,3).
+    reference :85-99 (square_distance + torch.topk).  Runs the sm_100a kernel rt_knn_expanded: same expanded-form
+    fp32 distances in torch's rounding order, never materialising the (B,S,N) matrix; ties -> lower index
+    (torch.topk leaves them undefined)."""
+    from . import _cabi
+
+    q = new_xyz.contiguous().float()
+    s = xyz.contiguous().float()
+    B, S, _ = q.shape
+    if nsample > 32 or not q.is_cuda:
+        raise _cabi.RatrackError("knn_point: needs CUDA tensors and nsample <= 32 (no CPU / torch fallback)")
+    idx = torch.empty(B, S, nsample, dtype=torch.int32, device=q.device)
+    with torch.cuda.device_of(q):
+        _cabi.call("rt_knn_expanded", B, S, s.shape[1], nsample, q.data_ptr(), s.data_ptr(), idx.data_ptr(),
+                   torch.cuda.current_stream(q.device).cuda_stream)
+    return idx.long()
 
 
 class WeightNet(nn.Module):

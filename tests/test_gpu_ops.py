@@ -145,3 +145,23 @@ def test_reference_kernels_agree_with_oracle_and_product():
         assert np.array_equal(r["knn_idx"], ki) and np.array_equal(r["knn_d2"], kd)
         feats = torch.randn((B, 8, S), generator=torch.Generator().manual_seed(1234)).numpy()
         assert np.array_equal(r["interp"], P.three_interpolate(feats, i3, r["interp_w"]))
+
+
+@pytest.mark.parametrize("n,m,k", [(1024, 1024, 16), (300, 1500, 16), (64, 33, 32), (10, 16, 16)])
+def test_knn_expanded_matches_torch_cpu_topk(n, m, k):
+    """Cost-volume kNN (model_utils.py:17-39, 85-99): same neighbour SETS as the reference's torch code on the CPU
+    wherever the k-th and (k+1)-th expanded-form distances differ; ascending order; ties -> lower index."""
+    from oracle import backbone_oracle
+    from ratrack_b200.model_utils import knn_point
+
+    q, s = _cloud(2, n, seed=11), _cloud(2, m, seed=12)
+    got = knn_point(k, _cu(s), _cu(q)).cpu()
+    dist = backbone_oracle.square_distance(torch.from_numpy(q), torch.from_numpy(s))
+    want = torch.topk(dist, k, dim=-1, largest=False, sorted=True)
+    dg = torch.gather(dist, 2, got)
+    assert (dg[..., 1:] >= dg[..., :-1]).all()                 # ascending in the reference's own distance values
+    assert torch.equal(dg, want[0])                            # same multiset of distances => same sets up to exact ties
+    kth = want[0][..., -1:]
+    strict = dist < kth                                        # everything strictly inside the k-th distance must be there
+    member = torch.zeros_like(dist, dtype=torch.bool).scatter_(2, got, True)
+    assert (member | ~strict).all()

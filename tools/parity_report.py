@@ -23,7 +23,7 @@ lines = []
 for batch, n in ((1, 256), (2, 1024), (4, 1024)):
     d = synthetic.make_batch(batch, n, seed=1234)
     c = {k: torch.from_numpy(v) for k, v in d.items()}
-    for fused in (False, 'simt', 'tc'):
+    for fused in (False, 'simt', 'tc-cv', 'tc'):
         net = Track4DBackbone(Args())
         sd = synthetic.make_state_dict(net, seed=1234)
         net.load_state_dict(sd, strict=False)
@@ -33,7 +33,7 @@ for batch, n in ((1, 256), (2, 1024), (4, 1024)):
         if fused:
             from ratrack_b200.engine import FusedBackbone
             net._engine = FusedBackbone(net)
-            net._engine.set_tensor_core_costvol(fused == 'tc')
+            net._engine.set_flags(costvol_tc=fused != 'simt', mlp_tc=fused == 'tc')
         with torch.no_grad():
             out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128, device="cuda"))
             knn = net.cost_volume_neighbours(t["pc1"], t["pc2"])
