@@ -238,18 +238,17 @@ def main():
         ev2[1].record()
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
-    tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(tm[0]), float(tm[1])
+    from ratrack_b200 import sharding
+    pairs_total, ms = sharding.job_throughput(B * a.steps, ms, device=dev)          # SUM of pairs, MAX of device time
+    _, ms_e2e = sharding.job_throughput(B * a.steps, ms_e2e, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks = _peaks()
-    value = world * B * a.steps / (ms * 1e-3)
-    e2e = world * B * a.steps / (ms_e2e * 1e-3)
+    value = pairs_total / (ms * 1e-3)
+    e2e = pairs_total / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * 4 for v in host.values())
     d2h = B * 3 * N * 4 + B * N * 4
     # ---- roofline of the dominant kernel (definitions: DESIGN.md "Kernels and rooflines") -----------

@@ -97,7 +97,7 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     w.xyz0 = c.take<float>(B2 * n * 3);
     w.ft0 = c.take<float>(B2 * n * 2);
     for (int l = 0; l < 3; ++l) w.xyz[l] = c.take<float>(B2 * S * 3);
-    w.temp = c.take<float>(B2 * (size_t)max(n, S));
+    w.temp = c.take<float>(3 * B2 * (size_t)max(n, S));   // one FPS scratch per level
     for (int l = 0; l < 3; ++l) w.fps[l] = c.take<int>(B2 * S);
     for (int l = 0; l < 3; ++l)
         for (int s = 0; s < 2; ++s) w.bq[l][s] = c.take<int>(B2 * S * kLevels[l].ns[s]);
@@ -174,6 +174,11 @@ struct rt_engine {
     int npoint;
     cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
     long long launches = 0;
+    // geometry runs beside the feature path on three streams: [0] the dependent FPS chain (latency-bound, 2B CTAs),
+    // [1] ball queries + three_nn (need only the FPS result of their level), [2] the cost-volume kNN
+    cudaStream_t geo_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
+                ev_nn = nullptr, ev_knn = nullptr;
     int flags = 3;                 // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
                                    // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow
     const int *last_status = nullptr;
@@ -181,20 +186,26 @@ struct rt_engine {
 
 namespace {
 
-// geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN
-int run_geometry(rt_engine *e, Ws &w, int b, int n, cudaStream_t st) {
+// geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN.
+// Every stage records an event the feature path (and the dependent geometry stages) wait on.
+int run_geometry(rt_engine *e, Ws &w, int b, int n) {
     const int B2 = 2 * b, S = e->npoint;
+    cudaStream_t s_fps = e->geo_stream[0], s_nbr = e->geo_stream[1], s_knn = e->geo_stream[2];
     const float *lvl_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
     const int lvl_n[3] = {n, S, S};
+    for (int g = 0; g < 3; ++g) cudaStreamWaitEvent(e->geo_stream[g], e->ev_in, 0);
     for (int l = 0; l < 3; ++l) {
-        RT_TRY(rt_launch_fill(w.temp, (long long)B2 * lvl_n[l], 1e10f, st));
-        RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp, w.fps[l], st));
-        RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], st));
+        RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
+        RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
+        RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], s_fps));
+        cudaEventRecord(e->ev_fps[l], s_fps);
+        cudaStreamWaitEvent(s_nbr, e->ev_fps[l], 0);
         for (int s = 0; s < 2; ++s) {
             const int ns = kLevels[l].ns[s];
-            cudaMemsetAsync(w.bq[l][s], 0, sizeof(int) * (size_t)B2 * S * ns, st);
-            RT_TRY(rt_ball_query(B2, lvl_n[l], S, kLevels[l].radius[s], ns, w.xyz[l], lvl_in[l], w.bq[l][s], st));
+            cudaMemsetAsync(w.bq[l][s], 0, sizeof(int) * (size_t)B2 * S * ns, s_nbr);
+            RT_TRY(rt_ball_query(B2, lvl_n[l], S, kLevels[l].radius[s], ns, w.xyz[l], lvl_in[l], w.bq[l][s], s_nbr));
         }
+        cudaEventRecord(e->ev_lvl[l], s_nbr);
         e->launches += 7;
     }
     // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
@@ -202,13 +213,19 @@ int run_geometry(rt_engine *e, Ws &w, int b, int n, cudaStream_t st) {
     const float *kn[3] = {w.xyz[2], w.xyz[1], w.xyz[0]};
     const int un[3] = {S, S, n};
     for (int l = 0; l < 3; ++l) {
-        RT_TRY(rt_three_nn(B2, un[l], S, unk[l], kn[l], w.nn_w[l], w.nn_idx[l], st));
-        RT_TRY(rt_launch_nn_weights((long long)B2 * un[l], w.nn_w[l], st));
+        RT_TRY(rt_three_nn(B2, un[l], S, unk[l], kn[l], w.nn_w[l], w.nn_idx[l], s_nbr));
+        RT_TRY(rt_launch_nn_weights((long long)B2 * un[l], w.nn_w[l], s_nbr));
         e->launches += 2;
     }
+    cudaEventRecord(e->ev_nn, s_nbr);
+    // cost-volume kNN: only after the FPS chain.  FPS is a chain of ~1500 dependent rounds on 2b CTAs; measured on
+    // B200, any kernel sharing its SMs stretches every round 2-3x (438 us instead of 148 us for FPS-1 with the kNN
+    // beside it), so the throughput-bound kNN is ordered behind it and overlaps the SA / FP kernels instead.
     const float *pc1 = w.xyz0, *pc2 = w.xyz0 + (size_t)b * n * 3;
-    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, st));
-    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, st));
+    cudaStreamWaitEvent(s_knn, e->ev_fps[2], 0);
+    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
+    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+    cudaEventRecord(e->ev_knn, s_knn);
     e->launches += 2;
     return RT_OK;
 }
@@ -249,6 +266,7 @@ int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSe
         pg.ldy = c1tot;
         RT_TRY(rt_launch_rowgemm(pg, st));
         e->launches += 1;
+        cudaStreamWaitEvent(st, e->ev_lvl[l], 0);   // FPS + ball query of this level
         const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
         int coff = 0;
         for (int s = 0; s < 2; ++s) {
@@ -278,6 +296,7 @@ int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSe
         e->launches += 1;
     }
     // feature propagation (lib/pointnet2_modules.py:129-158): interpolate, concat skip, 1-layer SharedMLP
+    cudaStreamWaitEvent(st, e->ev_nn, 0);
     {   // FP3: l2 <- l3
         RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
         RtRowGemm g{};
@@ -353,7 +372,9 @@ int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int c
         mlp_layer(pg, pk.proj[l], nullptr, k0, c1tot, RT_ACT_NONE);
         mlp_out(pg, w.proj, c1tot, 0, c1tot);
         pg.status = w.status;
+        if (l > 0) cudaStreamWaitEvent(st, e->ev_lvl[l - 1], 0);
         RT_TRY(rt_launch_mlp_tc(pg, st));
+        cudaStreamWaitEvent(st, e->ev_lvl[l], 0);   // FPS + ball query of this level
         const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
         int coff = 0;
         for (int s = 0; s < 2; ++s) {
@@ -378,6 +399,7 @@ int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int c
         RT_TRY(rt_launch_mlp_tc(lg, st));
         e->launches += 4;
     }
+    cudaStreamWaitEvent(st, e->ev_nn, 0);
     {   // FP3: l2 <- l3
         RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
         RtMlpTc m = mlp_rows((long long)clouds * S, w.interp, 64, 64);
@@ -515,6 +537,14 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
             return RT_ERR_INVALID;
         }
     }
+    for (int g = 0; g < 3; ++g) cudaStreamCreateWithFlags(&e->geo_stream[g], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
+    for (int l = 0; l < 3; ++l) {
+        cudaEventCreateWithFlags(&e->ev_lvl[l], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_fps[l], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&e->ev_nn, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_knn, cudaEventDisableTiming);
     const int rc = build_packs(e);
     if (rc != RT_OK) {
         if (e->arena) cudaFree(e->arena);
@@ -528,6 +558,12 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
 RT_API void rt_engine_destroy(rt_engine *e) {
     if (!e) return;
     if (e->arena) cudaFree(e->arena);
+    for (int g = 0; g < 3; ++g)
+        if (e->geo_stream[g]) cudaStreamDestroy(e->geo_stream[g]);
+    cudaEvent_t evs[9] = {e->ev_in, e->ev_lvl[0], e->ev_lvl[1], e->ev_lvl[2], e->ev_nn, e->ev_knn,
+                          e->ev_fps[0], e->ev_fps[1], e->ev_fps[2]};
+    for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -591,7 +627,9 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft1, w.ft0, 2, 0, st));
     RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft2, w.ft0 + half2, 2, 0, st));
     e->launches += 4;
-    RT_TRY(run_geometry(e, w, b, n, st));
+    // fork: geometry depends only on xyz, so it runs on its own stream and the feature path joins stage by stage
+    cudaEventRecord(e->ev_in, st);
+    RT_TRY(run_geometry(e, w, b, n));
 
     // feature_extraction_head: pn_head over both clouds of every pair at once (track4d.py:102-106)
     const bool tc_mlp = (e->flags & 2) != 0;
@@ -636,6 +674,7 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
     }
+    cudaStreamWaitEvent(st, e->ev_knn, 0);   // join: everything the geometry stream produced is now ordered before `st`
     if (e->flags & 1) {
         if (e->prof_start) cudaEventRecord(e->prof_start, st);
         RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,

@@ -167,15 +167,28 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
             if (cp >= ncp) break;
             const int cloud = (int)(cp / a.npts);
             float acc = 0.0f;
-            for (int s = 0; s < a.ns; ++s) {
-                const float *h2 = s_h2 + (p * a.ns + s) * 8;
-                float w = bc;
+            for (int s0 = 0; s0 < a.ns; s0 += 8) {
+                // issue the (gathered) value loads of 8 neighbours before any arithmetic: memory-level parallelism
+                float vv[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
-                w = fmaxf(w, 0.0f);
-                const float v = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
+                for (int u = 0; u < 8; ++u) {
+                    const int s = s0 + u;
+                    vv[u] = 0.0f;
+                    if (s < a.ns)
+                        vv[u] = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
                                            : __ldg(a.v + (cp * a.ns + s) * a.c + ch);
-                acc = fmaf(w, v, acc);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int s = s0 + u;
+                    if (s < a.ns) {
+                        const float *h2 = s_h2 + (p * a.ns + s) * 8;
+                        float w = bc;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
+                        acc = fmaf(fmaxf(w, 0.0f), vv[u], acc);
+                    }
+                }
             }
             a.out[cp * a.c + ch] = acc;
         }
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(384) gru_kernel(int bsz, const float *__restri
         const float *wi = wih_t + (long long)l * 128 * 384 + t;
         const float *wh = whh_t + (long long)l * 128 * 384 + t;
         float gi = 0.0f, gh = 0.0f;
-#pragma unroll 8
+#pragma unroll 32
         for (int k = 0; k < 128; ++k) {
             gi = fmaf(__ldg(wi + k * 384), s_in[k], gi);
             gh = fmaf(__ldg(wh + k * 384), s_h[k], gh);

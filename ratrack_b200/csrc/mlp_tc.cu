@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int MT_WORKER_WARPS = 4;
+constexpr int MT_WORKER_WARPS = 8;   // two per TMEM lane quarter: they split the 16-column chunks of a row between them
 constexpr int MT_THREADS = 32 * (MT_WORKER_WARPS + 1);
 constexpr float MT_WINV = 1.0f / 1024.0f;
 
@@ -91,6 +91,36 @@ __device__ __forceinline__ void mt_store16(const float *v, uint32_t t_hi, uint32
     mt_st8(t_lo, lo);
 }
 
+// max over the NS consecutive lanes of a centre for 16 values per lane.  Halving butterfly: at every step a lane
+// keeps half of its values and hands the other half to its partner, so NS-lane groups need ~16 shuffles, not 16*log2(NS).
+// On return v[0..cnt) are the maxima of columns col0 .. col0+cnt of the chunk; lanes with `writer` store them.
+template <int NS>
+__device__ __forceinline__ void mt_group_max(float *v, int lane, int &col0, int &cnt, bool &writer) {
+    col0 = 0;
+    writer = true;
+    constexpr int STEPS = NS == 32 ? 5 : NS == 16 ? 4 : NS == 8 ? 3 : NS == 4 ? 2 : NS == 2 ? 1 : 0;
+    int c = 16;
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+        const int off = NS >> (st + 1);
+        const int half = 16 >> (st + 1);   // compile-time after unrolling
+        if (half >= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = up ? v[i] : v[i + half], keep = up ? v[i + half] : v[i];
+                v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+            }
+            col0 += up ? half : 0;
+            c = half;
+        } else {
+            v[0] = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], off));
+            writer = writer && (lane & off) == 0;
+        }
+    }
+    cnt = c;
+}
+
 __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_a, bar_d;
@@ -109,6 +139,15 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         const int n16 = (w_off[l + 1] - w_off[l]) / 16;
         for (int i = threadIdx.x; i < n16; i += MT_THREADS) dst[i] = __ldg(src + i);
     }
+    // gather mode: xyz columns of the first conv and its bias -> shared memory, [wx | wy | wz | b1][c1]
+    float *s_gc = reinterpret_cast<float *>(smem + w_off[RT_MLP_MAX_LAYERS]);
+    if (a.load_mode == RT_MLP_LOAD_GATHER)
+        for (int i = threadIdx.x; i < a.c1; i += MT_THREADS) {
+            s_gc[i] = __ldg(a.wx + i * 3 + 0);
+            s_gc[a.c1 + i] = __ldg(a.wx + i * 3 + 1);
+            s_gc[2 * a.c1 + i] = __ldg(a.wx + i * 3 + 2);
+            s_gc[3 * a.c1 + i] = __ldg(a.b1 + i);
+        }
     if (threadIdx.x == 0) {
         rt_mbar_init(&bar_a, MT_WORKER_WARPS);
         rt_mbar_init(&bar_d, 1);
@@ -149,8 +188,9 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         __syncwarp();
     } else {
         // ===== worker warps: one thread per row =====
-        const int row_in_tile = 32 * warp + lane;
-        const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+        const int q = warp & 3, hlf = warp >> 2;        // TMEM lane quarter, chunk parity
+        const int row_in_tile = 32 * q + lane;
+        const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         uint32_t d_phase = 0;
         float amax = 0.0f;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -165,6 +205,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     const int ks = a.seg[s].k;
                     const bool vec = (a.seg[s].ldx & 3) == 0;
                     for (int o = 0; o < ks; o += 16, c0 += 16) {
+                        if (((c0 >> 4) & 1) != hlf) continue;
                         float v[16];
                         if (vec && o + 16 <= ks) {
 #pragma unroll
@@ -188,7 +229,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                 const float dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(a.xyz_c + cp * 3 + 1);
                 const float dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(a.xyz_c + cp * 3 + 2);
                 const float *yrow = a.y + g * a.ldy + a.yoff;
-                for (int c0 = 0; c0 < a.c1; c0 += 16) {
+                for (int c0 = 16 * hlf; c0 < a.c1; c0 += 32) {
                     float v[16];
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
@@ -197,9 +238,8 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float *w = a.wx + (c0 + i) * 3;
-                        float t = v[i] + fmaf(__ldg(w + 2), dz, fmaf(__ldg(w + 1), dy, __ldg(w + 0) * dx));
-                        t += __ldg(a.b1 + c0 + i);
+                        float t = v[i] + fmaf(s_gc[2 * a.c1 + c0 + i], dz, fmaf(s_gc[a.c1 + c0 + i], dy, s_gc[c0 + i] * dx));
+                        t += s_gc[3 * a.c1 + c0 + i];
                         v[i] = fmaxf(t, 0.0f);
                     }
                     mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
@@ -218,7 +258,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                 const float *bias = a.layer[l].bias;
                 const float *cb = (l == 0 && a.cloud_bias) ? a.cloud_bias + (rc / a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
                 const bool last = l == a.nlayers - 1;
-                for (int c0 = 0; c0 < n; c0 += 16) {
+                for (int c0 = 16 * hlf; c0 < n; c0 += 32) {
                     uint32_t r[16];
                     mt_ld16(tD + lane_base + c0, r);
                     float v[16];
@@ -246,15 +286,21 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                         }
                     } else {
                         // max over the ns consecutive rows (= lanes) of a centre; 128 % ns == 0 so groups never straddle tiles
-                        for (int off = a.ns >> 1; off >= 1; off >>= 1) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], off));
+                        int col0 = 0, cnt = 16;
+                        bool writer = true;
+                        switch (a.ns) {
+                            case 32: mt_group_max<32>(v, lane, col0, cnt, writer); break;
+                            case 16: mt_group_max<16>(v, lane, col0, cnt, writer); break;
+                            case 8: mt_group_max<8>(v, lane, col0, cnt, writer); break;
+                            case 4: mt_group_max<4>(v, lane, col0, cnt, writer); break;
+                            case 2: mt_group_max<2>(v, lane, col0, cnt, writer); break;
+                            default: break;
                         }
-                        if (valid && (lane & (a.ns - 1)) == 0) {
-                            float *o = a.out + (row / a.ns) * a.ldo + a.ooff + c0;
+                        if (valid && writer) {
+                            float *o = a.out + (row / a.ns) * a.ldo + a.ooff + c0 + col0;
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                if (c0 + i < a.n_out) o[i] = v[i];
+                                if (i < cnt && c0 + col0 + i < a.n_out) o[i] = v[i];
                         }
                     }
                 }
@@ -319,13 +365,14 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // resident CTAs per SM: bounded by TMEM columns, shared memory and (to keep tail effects small) 4
     int per_sm = 512 / cols;
-    const int by_smem = (220 * 1024) / (wbytes + 2048);
+    const int gc_bytes = a.load_mode == RT_MLP_LOAD_GATHER ? 16 * a.c1 : 0;
+    const int by_smem = (220 * 1024) / (wbytes + gc_bytes + 2048);
     per_sm = per_sm < by_smem ? per_sm : by_smem;
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);   // 72 registers x 288 threads: 3 CTAs fill the register file
     const long long ntiles = (a.rows + 127) / 128;
     long long grid = (long long)sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    mlp_tc_kernel<<<(int)grid, MT_THREADS, wbytes, st>>>(a);
+    mlp_tc_kernel<<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
     return rt_check_launch("mlp_tc_kernel");
 }
 

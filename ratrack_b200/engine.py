@@ -241,6 +241,17 @@ def roofline_of_dominant(batch, points, dom_ms, peaks):
     avg_ms = sum(dom_ms) / max(1, len(dom_ms))
     ach = flops / (avg_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_sustained") or peaks["bf16"]
-    return {"kernel": "cost-volume MLP (2 x [rows x 256 x 256], LeakyReLU)", "bound": "tensor", "achieved": ach,
-            "peak": peak, "peak_source": peaks["src"] + " dense bf16 (sustained)", "unit": "TFLOP/s",
-            "frac": ach / peak, "traffic": None, "avg_launch_ms": avg_ms, "flops_per_launch": flops}
+    traffic = None   # dram bytes of one launch from the committed ncu --set full capture, when it is this configuration
+    try:
+        import json
+        import os
+        t = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                                        "costvol_traffic.json")))
+        if t["batch"] == batch and t["points"] == points:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return {"kernel": "costvol_tc_kernel: gather + cost-volume MLP (2 x [rows x 256 x 256], LeakyReLU) + WeightNet sum",
+            "bound": "tensor", "achieved": ach, "peak": peak, "peak_source": peaks["src"] + " dense bf16 (sustained)",
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "avg_launch_ms": avg_ms, "flops_per_launch": flops,
+            "note": "achieved counts the fp32-accurate useful FLOPs; the tensor pipe executes 3x that (fp16 hi/lo split products)"}
