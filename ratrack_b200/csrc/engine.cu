@@ -177,6 +177,9 @@ struct rt_engine {
     // geometry runs beside the feature path on three streams: [0] the dependent FPS chain (latency-bound, 2B CTAs),
     // [1] ball queries + three_nn (need only the FPS result of their level), [2] the cost-volume kNN
     cudaStream_t geo_stream[3] = {nullptr, nullptr, nullptr};
+    // output stream: API-layout transposes and the cls head hang off the feature path, nothing waits for them until the end
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr;
     cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
                 ev_nn = nullptr, ev_knn = nullptr;
     int flags = 3;                 // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
@@ -538,6 +541,11 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
         }
     }
     for (int g = 0; g < 3; ++g) cudaStreamCreateWithFlags(&e->geo_stream[g], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e->ev_feat, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_cor, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_prop, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_aux, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
     for (int l = 0; l < 3; ++l) {
         cudaEventCreateWithFlags(&e->ev_lvl[l], cudaEventDisableTiming);
@@ -560,8 +568,9 @@ RT_API void rt_engine_destroy(rt_engine *e) {
     if (e->arena) cudaFree(e->arena);
     for (int g = 0; g < 3; ++g)
         if (e->geo_stream[g]) cudaStreamDestroy(e->geo_stream[g]);
-    cudaEvent_t evs[9] = {e->ev_in, e->ev_lvl[0], e->ev_lvl[1], e->ev_lvl[2], e->ev_nn, e->ev_knn,
-                          e->ev_fps[0], e->ev_fps[1], e->ev_fps[2]};
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    cudaEvent_t evs[13] = {e->ev_in, e->ev_lvl[0], e->ev_lvl[1], e->ev_lvl[2], e->ev_nn, e->ev_knn,
+                           e->ev_fps[0], e->ev_fps[1], e->ev_fps[2], e->ev_feat, e->ev_cor, e->ev_prop, e->ev_aux};
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
     delete e;
@@ -643,11 +652,16 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         RT_TRY(run_head(e, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     }
     RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
-    // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95)
-    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat, 128, 0, f1, 256, 0, st));
-    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat + half128, 128, 0, f2, 256, 0, st));
-    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax, f1, 256, 128, st));
-    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax + (size_t)b * 128, f2, 256, 128, st));
+    // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95): off the critical path
+    cudaStream_t aux = tc_mlp ? e->aux_stream : st;
+    if (aux != st) {
+        cudaEventRecord(e->ev_feat, st);
+        cudaStreamWaitEvent(aux, e->ev_feat, 0);
+    }
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat, 128, 0, f1, 256, 0, aux));
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat + half128, 128, 0, f2, 256, 0, aux));
+    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax, f1, 256, 128, aux));
+    RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax + (size_t)b * 128, f2, 256, 128, aux));
     e->launches += 5;
 
     // FeatureCorrelator (model_utils.py:193-250)
@@ -702,10 +716,14 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         ws.v = w.cost1; ws.out = w.cor;
         RT_TRY(rt_launch_weighted_sum(ws, st));
     }
-    RT_TRY(rt_launch_rows_to_cm(b, 256, n, w.cor, 256, 0, cor, 256, 0, st));
+    if (aux != st) {
+        cudaEventRecord(e->ev_cor, st);
+        cudaStreamWaitEvent(aux, e->ev_cor, 0);
+    }
+    RT_TRY(rt_launch_rows_to_cm(b, 256, n, w.cor, 256, 0, cor, 256, 0, aux));
     e->launches += 10;
 
-    // FlowDecoder (model_utils.py:281-305): cls head on the cost volume
+    // FlowDecoder (model_utils.py:281-305): cls head on the cost volume (independent of the mse head: output stream)
     const ClsW &cp = e->w.cp;
     const long long pts = (long long)b * n;
     if (tc_mlp) {
@@ -715,13 +733,13 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         mlp_layer(m, e->packs.cp[2], cp.b3, 64, 32, RT_ACT_RELU);
         mlp_out(m, w.h3, 32, 0, 32);
         m.status = w.status;
-        RT_TRY(rt_launch_mlp_tc(m, st));
+        RT_TRY(rt_launch_mlp_tc(m, aux));
     } else {
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 128, w.cor, 256, 256, cp.w1, cp.b1, RT_ACT_RELU, w.h1, 128), st));
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 64, w.h1, 128, 128, cp.w2, cp.b2, RT_ACT_RELU, w.h2, 64), st));
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, cp.w3, cp.b3, RT_ACT_RELU, w.h3, 32), st));
     }
-    RT_TRY(rt_launch_cls_tail(pts, w.h3, cp.w4, cp.lin_w, cp.lin_b, cls, st));
+    RT_TRY(rt_launch_cls_tail(pts, w.h3, cp.w4, cp.lin_w, cp.lin_b, cls, aux));
     // second PNHead over embeddings = cat(feature1, pc1_features, cor_features) on pc1's geometry
     const HeadW &mse = e->w.mse;
     RT_TRY(rt_launch_cloud_matvec(b, 32, 128, mse.wf_glob, 128, w.gmax, 128, nullptr, w.cb_a, st));
@@ -733,7 +751,12 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
                          RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
         RT_TRY(run_head(e, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     }
-    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, st));
+    if (aux != st) {
+        cudaEventRecord(e->ev_prop, st);
+        cudaStreamWaitEvent(aux, e->ev_prop, 0);
+    }
+    RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, aux));
+    if (aux != st) cudaEventRecord(e->ev_aux, aux);
     RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
     RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, st));
     // FlowPredictor on cat(prop_features, broadcast GRU output)
@@ -758,6 +781,7 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     }
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
     e->launches += 14;
+    if (aux != st) cudaStreamWaitEvent(st, e->ev_aux, 0);   // join the output stream
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     return rt_check_launch("backbone_forward");

@@ -18,6 +18,8 @@
 //   * the cloud's xyz is staged once into shared memory by the bulk-copy engine (TMA, UBLKCP)
 //     for the broadcast read of the newly selected point each round.
 //   A generic kernel (any n) keeps the same ordering rule with 64-bit packed keys.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -76,18 +78,30 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *_
 
     for (int j = 1; j < m; ++j) {
         const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
-        float best = -1.0f;
-        int besti = 0;
+        // per-thread arg-max as a tournament over the priority-ordered slots (left wins ties == "first strict
+        // maximum" of the reference's scan), so the dependent chain is log2(PPT) deep instead of PPT
+        float cd[PPT];
+        int ci[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
             const float d = rt_sqdist(px[s], py[s], pz[s], x1, y1, z1);
             // padding slots hold td = -2 and stay there (fminf keeps the smaller)
             const float d2 = fminf(d, td[s]);
             td[s] = d2;
-            const bool up = d2 > best;
-            besti = up ? pk[s] : besti;
-            best = up ? d2 : best;
+            cd[s] = (d2 > -1.0f) ? d2 : -2.0f;   // the reference's best starts at -1: NaN / padding never win
+            ci[s] = pk[s];
         }
+#pragma unroll
+        for (int stride = 1; stride < PPT; stride *= 2)
+#pragma unroll
+            for (int i = 0; i + stride < PPT; i += 2 * stride)
+                if (cd[i + stride] > cd[i]) {
+                    cd[i] = cd[i + stride];
+                    ci[i] = ci[i + stride];
+                }
+        const bool any = cd[0] > -1.0f;
+        const float best = any ? cd[0] : -1.0f;
+        const int besti = any ? ci[0] : 0;
         const uint32_t key = rt_float_ordered(best);
         const uint32_t wmax = rt_redux_max_u32(key);
         const uint32_t vote = __ballot_sync(0xffffffffu, key == wmax);
@@ -191,21 +205,32 @@ RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, flo
     cudaStream_t st = (cudaStream_t)stream;
     const int bs = rt_ref_block_size(n);
     const int ph = (n + bs - 1) / bs;
-    // register-resident variants: T = 128 threads (4 warps = one per SM sub-partition), Q = bs/T
+    // register-resident variants: T threads, Q = bs / T residues per thread, PH = ceil(n / bs) passes.
+    // T = 256 halves the per-thread work of a round (the rounds are a pure latency chain); RT_FPS_THREADS=128
+    // selects the 4-warp variant for A/B timing.
+    static int pref_t = 0;
+    if (!pref_t) {
+        const char *env = getenv("RT_FPS_THREADS");
+        pref_t = (env && atoi(env) == 128) ? 128 : 256;
+    }
+#define RT_FPS_CASE(TT, QQ, PP) \
+    if (t == TT && q == QQ && ph == PP) return launch_reg<TT, QQ, PP>(b, n, m, xyz, temp, idx, st);
     if (bs >= 128 && ph <= 4) {
-        const int q = bs / 128;
-#define RT_FPS_CASE(QQ, PP) \
-    if (q == QQ && ph == PP) return launch_reg<128, QQ, PP>(b, n, m, xyz, temp, idx, st);
-        RT_FPS_CASE(1, 1) RT_FPS_CASE(1, 2)
-        RT_FPS_CASE(2, 1) RT_FPS_CASE(2, 2)
-        RT_FPS_CASE(4, 1) RT_FPS_CASE(4, 2)
-        RT_FPS_CASE(8, 1) RT_FPS_CASE(8, 2)
-#undef RT_FPS_CASE
-        if (q == 8 && ph <= 4) {  // 2048 < n <= 4096: 256 threads x 16 points
+        const int t = (bs >= 256 && pref_t == 256) ? 256 : 128;
+        const int q = bs / t;
+        RT_FPS_CASE(256, 1, 1) RT_FPS_CASE(256, 1, 2)
+        RT_FPS_CASE(256, 2, 1) RT_FPS_CASE(256, 2, 2)
+        RT_FPS_CASE(256, 4, 1) RT_FPS_CASE(256, 4, 2) RT_FPS_CASE(256, 4, 3) RT_FPS_CASE(256, 4, 4)
+        RT_FPS_CASE(128, 1, 1) RT_FPS_CASE(128, 1, 2)
+        RT_FPS_CASE(128, 2, 1) RT_FPS_CASE(128, 2, 2)
+        RT_FPS_CASE(128, 4, 1) RT_FPS_CASE(128, 4, 2)
+        RT_FPS_CASE(128, 8, 1) RT_FPS_CASE(128, 8, 2)
+        if (bs == 1024 && ph <= 4) {  // 2048 < n <= 4096 with the 128-thread preference: 256 threads x 16 points
             if (ph == 3) return launch_reg<256, 4, 3>(b, n, m, xyz, temp, idx, st);
             return launch_reg<256, 4, 4>(b, n, m, xyz, temp, idx, st);
         }
     }
+#undef RT_FPS_CASE
     int logbs = 0;
     while ((1 << logbs) < bs) ++logbs;
     RT_REQUIRE((n >> logbs) < (1 << 21), "furthest_point_sampling: n too large");
