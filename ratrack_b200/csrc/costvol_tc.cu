@@ -131,6 +131,37 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// Per-row operands of a tile's layer 1.  They are fetched one tile ahead (head) and one 16-channel chunk ahead (body)
+// so the index -> xyz -> P1/P2 load chain hides under the MMA phases instead of stalling the prologue.
+struct CtRow {
+    int p, pc;
+    bool valid;
+    size_t g2;
+    float dx, dy, dz;
+    float4 u[4], v[4];   // chunk of P2[neighbour] and P1[point]
+};
+__device__ __forceinline__ void ct_issue_chunk(const CostVolTcArgs &a, const CtRow &r, int c0, float4 *u, float4 *v) {
+    const float4 *p1r = reinterpret_cast<const float4 *>(a.p1 + (size_t)r.pc * CT_C + c0);
+    const float4 *p2r = reinterpret_cast<const float4 *>(a.p2 + r.g2 * CT_C + c0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        u[g] = __ldg(p2r + g);
+        v[g] = __ldg(p1r + g);
+    }
+}
+__device__ __forceinline__ void ct_issue_row(const CostVolTcArgs &a, int tile, int row, int cbeg, CtRow &r) {
+    r.p = tile * CT_PTS + (row >> 4);
+    r.valid = r.p < a.total_pts;
+    r.pc = r.valid ? r.p : a.total_pts - 1;
+    const int cloud = r.pc / a.n;
+    const int nbr = __ldg(a.knn + (size_t)r.pc * CT_NS + (row & 15));
+    r.g2 = (size_t)cloud * a.n + nbr;
+    r.dx = __ldg(a.xyz2 + r.g2 * 3 + 0) - __ldg(a.xyz1 + (size_t)r.pc * 3 + 0);
+    r.dy = __ldg(a.xyz2 + r.g2 * 3 + 1) - __ldg(a.xyz1 + (size_t)r.pc * 3 + 1);
+    r.dz = __ldg(a.xyz2 + r.g2 * 3 + 2) - __ldg(a.xyz1 + (size_t)r.pc * 3 + 2);
+    ct_issue_chunk(a, r, cbeg, r.u, r.v);
+}
+
 __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_stage = smem + SM_STAGES;
@@ -253,17 +284,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
         const int cbeg = 128 * hlf;
         uint32_t d_phase = 0;
         float amax = 0.0f;
+        CtRow cur;
+        if ((int)blockIdx.x < ntiles) ct_issue_row(a, blockIdx.x, row, cbeg, cur);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // ---------- layer 1 ----------
-            const int p = tile * CT_PTS + (row >> 4);
-            const bool valid = p < a.total_pts;
-            const int pc = valid ? p : a.total_pts - 1;
-            const int cloud = pc / a.n;
-            const int nbr = __ldg(a.knn + (size_t)pc * CT_NS + (row & 15));
-            const size_t g2 = (size_t)cloud * a.n + nbr;
-            const float dx = __ldg(a.xyz2 + g2 * 3 + 0) - __ldg(a.xyz1 + (size_t)pc * 3 + 0);
-            const float dy = __ldg(a.xyz2 + g2 * 3 + 1) - __ldg(a.xyz1 + (size_t)pc * 3 + 1);
-            const float dz = __ldg(a.xyz2 + g2 * 3 + 2) - __ldg(a.xyz1 + (size_t)pc * 3 + 2);
+            // ---------- layer 1 ----------  (row operands + first chunk were issued during the previous tile)
+            const int p = cur.p;
+            const bool valid = cur.valid;
+            const float dx = cur.dx, dy = cur.dy, dz = cur.dz;
             if (hlf == 0) {
                 // WeightNet trunk 3 -> 8 -> 8 (ReLU), result = A operand (K = 8, padded to 16) of the last-layer MMA
                 float h1[8], h2[8];
@@ -289,27 +316,32 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 *reinterpret_cast<uint4 *>(s_aw + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(s_aw + CT_AW_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            {
-                const float4 *p1r = reinterpret_cast<const float4 *>(a.p1 + (size_t)pc * CT_C);
-                const float4 *p2r = reinterpret_cast<const float4 *>(a.p2 + g2 * CT_C);
-                for (int c0 = cbeg; c0 < cbeg + 128; c0 += 16) {
-                    uint32_t hi[8], lo[8];
+            for (int c0 = cbeg; c0 < cbeg + 128; c0 += 16) {
+                float4 un[4], vn[4];
+                if (c0 + 16 < cbeg + 128) ct_issue_chunk(a, cur, c0 + 16, un, vn);   // next chunk's loads before this chunk's math
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int c = c0 + 4 * g;
+                    const float4 u = cur.u[g], v1 = cur.v[g];
+                    const float4 wx = *reinterpret_cast<const float4 *>(s_wx + c);
+                    const float4 wy = *reinterpret_cast<const float4 *>(s_wx + CT_C + c);
+                    const float4 wz = *reinterpret_cast<const float4 *>(s_wx + 2 * CT_C + c);
+                    const float x0 = leaky01(u.x + fmaf(wz.x, dz, fmaf(wy.x, dy, wx.x * dx)) + v1.x);
+                    const float x1 = leaky01(u.y + fmaf(wz.y, dz, fmaf(wy.y, dy, wx.y * dx)) + v1.y);
+                    const float x2 = leaky01(u.z + fmaf(wz.z, dz, fmaf(wy.z, dy, wx.z * dx)) + v1.z);
+                    const float x3 = leaky01(u.w + fmaf(wz.w, dz, fmaf(wy.w, dy, wx.w * dx)) + v1.w);
+                    split2(x0, x1, hi[2 * g], lo[2 * g], amax);
+                    split2(x2, x3, hi[2 * g + 1], lo[2 * g + 1], amax);
+                }
+                ct_st8(tAhi + lane_base + c0 / 2, hi);
+                ct_st8(tAlo + lane_base + c0 / 2, lo);
+                if (c0 + 16 < cbeg + 128) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int c = c0 + 4 * g;
-                        const float4 u = __ldg(p2r + c / 4), v1 = __ldg(p1r + c / 4);
-                        const float4 wx = *reinterpret_cast<const float4 *>(s_wx + c);
-                        const float4 wy = *reinterpret_cast<const float4 *>(s_wx + CT_C + c);
-                        const float4 wz = *reinterpret_cast<const float4 *>(s_wx + 2 * CT_C + c);
-                        const float x0 = leaky01(u.x + fmaf(wz.x, dz, fmaf(wy.x, dy, wx.x * dx)) + v1.x);
-                        const float x1 = leaky01(u.y + fmaf(wz.y, dz, fmaf(wy.y, dy, wx.y * dx)) + v1.y);
-                        const float x2 = leaky01(u.z + fmaf(wz.z, dz, fmaf(wy.z, dy, wx.z * dx)) + v1.z);
-                        const float x3 = leaky01(u.w + fmaf(wz.w, dz, fmaf(wy.w, dy, wx.w * dx)) + v1.w);
-                        split2(x0, x1, hi[2 * g], lo[2 * g], amax);
-                        split2(x2, x3, hi[2 * g + 1], lo[2 * g + 1], amax);
+                        cur.u[g] = un[g];
+                        cur.v[g] = vn[g];
                     }
-                    ct_st8(tAhi + lane_base + c0 / 2, hi);
-                    ct_st8(tAlo + lane_base + c0 / 2, lo);
                 }
             }
             ct_st_wait();
@@ -339,6 +371,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             ct_fence_before();
             __syncwarp();
             if (lane == 0) rt_mbar_arrive(bar_a);
+            // next tile's index / xyz / first P1,P2 chunk: in flight during the layer-3 MMAs and the final epilogue
+            const int p_out = p;
+            const bool valid_out = valid;
+            if (tile + (int)gridDim.x < ntiles) ct_issue_row(a, tile + gridDim.x, row, cbeg, cur);
 
             // ---------- final epilogue: LeakyReLU(layer 3) * ReLU(WeightNet), summed over the 16 neighbours ----------
             ct_mbar_wait(bar_d, d_phase);
@@ -381,9 +417,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                     const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
                     v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
                 }
-                if (valid) {
+                if (valid_out) {
                     const int col = c0 + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-                    *reinterpret_cast<float2 *>(a.out + (size_t)p * CT_C + col) = make_float2(v[0], v[1]);
+                    *reinterpret_cast<float2 *>(a.out + (size_t)p_out * CT_C + col) = make_float2(v[0], v[1]);
                 }
             }
             ct_fence_before();

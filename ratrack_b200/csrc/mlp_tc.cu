@@ -121,6 +121,26 @@ __device__ __forceinline__ void mt_group_max(float *v, int lane, int &col0, int 
     cnt = c;
 }
 
+// Gather-mode operands of one row, fetched one tile ahead so that the index -> xyz -> projection-row load chain of
+// tile t+1 (three dependent L2 round trips) runs underneath the MMA and epilogue of tile t.
+struct MtGatherRow {
+    const float *yrow;   // projected row of the neighbour (this scale's columns)
+    float dx, dy, dz;
+};
+__device__ __forceinline__ void mt_gather_issue(const RtMlpTc &a, long long tile, int row_in_tile, MtGatherRow &r) {
+    long long row = tile * 128 + row_in_tile;
+    if (row >= a.rows) row = a.rows - 1;
+    const long long cp = row / a.ns;                 // (cloud, centre)
+    const int cloud = (int)(cp / a.npts);
+    const int j = __ldg(a.idx + row);
+    const long long g = (long long)cloud * a.n_in + j;
+    r.dx = __ldg(a.xyz_in + g * 3 + 0) - __ldg(a.xyz_c + cp * 3 + 0);
+    r.dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(a.xyz_c + cp * 3 + 1);
+    r.dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(a.xyz_c + cp * 3 + 2);
+    r.yrow = a.y + g * a.ldy + a.yoff;
+}
+
+template <int LOAD_MODE>
 __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_a, bar_d;
@@ -139,15 +159,16 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         const int n16 = (w_off[l + 1] - w_off[l]) / 16;
         for (int i = threadIdx.x; i < n16; i += MT_THREADS) dst[i] = __ldg(src + i);
     }
-    // gather mode: xyz columns of the first conv and its bias -> shared memory, [wx | wy | wz | b1][c1]
-    float *s_gc = reinterpret_cast<float *>(smem + w_off[RT_MLP_MAX_LAYERS]);
-    if (a.load_mode == RT_MLP_LOAD_GATHER)
-        for (int i = threadIdx.x; i < a.c1; i += MT_THREADS) {
-            s_gc[i] = __ldg(a.wx + i * 3 + 0);
-            s_gc[a.c1 + i] = __ldg(a.wx + i * 3 + 1);
-            s_gc[2 * a.c1 + i] = __ldg(a.wx + i * 3 + 2);
-            s_gc[3 * a.c1 + i] = __ldg(a.b1 + i);
-        }
+    // per-layer biases -> shared memory (zeros when a layer has none), 256 floats per layer
+    float *s_bias = reinterpret_cast<float *>(smem + w_off[RT_MLP_MAX_LAYERS]);
+    for (int l = 0; l < a.nlayers; ++l)
+        for (int i = threadIdx.x; i < a.layer[l].n; i += MT_THREADS)
+            s_bias[l * 256 + i] = a.layer[l].bias ? __ldg(a.layer[l].bias + i) : 0.0f;
+    // gather mode: (wx, wy, wz, b1) of every first-conv channel as one float4
+    float4 *s_gc = reinterpret_cast<float4 *>(s_bias + RT_MLP_MAX_LAYERS * 256);
+    if (LOAD_MODE == RT_MLP_LOAD_GATHER)
+        for (int i = threadIdx.x; i < a.c1; i += MT_THREADS)
+            s_gc[i] = make_float4(__ldg(a.wx + i * 3 + 0), __ldg(a.wx + i * 3 + 1), __ldg(a.wx + i * 3 + 2), __ldg(a.b1 + i));
     if (threadIdx.x == 0) {
         rt_mbar_init(&bar_a, MT_WORKER_WARPS);
         rt_mbar_init(&bar_d, 1);
@@ -193,12 +214,14 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         uint32_t d_phase = 0;
         float amax = 0.0f;
+        MtGatherRow pre;
+        if (LOAD_MODE == RT_MLP_LOAD_GATHER && (long long)blockIdx.x < ntiles) mt_gather_issue(a, blockIdx.x, row_in_tile, pre);
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long row = tile * 128 + row_in_tile;
             const bool valid = row < a.rows;
             const long long rc = valid ? row : a.rows - 1;
             // ---------- layer-0 input ----------
-            if (a.load_mode == RT_MLP_LOAD_ROWS) {
+            if (LOAD_MODE == RT_MLP_LOAD_ROWS) {
                 int c0 = 0;
                 for (int s = 0; s < a.nseg; ++s) {
                     const float *x = a.seg[s].x + rc * a.seg[s].ldx;
@@ -221,25 +244,18 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     }
                 }
             } else {
-                const long long cp = rc / a.ns;                 // (cloud, centre)
-                const int cloud = (int)(cp / a.npts);
-                const int j = __ldg(a.idx + rc);
-                const long long g = (long long)cloud * a.n_in + j;
-                const float dx = __ldg(a.xyz_in + g * 3 + 0) - __ldg(a.xyz_c + cp * 3 + 0);
-                const float dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(a.xyz_c + cp * 3 + 1);
-                const float dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(a.xyz_c + cp * 3 + 2);
-                const float *yrow = a.y + g * a.ldy + a.yoff;
+                // index, xyz difference and row pointer were fetched during the previous tile; the row itself now
                 for (int c0 = 16 * hlf; c0 < a.c1; c0 += 32) {
                     float v[16];
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(yrow + c0) + gq);
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(pre.yrow + c0) + gq);
                         v[4 * gq] = t.x; v[4 * gq + 1] = t.y; v[4 * gq + 2] = t.z; v[4 * gq + 3] = t.w;
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float t = v[i] + fmaf(s_gc[2 * a.c1 + c0 + i], dz, fmaf(s_gc[a.c1 + c0 + i], dy, s_gc[c0 + i] * dx));
-                        t += s_gc[3 * a.c1 + c0 + i];
+                        const float4 w = s_gc[c0 + i];
+                        const float t = v[i] + fmaf(w.z, pre.dz, fmaf(w.y, pre.dy, w.x * pre.dx)) + w.w;
                         v[i] = fmaxf(t, 0.0f);
                     }
                     mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
@@ -249,13 +265,15 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
             mt_fence_before();
             __syncwarp();
             if (lane == 0) rt_mbar_arrive(&bar_a);
+            if (LOAD_MODE == RT_MLP_LOAD_GATHER && tile + gridDim.x < ntiles)
+                mt_gather_issue(a, tile + gridDim.x, row_in_tile, pre);   // next tile's index -> xyz chain flies under this tile's MMA
 
             for (int l = 0; l < a.nlayers; ++l) {
                 mt_mbar_wait(&bar_d, d_phase);
                 d_phase ^= 1;
                 mt_fence_after();
                 const int n = a.layer[l].n, act = a.layer[l].act;
-                const float *bias = a.layer[l].bias;
+                const float *bias = s_bias + l * 256;
                 const float *cb = (l == 0 && a.cloud_bias) ? a.cloud_bias + (rc / a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
                 const bool last = l == a.nlayers - 1;
                 for (int c0 = 16 * hlf; c0 < n; c0 += 32) {
@@ -264,8 +282,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float t = __uint_as_float(r[i]) * MT_WINV;
-                        if (bias) t += __ldg(bias + c0 + i);
+                        float t = fmaf(__uint_as_float(r[i]), MT_WINV, bias[c0 + i]);
                         if (cb) t += __ldg(cb + c0 + i);
                         v[i] = mt_act(t, act);
                     }
@@ -339,7 +356,7 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
         for (int s = 0; s < a.nseg; ++s) ktot += (a.seg[s].k + 15) / 16 * 16;
         RT_REQUIRE(ktot == a.layer[0].k, "mlp_tc: segments cover %d columns, layer 0 expects %d", ktot, a.layer[0].k);
     } else {
-        RT_REQUIRE(a.c1 == a.layer[0].k && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
+        RT_REQUIRE(a.c1 == a.layer[0].k && a.c1 <= 64 && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
     }
     if (a.out_mode == RT_MLP_OUT_MAXPOOL || a.load_mode == RT_MLP_LOAD_GATHER)
         RT_REQUIRE(a.ns >= 1 && a.ns <= 32 && (a.ns & (a.ns - 1)) == 0, "mlp_tc: ns=%d must be a power of two <= 32", a.ns);
@@ -351,28 +368,35 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     a.d_cols = dmax;
     a.a_cols = kmax / 2;
     RT_REQUIRE(wbytes <= 200 * 1024, "mlp_tc: %d bytes of weights do not fit in shared memory", wbytes);
-    static int smem_set = 0;
-    if (wbytes > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static bool smem_set = false;
+    if (!smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e != cudaSuccess) {
             rt_set_error("mlp_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        smem_set = 200 * 1024;
+        smem_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // resident CTAs per SM: bounded by TMEM columns, shared memory and (to keep tail effects small) 4
     int per_sm = 512 / cols;
-    const int gc_bytes = a.load_mode == RT_MLP_LOAD_GATHER ? 16 * a.c1 : 0;
+    const bool gather = a.load_mode == RT_MLP_LOAD_GATHER;
+    const int gc_bytes = RT_MLP_MAX_LAYERS * 256 * 4 + (gather ? 16 * a.c1 : 0);   // biases + gather constants
     const int by_smem = (220 * 1024) / (wbytes + gc_bytes + 2048);
     per_sm = per_sm < by_smem ? per_sm : by_smem;
-    per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);   // 72 registers x 288 threads: 3 CTAs fill the register file
+    // register file: the row-loading variant (72 regs x 288 threads) fits 3 CTAs per SM, the gather variant, which keeps
+    // the next tile's operands in flight in registers (96 regs), fits 2
+    const int by_regs = 3;
+    per_sm = per_sm < 1 ? 1 : (per_sm > by_regs ? by_regs : per_sm);
     const long long ntiles = (a.rows + 127) / 128;
     long long grid = (long long)sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    mlp_tc_kernel<<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
+    if (gather) mlp_tc_kernel<RT_MLP_LOAD_GATHER><<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
+    else mlp_tc_kernel<RT_MLP_LOAD_ROWS><<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
     return rt_check_launch("mlp_tc_kernel");
 }
 
