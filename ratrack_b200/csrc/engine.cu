@@ -203,13 +203,12 @@ int run_geometry(rt_engine *e, Ws &w, int b, int n) {
         RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], s_fps));
         cudaEventRecord(e->ev_fps[l], s_fps);
         cudaStreamWaitEvent(s_nbr, e->ev_fps[l], 0);
-        for (int s = 0; s < 2; ++s) {
-            const int ns = kLevels[l].ns[s];
-            cudaMemsetAsync(w.bq[l][s], 0, sizeof(int) * (size_t)B2 * S * ns, s_nbr);
-            RT_TRY(rt_ball_query(B2, lvl_n[l], S, kLevels[l].radius[s], ns, w.xyz[l], lvl_in[l], w.bq[l][s], s_nbr));
-        }
+        // both radii of the level in one pass; w.bq[l][0] and [1] are adjacent in the workspace: one memset
+        cudaMemsetAsync(w.bq[l][0], 0, (size_t)((char *)(w.bq[l][1] + (size_t)B2 * S * kLevels[l].ns[1]) - (char *)w.bq[l][0]), s_nbr);
+        RT_TRY(rt_launch_ball_query2(B2, lvl_n[l], S, kLevels[l].radius[0], kLevels[l].ns[0], w.bq[l][0], kLevels[l].radius[1],
+                                     kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], s_nbr));
         cudaEventRecord(e->ev_lvl[l], s_nbr);
-        e->launches += 7;
+        e->launches += 5;
     }
     // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
     const float *unk[3] = {w.xyz[1], w.xyz[0], w.xyz0};

@@ -310,22 +310,73 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                 }
             }
             uint32_t cd = car_d[u], ci = car_i[u], nd = 0x7f800000u, ni = 0xffffffffu;
-            for (int r = 0; r < k; ++r) {
-                // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
-                uint32_t ld = cd, li = ci;
-                int lslot = -1;
+            // ---- prune: U = k-th smallest of the 32 lane minima.  The k lanes with the smallest minima each own a
+            // candidate <= U, so the k nearest are all <= U; typically only ~k..2k candidates survive.
+            uint32_t lmin = cd;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (d[i] < ld) { ld = d[i]; li = (uint32_t)(base + lane + 32 * i); lslot = i; }
-                const uint32_t md = rt_redux_min_u32(ld);
-                const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
-                if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
-                    if (lslot < 0) cd = 0x7f800000u;
+            for (int i = 0; i < 32; ++i) lmin = min(lmin, d[i]);
+            uint32_t sv = lmin;   // bitonic sort of the 32 lane minima across the warp (ascending by lane)
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, sv, j);
+                    const bool asc = (lane & k2) == 0, low = (lane & j) == 0;
+                    sv = (asc == low) ? min(sv, other) : max(sv, other);
+                }
+            const uint32_t U = __shfl_sync(0xffffffffu, sv, k - 1);
+            // survivors of this lane, in index order, into 4 register slots
+            uint32_t sd0 = 0x7f800000u, sd1 = sd0, sd2 = sd0, sd3 = sd0, si0 = 0, si1 = 0, si2 = 0, si3 = 0;
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (d[i] <= U && d[i] != 0x7f800000u) {
+                    const uint32_t id = (uint32_t)(base + lane + 32 * i);
+                    if (cnt == 0) { sd0 = d[i]; si0 = id; }
+                    else if (cnt == 1) { sd1 = d[i]; si1 = id; }
+                    else if (cnt == 2) { sd2 = d[i]; si2 = id; }
+                    else if (cnt == 3) { sd3 = d[i]; si3 = id; }
+                    ++cnt;
+                }
+            }
+            if (__any_sync(0xffffffffu, cnt > 4)) {
+                // rare (heavy ties / clustered duplicates): extract from the full register tile
+                for (int r = 0; r < k; ++r) {
+                    uint32_t ld = cd, li = ci;
+                    int lslot = -1;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (i == lslot) d[i] = 0x7f800000u;
+                        if (d[i] < ld) { ld = d[i]; li = (uint32_t)(base + lane + 32 * i); lslot = i; }
+                    const uint32_t md = rt_redux_min_u32(ld);
+                    const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
+                    if (ld == md && li == mi) {
+                        if (lslot < 0) cd = 0x7f800000u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i == lslot) d[i] = 0x7f800000u;
+                    }
+                    if (lane == r) { nd = md; ni = mi; }
                 }
-                if (lane == r) { nd = md; ni = mi; }
+            } else {
+                for (int r = 0; r < k; ++r) {
+                    // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
+                    uint32_t ld = cd, li = ci;
+                    int lslot = -1;
+                    if (sd0 < ld) { ld = sd0; li = si0; lslot = 0; }
+                    if (sd1 < ld) { ld = sd1; li = si1; lslot = 1; }
+                    if (sd2 < ld) { ld = sd2; li = si2; lslot = 2; }
+                    if (sd3 < ld) { ld = sd3; li = si3; lslot = 3; }
+                    const uint32_t md = rt_redux_min_u32(ld);
+                    const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
+                    if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
+                        if (lslot < 0) cd = 0x7f800000u;
+                        else if (lslot == 0) sd0 = 0x7f800000u;
+                        else if (lslot == 1) sd1 = 0x7f800000u;
+                        else if (lslot == 2) sd2 = 0x7f800000u;
+                        else sd3 = 0x7f800000u;
+                    }
+                    if (lane == r) { nd = md; ni = mi; }
+                }
             }
             car_d[u] = nd;
             car_i[u] = ni;

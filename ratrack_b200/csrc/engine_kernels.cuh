@@ -92,3 +92,6 @@ int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, co
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b,
                        float *cls, cudaStream_t st);
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st);
+// neighbors.cu: ball query of two radii over the same centres in one launch
+int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
+                          int *idx_b, const float *new_xyz, const float *xyz, cudaStream_t st);

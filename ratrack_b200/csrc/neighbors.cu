@@ -22,16 +22,18 @@ constexpr int TILE_PTS = 2048;  // 24 KB of xyz per tile (two CTAs per SM stay u
 constexpr int BQ_THREADS = 256;
 constexpr int BQ_QPB = 64;
 
-__global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, float radius, int nsample,
+// Two radii in one pass (the MSG set-abstraction layers always query the same centres with two radii): the distance
+// of a candidate is evaluated once and feeds two independent ordered compactions.  nsample_b == 0 disables the second.
+__global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, float radius_a, int nsample_a, int *__restrict__ idx_a,
+                                                                float radius_b, int nsample_b, int *__restrict__ idx_b,
                                                                 const float *__restrict__ new_xyz,
-                                                                const float *__restrict__ xyz,
-                                                                int *__restrict__ idx) {
+                                                                const float *__restrict__ xyz) {
     extern __shared__ __align__(16) float s_pts[];  // min(n, TILE_PTS)*3
     __shared__ __align__(8) uint64_t s_bar;
     const int cloud = blockIdx.y;
     const float *pts = xyz + (size_t)cloud * n * 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float radius2 = __fmul_rn(radius, radius);
+    const float r2a = __fmul_rn(radius_a, radius_a), r2b = __fmul_rn(radius_b, radius_b);
     constexpr int QPW = BQ_QPB / (BQ_THREADS / 32);
 
     if (threadIdx.x == 0) {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
 
     const int q0 = blockIdx.x * BQ_QPB + warp * QPW;
     float qx[QPW], qy[QPW], qz[QPW];
-    int cnt[QPW], first[QPW];
+    int cnt_a[QPW], first_a[QPW], cnt_b[QPW], first_b[QPW];
 #pragma unroll
     for (int i = 0; i < QPW; ++i) {
         const int q = q0 + i;
@@ -51,8 +53,9 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
         qx[i] = __ldg(c + 0);
         qy[i] = __ldg(c + 1);
         qz[i] = __ldg(c + 2);
-        cnt[i] = ok ? 0 : nsample;  // out-of-range queries are "done"
-        first[i] = -1;
+        cnt_a[i] = ok ? 0 : nsample_a;  // out-of-range queries are "done"
+        cnt_b[i] = ok ? 0 : nsample_b;
+        first_a[i] = first_b[i] = -1;
     }
 
     uint32_t parity = 0;
@@ -63,34 +66,53 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
         parity ^= 1;
 #pragma unroll
         for (int i = 0; i < QPW; ++i) {
-            if (cnt[i] >= nsample) continue;  // warp-uniform
-            int *out = idx + ((size_t)cloud * m + (q0 + i)) * nsample;
-            int c = cnt[i], f = first[i];
-            for (int k0 = 0; k0 < tn && c < nsample; k0 += 32) {
+            int ca = cnt_a[i], cb = cnt_b[i], fa = first_a[i], fb = first_b[i];
+            if (ca >= nsample_a && cb >= nsample_b) continue;  // warp-uniform
+            int *oa = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a;
+            int *ob = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b;
+            for (int k0 = 0; k0 < tn && (ca < nsample_a || cb < nsample_b); k0 += 32) {
                 const int k = k0 + lane;
-                bool hit = false;
+                bool hit_a = false, hit_b = false;
                 if (k < tn) {
                     const float d2 = rt_sqdist(qx[i], qy[i], qz[i], s_pts[k * 3 + 0], s_pts[k * 3 + 1], s_pts[k * 3 + 2]);
-                    hit = d2 < radius2;
+                    hit_a = d2 < r2a;
+                    hit_b = d2 < r2b;
                 }
-                const uint32_t vote = __ballot_sync(0xffffffffu, hit);
-                if (vote) {
-                    if (f < 0) f = base + k0 + __ffs(vote) - 1;
-                    const int slot = c + __popc(vote & ((1u << lane) - 1u));
-                    if (hit && slot < nsample) out[slot] = base + k;
-                    c += __popc(vote);
+                if (ca < nsample_a) {
+                    const uint32_t vote = __ballot_sync(0xffffffffu, hit_a);
+                    if (vote) {
+                        if (fa < 0) fa = base + k0 + __ffs(vote) - 1;
+                        const int slot = ca + __popc(vote & ((1u << lane) - 1u));
+                        if (hit_a && slot < nsample_a) oa[slot] = base + k;
+                        ca += __popc(vote);
+                    }
+                }
+                if (cb < nsample_b) {
+                    const uint32_t vote = __ballot_sync(0xffffffffu, hit_b);
+                    if (vote) {
+                        if (fb < 0) fb = base + k0 + __ffs(vote) - 1;
+                        const int slot = cb + __popc(vote & ((1u << lane) - 1u));
+                        if (hit_b && slot < nsample_b) ob[slot] = base + k;
+                        cb += __popc(vote);
+                    }
                 }
             }
-            cnt[i] = c;
-            first[i] = f;
+            cnt_a[i] = ca; cnt_b[i] = cb;
+            first_a[i] = fa; first_b[i] = fb;
         }
     }
     // pad unused slots with the first hit; queries with no hit leave the caller's buffer untouched
 #pragma unroll
     for (int i = 0; i < QPW; ++i) {
-        if (first[i] < 0 || q0 + i >= m) continue;
-        int *out = idx + ((size_t)cloud * m + (q0 + i)) * nsample;
-        for (int s = cnt[i] + lane; s < nsample; s += 32) out[s] = first[i];
+        if (q0 + i >= m) continue;
+        if (first_a[i] >= 0) {
+            int *out = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a;
+            for (int s = cnt_a[i] + lane; s < nsample_a; s += 32) out[s] = first_a[i];
+        }
+        if (first_b[i] >= 0) {
+            int *out = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b;
+            for (int s = cnt_b[i] + lane; s < nsample_b; s += 32) out[s] = first_b[i];
+        }
     }
 }
 
@@ -247,9 +269,20 @@ RT_API int rt_ball_query(int b, int n, int m, float radius, int nsample, const f
     if (b == 0 || m == 0 || nsample == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     dim3 grid(rt_divup(m, BQ_QPB), b);
-    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes(n), (cudaStream_t)stream>>>(n, m, radius, nsample, new_xyz, xyz,
-                                                                                 idx);
+    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
+                                                                                 new_xyz, xyz);
     return rt_check_launch("ball_query_kernel");
+}
+
+// engine-internal: two radii over the same centres in one launch (same results as two rt_ball_query calls)
+int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
+                          int *idx_b, const float *new_xyz, const float *xyz, cudaStream_t st) {
+    if (b == 0 || m == 0 || n == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535 && nsample_a > 0 && nsample_b > 0, "ball_query2: bad arguments");
+    dim3 grid(rt_divup(m, BQ_QPB), b);
+    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
+                                                              new_xyz, xyz);
+    return rt_check_launch("ball_query_kernel(2 radii)");
 }
 
 // replaces three_nn_wrapper_fast (reference: src/lib/src/interpolate.cpp:16-25)
