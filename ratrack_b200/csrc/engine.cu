@@ -335,7 +335,7 @@ RtMlpTc mlp_rows(long long rows, const float *x, int ldx, int k) {
     m.load_mode = RT_MLP_LOAD_ROWS;
     m.out_mode = RT_MLP_OUT_ROWS;
     m.nseg = 1;
-    m.seg[0] = RtMlpSeg{x, ldx, k};
+    m.seg[0] = RtMlpSeg{x, ldx, k, nullptr, nullptr, 0, 0};
     m.rows_per_cloud = 1;
     return m;
 }
@@ -402,30 +402,31 @@ int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int c
         e->launches += 4;
     }
     cudaStreamWaitEvent(st, e->ev_nn, 0);
+    // the three-point interpolation is evaluated inside the GEMM's operand loader (no interp buffer, no extra launch)
     {   // FP3: l2 <- l3
-        RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
-        RtMlpTc m = mlp_rows((long long)clouds * S, w.interp, 64, 64);
-        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l2, 64, 64};
+        RtMlpTc m = mlp_rows((long long)clouds * S, nullptr, 0, 0);
+        m.seg[0] = RtMlpSeg{w.l3, 64, 64, w.nn_idx[0], w.nn_w[0], S, S};
+        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l2, 64, 64, nullptr, nullptr, 0, 0};
         mlp_layer(m, pk.fp3, hw.fp3_b, 128, 128, RT_ACT_RELU);
         mlp_out(m, w.l2p, 128, 0, 128); m.status = w.status;
         RT_TRY(rt_launch_mlp_tc(m, st));
     }
     {   // FP2: l1 <- l2'
-        RT_TRY(rt_launch_interp3(clouds, S, S, 128, w.l2p, 128, w.nn_idx[1], w.nn_w[1], w.interp, 128, st));
-        RtMlpTc m = mlp_rows((long long)clouds * S, w.interp, 128, 128);
-        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l1, 32, 32};
+        RtMlpTc m = mlp_rows((long long)clouds * S, nullptr, 0, 0);
+        m.seg[0] = RtMlpSeg{w.l2p, 128, 128, w.nn_idx[1], w.nn_w[1], S, S};
+        m.nseg = 2; m.seg[1] = RtMlpSeg{w.l1, 32, 32, nullptr, nullptr, 0, 0};
         mlp_layer(m, pk.fp2, hw.fp2_b, 160, 128, RT_ACT_RELU);
         mlp_out(m, w.l1p, 128, 0, 128); m.status = w.status;
         RT_TRY(rt_launch_mlp_tc(m, st));
     }
     {   // FP1: l0 <- l1'
-        RT_TRY(rt_launch_interp3(clouds, n, S, 128, w.l1p, 128, w.nn_idx[2], w.nn_w[2], w.interp, 128, st));
-        RtMlpTc m = mlp_rows((long long)clouds * n, w.interp, 128, 128);
+        RtMlpTc m = mlp_rows((long long)clouds * n, nullptr, 0, 0);
+        m.seg[0] = RtMlpSeg{w.l1p, 128, 128, w.nn_idx[2], w.nn_w[2], n, S};
         mlp_layer(m, pk.fp1, hw.fp1_b, 128, 128, RT_ACT_RELU);
         mlp_out(m, out, 128, 0, 128); m.status = w.status;
         RT_TRY(rt_launch_mlp_tc(m, st));
     }
-    e->launches += 6;
+    e->launches += 3;
     return RT_OK;
 }
 
@@ -644,7 +645,7 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     cudaMemsetAsync(w.status, 0, 64 * sizeof(int), st);
     e->last_status = w.status;
     if (tc_mlp) {
-        RtMlpSeg seg_ft{w.ft0, 2, 2};
+        RtMlpSeg seg_ft{w.ft0, 2, 2, nullptr, nullptr, 0, 0};
         RT_TRY(run_head_tc(e, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     } else {
         RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
@@ -743,7 +744,8 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     const HeadW &mse = e->w.mse;
     RT_TRY(rt_launch_cloud_matvec(b, 32, 128, mse.wf_glob, 128, w.gmax, 128, nullptr, w.cb_a, st));
     if (tc_mlp) {
-        RtMlpSeg segs[3] = {RtMlpSeg{w.ft0, 2, 2}, RtMlpSeg{w.feat, 128, 128}, RtMlpSeg{w.cor, 256, 256}};
+        RtMlpSeg segs[3] = {RtMlpSeg{w.ft0, 2, 2, nullptr, nullptr, 0, 0}, RtMlpSeg{w.feat, 128, 128, nullptr, nullptr, 0, 0},
+                            RtMlpSeg{w.cor, 256, 256, nullptr, nullptr, 0, 0}};
         RT_TRY(run_head_tc(e, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     } else {
         RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},

@@ -157,6 +157,57 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
         s_idx[t] = j;
     }
     __syncthreads();
+    if ((a.c & 3) == 0 && a.c <= 256) {
+        // 4 channels per thread (128-bit gathers: 4x the bytes in flight per thread), 256 / (c/4) points side by side
+        const int lanes = a.c >> 2;                 // threads per point
+        const int pslots = blockDim.x / lanes;      // points processed concurrently
+        const int cg = threadIdx.x % lanes, ps = threadIdx.x / lanes;
+        if (ps < pslots) {
+            float wc[4][8], bc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wc[j][k] = __ldg(a.wc + (4 * cg + j) * 8 + k);
+                bc[j] = __ldg(a.bc + 4 * cg + j);
+            }
+            for (int p = ps; p < WS_PTS; p += pslots) {
+                const long long cp = cp0 + p;
+                if (cp >= ncp) break;
+                const int cloud = (int)(cp / a.npts);
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (int s0 = 0; s0 < a.ns; s0 += 8) {
+                    float4 vv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        vv[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (s < a.ns) {
+                            const float *row = a.gather_v ? a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c
+                                                          : a.v + (cp * a.ns + s) * a.c;
+                            vv[u] = __ldg(reinterpret_cast<const float4 *>(row) + cg);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        if (s < a.ns) {
+                            const float *h2 = s_h2 + (p * a.ns + s) * 8;
+                            const float vx[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float w = bc[j];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) w = fmaf(wc[j][k], h2[k], w);
+                                acc[j] = fmaf(fmaxf(w, 0.0f), vx[j], acc[j]);
+                            }
+                        }
+                    }
+                }
+                reinterpret_cast<float4 *>(a.out + cp * a.c)[cg] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            }
+        }
+        return;
+    }
     for (int ch = threadIdx.x; ch < a.c; ch += blockDim.x) {
         float wc[8];
 #pragma unroll
@@ -167,28 +218,14 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
             if (cp >= ncp) break;
             const int cloud = (int)(cp / a.npts);
             float acc = 0.0f;
-            for (int s0 = 0; s0 < a.ns; s0 += 8) {
-                // issue the (gathered) value loads of 8 neighbours before any arithmetic: memory-level parallelism
-                float vv[8];
+            for (int s = 0; s < a.ns; ++s) {
+                const float *h2 = s_h2 + (p * a.ns + s) * 8;
+                float w = bc;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int s = s0 + u;
-                    vv[u] = 0.0f;
-                    if (s < a.ns)
-                        vv[u] = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
+                for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
+                const float v = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
                                            : __ldg(a.v + (cp * a.ns + s) * a.c + ch);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int s = s0 + u;
-                    if (s < a.ns) {
-                        const float *h2 = s_h2 + (p * a.ns + s) * 8;
-                        float w = bc;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
-                        acc = fmaf(fmaxf(w, 0.0f), vv[u], acc);
-                    }
-                }
+                acc = fmaf(fmaxf(w, 0.0f), v, acc);
             }
             a.out[cp * a.c + ch] = acc;
         }
@@ -491,38 +528,39 @@ __global__ void __launch_bounds__(256) broadcast_cm_kernel(int c, int n, const f
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = v;
 }
 
-// 5-layer GRU, sequence length 1 (torch.nn.GRU equations): CTA per batch element, 384 threads (one per gate row).
-// Weights arrive TRANSPOSED, (5, 128, 384): thread t reads column t -> every load is coalesced.
-__global__ void __launch_bounds__(384) gru_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
-                                                  const float *__restrict__ wih_t, const float *__restrict__ whh_t,
-                                                  const float *__restrict__ bih, const float *__restrict__ bhh,
-                                                  float *__restrict__ h_out) {
-    __shared__ float s_in[128], s_h[128], s_gi[384], s_gh[384];
-    const int b = blockIdx.x, t = threadIdx.x;
-    if (t < 128) s_in[t] = x[(long long)b * 128 + t];
-    for (int l = 0; l < 5; ++l) {
-        if (t < 128) s_h[t] = h_in[((long long)l * bsz + b) * 128 + t];
-        __syncthreads();
-        const float *wi = wih_t + (long long)l * 128 * 384 + t;
-        const float *wh = whh_t + (long long)l * 128 * 384 + t;
-        float gi = 0.0f, gh = 0.0f;
-#pragma unroll 32
-        for (int k = 0; k < 128; ++k) {
-            gi = fmaf(__ldg(wi + k * 384), s_in[k], gi);
-            gh = fmaf(__ldg(wh + k * 384), s_h[k], gh);
-        }
-        s_gi[t] = gi + __ldg(bih + l * 384 + t);
-        s_gh[t] = gh + __ldg(bhh + l * 384 + t);
-        __syncthreads();
-        if (t < 128) {
-            const float r = 1.0f / (1.0f + expf(-(s_gi[t] + s_gh[t])));
-            const float z = 1.0f / (1.0f + expf(-(s_gi[128 + t] + s_gh[128 + t])));
-            const float nn = tanhf(s_gi[256 + t] + r * s_gh[256 + t]);
-            const float hn = (1.0f - z) * nn + z * s_h[t];
-            h_out[((long long)l * bsz + b) * 128 + t] = hn;
-            s_in[t] = hn;
-        }
-        __syncthreads();
+// One GRU layer, sequence length 1 (torch.nn.GRU equations).  grid (4, B): a CTA owns 32 hidden units of one batch
+// element; 192 threads = 6 dot products (r,z,n rows of W_ih and of W_hh) x 32 units, each 128 long.  Weights arrive
+// TRANSPOSED (128 x 384) so the 32 threads of a warp read 32 consecutive rows of one k: coalesced.
+__global__ void __launch_bounds__(192) gru_layer_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
+                                                        const float *__restrict__ wih_t, const float *__restrict__ whh_t,
+                                                        const float *__restrict__ bih, const float *__restrict__ bhh,
+                                                        float *__restrict__ h_out) {
+    __shared__ float s_x[128], s_h[128], s_g[6][32];
+    const int b = blockIdx.y, j0 = blockIdx.x * 32, t = threadIdx.x;
+    if (t < 128) {
+        s_x[t] = x[(long long)b * 128 + t];
+        s_h[t] = h_in[(long long)b * 128 + t];
+    }
+    __syncthreads();
+    const int part = t >> 5, jj = t & 31;          // part 0..2: W_ih gates r,z,n; 3..5: W_hh gates r,z,n
+    const int row = (part % 3) * 128 + j0 + jj;
+    const float *w = (part < 3 ? wih_t : whh_t) + row;
+    const float *v = part < 3 ? s_x : s_h;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;   // four partial sums: shorter dependent chains
+#pragma unroll 8
+    for (int k = 0; k < 128; k += 4) {
+        a0 = fmaf(__ldg(w + (k + 0) * 384), v[k + 0], a0);
+        a1 = fmaf(__ldg(w + (k + 1) * 384), v[k + 1], a1);
+        a2 = fmaf(__ldg(w + (k + 2) * 384), v[k + 2], a2);
+        a3 = fmaf(__ldg(w + (k + 3) * 384), v[k + 3], a3);
+    }
+    s_g[part][jj] = (a0 + a1) + (a2 + a3) + __ldg((part < 3 ? bih : bhh) + row);
+    __syncthreads();
+    if (t < 32) {
+        const float r = 1.0f / (1.0f + expf(-(s_g[0][t] + s_g[3][t])));
+        const float z = 1.0f / (1.0f + expf(-(s_g[1][t] + s_g[4][t])));
+        const float nn = tanhf(s_g[2][t] + r * s_g[5][t]);
+        h_out[(long long)b * 128 + j0 + t] = (1.0f - z) * nn + z * s_h[j0 + t];
     }
 }
 
@@ -639,8 +677,14 @@ int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int 
 int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
                   const float *bhh, float *h_out, cudaStream_t st) {
     if (b <= 0) return RT_OK;
-    gru_kernel<<<b, 384, 0, st>>>(b, x, h_in, wih, whh, bih, bhh, h_out);
-    return rt_check_launch("gru_kernel");
+    // five dependent layer launches; layer l reads h_in[l] and the previous layer's output
+    for (int l = 0; l < 5; ++l) {
+        const float *xin = l == 0 ? x : h_out + (size_t)(l - 1) * b * 128;
+        gru_layer_kernel<<<dim3(4, b), 192, 0, st>>>(b, xin, h_in + (size_t)l * b * 128, wih + (size_t)l * 128 * 384,
+                                                    whh + (size_t)l * 128 * 384, bih + l * 384, bhh + l * 384,
+                                                    h_out + (size_t)l * b * 128);
+    }
+    return rt_check_launch("gru_layer_kernel");
 }
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b, float *cls,
                        cudaStream_t st) {

@@ -224,8 +224,34 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
             if (LOAD_MODE == RT_MLP_LOAD_ROWS) {
                 int c0 = 0;
                 for (int s = 0; s < a.nseg; ++s) {
-                    const float *x = a.seg[s].x + rc * a.seg[s].ldx;
                     const int ks = a.seg[s].k;
+                    if (a.seg[s].nn_idx) {
+                        // interpolated segment: three gathered rows, the reference kernel's fma order
+                        const int *ix = a.seg[s].nn_idx + rc * 3;
+                        const float *ww = a.seg[s].nn_w + rc * 3;
+                        const long long cbase = (rc / a.seg[s].nn_n) * a.seg[s].nn_m;
+                        const float *r0 = a.seg[s].x + (cbase + __ldg(ix + 0)) * a.seg[s].ldx;
+                        const float *r1 = a.seg[s].x + (cbase + __ldg(ix + 1)) * a.seg[s].ldx;
+                        const float *r2 = a.seg[s].x + (cbase + __ldg(ix + 2)) * a.seg[s].ldx;
+                        const float w0 = __ldg(ww + 0), w1 = __ldg(ww + 1), w2 = __ldg(ww + 2);
+                        for (int o = 0; o < ks; o += 16, c0 += 16) {
+                            if (((c0 >> 4) & 1) != hlf) continue;
+                            float v[16];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 p0 = __ldg(reinterpret_cast<const float4 *>(r0 + o) + g);
+                                const float4 p1 = __ldg(reinterpret_cast<const float4 *>(r1 + o) + g);
+                                const float4 p2 = __ldg(reinterpret_cast<const float4 *>(r2 + o) + g);
+                                v[4 * g + 0] = __fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x)));
+                                v[4 * g + 1] = __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y)));
+                                v[4 * g + 2] = __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z)));
+                                v[4 * g + 3] = __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w)));
+                            }
+                            mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
+                        }
+                        continue;
+                    }
+                    const float *x = a.seg[s].x + rc * a.seg[s].ldx;
                     const bool vec = (a.seg[s].ldx & 3) == 0;
                     for (int o = 0; o < ks; o += 16, c0 += 16) {
                         if (((c0 >> 4) & 1) != hlf) continue;
@@ -355,6 +381,9 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
         int ktot = 0;
         for (int s = 0; s < a.nseg; ++s) ktot += (a.seg[s].k + 15) / 16 * 16;
         RT_REQUIRE(ktot == a.layer[0].k, "mlp_tc: segments cover %d columns, layer 0 expects %d", ktot, a.layer[0].k);
+        for (int s = 0; s < a.nseg; ++s)
+            RT_REQUIRE(!a.seg[s].nn_idx || ((a.seg[s].k & 15) == 0 && (a.seg[s].ldx & 3) == 0 && a.seg[s].nn_w),
+                       "mlp_tc: interpolated segment %d needs k %% 16 == 0 and ldx %% 4 == 0", s);
     } else {
         RT_REQUIRE(a.c1 == a.layer[0].k && a.c1 <= 64 && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
     }

@@ -16,6 +16,12 @@ struct RtMlpLayer {
 struct RtMlpSeg {
     const float *x;
     int ldx, k;         // k real columns; occupies ceil16(k) columns of layer 0's K
+    // optional three-point interpolation of the segment (PointnetFPModule, reference lib/pointnet2_modules.py:141-146):
+    // value[row, c] = fma(w2, x[i2, c], fma(w0, x[i0, c], w1 * x[i1, c])) with (i, w) = nn_idx / nn_w[row, 0..2] and
+    // x rows taken from cloud (row / nn_n) of nn_m points.  nn_idx == nullptr: plain rows.
+    const int *nn_idx;
+    const float *nn_w;
+    int nn_n, nn_m;
 };
 struct RtMlpTc {
     long long rows;
