@@ -132,8 +132,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic N={a.points} pts, batch={a.batch}, full backbone+scene-flow forward",
-                   "batch_per_gpu": a.batch, "points": a.points, "npoints": 512, "l2": "cpu run"},
+        "config": {"workload": f"synthetic N={a.points} pts, batch={a.batch} per GPU, full backbone+scene-flow forward (configs[1])",
+                   "batch_per_gpu": a.batch, "points": a.points, "npoints": 512, "path": "reference CPU path (oracle port)",
+                   "l2": "n/a (host run)", "parallelism": f"dp{a.gpus}"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -254,7 +255,8 @@ def main():
     # ---- roofline of the dominant kernel (definitions: DESIGN.md "Kernels and rooflines") -----------
     if fused:
         from ratrack_b200 import engine
-        roof = engine.roofline_of_dominant(B, N, dom_ms, peaks)
+        roof = engine.roofline_of_dominant(B, N, dom_ms, peaks, launch_pairs=(B + 1) // 2 if eng.num_lanes(B) == 2 else B)
+        roof["lanes"] = eng.num_lanes(B)
     else:
         # modular path: the largest launch of ours is group_points of the 514-channel embedding
         # (mse SA1, C=514, ns=8): algorithmic bytes 4*S*ns + 4*C*min(N,S*ns) + 4*C*S*ns per cloud
@@ -270,7 +272,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic N={N} pts, batch={B}, full backbone+scene-flow forward on 1xB200 (configs[1])",
+        "config": {"workload": f"synthetic N={N} pts, batch={B} per GPU, full backbone+scene-flow forward (configs[1])",
                    "batch_per_gpu": B, "points": N, "npoints": 512, "path": "fused" if fused else "modular",
                    "l2": "flushed between timed iterations (256 MiB memset)", "parallelism": f"dp{world}"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -115,9 +115,13 @@ long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n);
  * cost-volume MLP) of every forward; pass NULL, NULL to disable */
 int rt_engine_set_profile_events(rt_engine *e, void *start_event, void *stop_event);
 
-/* flags: bit 0 (default on) = cost volume on the tcgen05 tensor-core kernel; off = the SIMT fp32 chain with the
- * same dataflow (kept for A/B parity checks of the fp16x3 split arithmetic) */
+/* flags (default 3): bit 0 = cost volume on the tcgen05 tensor-core kernel, bit 1 = every other dense layer on the
+ * tcgen05 MLP kernel; cleared bits select the fp32 SIMT kernels of the same dataflow (A/B parity of the split-fp16
+ * arithmetic).  bit 2 = split batches of >= 8 pairs over two concurrent lanes (stream sets); bit-identical results, off by default. */
 int rt_engine_set_flags(rt_engine *e, int flags);
+
+/* how many lanes rt_backbone_forward will use for a batch of b pairs (1 or 2); lane 0 gets ceil(b/2) pairs */
+int rt_engine_num_lanes(const rt_engine *e, int b);
 
 /* blocking: device status word of the last rt_backbone_forward.  0 = ok; bit 1 = an activation of the cost-volume
  * MLP left the fp16 hi/lo range (|x| >= 65000): that call's outputs are invalid */

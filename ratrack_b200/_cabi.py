@@ -37,6 +37,7 @@ OTHER = {
     "rt_engine_destroy": ([_P], None),
     "rt_engine_workspace_bytes": ([_P, _I, _I], ctypes.c_longlong),
     "rt_engine_launch_count": ([_P], ctypes.c_longlong),
+    "rt_engine_num_lanes": ([_P, _I], ctypes.c_int),
 }
 
 _lib = None

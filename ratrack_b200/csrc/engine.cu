@@ -11,6 +11,7 @@
 //   * channels that are constant over a cloud (global max-pool features, the GRU output) enter the next
 //     layer as a per-cloud bias instead of being broadcast and concatenated.
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ratrack_b200.h"
@@ -167,6 +168,19 @@ RtRowGemm gemm1(long long rows, int nout, const float *x, int ldx, int k, const 
 struct HeadPacks { void *proj[3], *w2[3][2], *w3[2], *lin[3], *fp3, *fp2, *fp1; };
 struct Packs { HeadPacks pn, mse; void *p1, *p2, *cp[3], *fw[4]; };
 
+// Streams and events of one in-flight sub-batch.  A forward call splits its batch over two lanes so the latency-bound
+// stretches of one half (the FPS chain, small tail kernels) are filled by the throughput-bound kernels of the other.
+struct Lane {
+    // geometry runs beside the feature path on three streams: [0] the dependent FPS chain (latency-bound, 2B CTAs),
+    // [1] ball queries + three_nn (need only the FPS result of their level), [2] the cost-volume kNN
+    cudaStream_t main_stream = nullptr, geo_stream[3] = {nullptr, nullptr, nullptr};
+    // output stream: API-layout transposes and the cls head hang off the feature path, nothing waits for them until the end
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
+                ev_nn = nullptr, ev_knn = nullptr, ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr,
+                ev_done = nullptr;
+};
+
 struct rt_engine {
     EngineW w;
     Packs packs;
@@ -174,40 +188,35 @@ struct rt_engine {
     int npoint;
     cudaEvent_t prof_start = nullptr, prof_stop = nullptr;
     long long launches = 0;
-    // geometry runs beside the feature path on three streams: [0] the dependent FPS chain (latency-bound, 2B CTAs),
-    // [1] ball queries + three_nn (need only the FPS result of their level), [2] the cost-volume kNN
-    cudaStream_t geo_stream[3] = {nullptr, nullptr, nullptr};
-    // output stream: API-layout transposes and the cls head hang off the feature path, nothing waits for them until the end
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
-                ev_nn = nullptr, ev_knn = nullptr;
+    Lane lanes[2];
+    cudaEvent_t ev_fork = nullptr;
     int flags = 3;                 // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
-                                   // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow
-    const int *last_status = nullptr;
+                                   // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow;
+                                   // bit 2 (off by default: measured 4 % slower at 32 pairs, neutral at 128): split batches of >= 8 pairs over two lanes
+    const int *last_status[2] = {nullptr, nullptr};
 };
 
 namespace {
 
 // geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN.
 // Every stage records an event the feature path (and the dependent geometry stages) wait on.
-int run_geometry(rt_engine *e, Ws &w, int b, int n) {
+int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     const int B2 = 2 * b, S = e->npoint;
-    cudaStream_t s_fps = e->geo_stream[0], s_nbr = e->geo_stream[1], s_knn = e->geo_stream[2];
+    cudaStream_t s_fps = L.geo_stream[0], s_nbr = L.geo_stream[1], s_knn = L.geo_stream[2];
     const float *lvl_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
     const int lvl_n[3] = {n, S, S};
-    for (int g = 0; g < 3; ++g) cudaStreamWaitEvent(e->geo_stream[g], e->ev_in, 0);
+    for (int g = 0; g < 3; ++g) cudaStreamWaitEvent(L.geo_stream[g], L.ev_in, 0);
     for (int l = 0; l < 3; ++l) {
         RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
         RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
         RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], s_fps));
-        cudaEventRecord(e->ev_fps[l], s_fps);
-        cudaStreamWaitEvent(s_nbr, e->ev_fps[l], 0);
+        cudaEventRecord(L.ev_fps[l], s_fps);
+        cudaStreamWaitEvent(s_nbr, L.ev_fps[l], 0);
         // both radii of the level in one pass; w.bq[l][0] and [1] are adjacent in the workspace: one memset
         cudaMemsetAsync(w.bq[l][0], 0, (size_t)((char *)(w.bq[l][1] + (size_t)B2 * S * kLevels[l].ns[1]) - (char *)w.bq[l][0]), s_nbr);
         RT_TRY(rt_launch_ball_query2(B2, lvl_n[l], S, kLevels[l].radius[0], kLevels[l].ns[0], w.bq[l][0], kLevels[l].radius[1],
                                      kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], s_nbr));
-        cudaEventRecord(e->ev_lvl[l], s_nbr);
+        cudaEventRecord(L.ev_lvl[l], s_nbr);
         e->launches += 5;
     }
     // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
@@ -219,22 +228,22 @@ int run_geometry(rt_engine *e, Ws &w, int b, int n) {
         RT_TRY(rt_launch_nn_weights((long long)B2 * un[l], w.nn_w[l], s_nbr));
         e->launches += 2;
     }
-    cudaEventRecord(e->ev_nn, s_nbr);
+    cudaEventRecord(L.ev_nn, s_nbr);
     // cost-volume kNN: only after the FPS chain.  FPS is a chain of ~1500 dependent rounds on 2b CTAs; measured on
     // B200, any kernel sharing its SMs stretches every round 2-3x (438 us instead of 148 us for FPS-1 with the kNN
     // beside it), so the throughput-bound kNN is ordered behind it and overlaps the SA / FP kernels instead.
     const float *pc1 = w.xyz0, *pc2 = w.xyz0 + (size_t)b * n * 3;
-    cudaStreamWaitEvent(s_knn, e->ev_fps[2], 0);
+    cudaStreamWaitEvent(s_knn, L.ev_fps[2], 0);
     RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
     RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
-    cudaEventRecord(e->ev_knn, s_knn);
+    cudaEventRecord(L.ev_knn, s_knn);
     e->launches += 2;
     return RT_OK;
 }
 
 // One PNHead (utils/model_utils/model_utils.py:409-424) over the first `clouds` clouds of the geometry.
 // Level-1 input features arrive as row segments; `cloud_bias1` carries cloud-constant channels.
-int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSeg *segs, int nseg, const float *cloud_bias1,
+int run_head(rt_engine *e, Lane &L, const HeadW &hw, Ws &w, int clouds, int n, const RtSeg *segs, int nseg, const float *cloud_bias1,
              float *out, cudaStream_t st) {
     const int S = e->npoint;
     const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
@@ -268,7 +277,7 @@ int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSe
         pg.ldy = c1tot;
         RT_TRY(rt_launch_rowgemm(pg, st));
         e->launches += 1;
-        cudaStreamWaitEvent(st, e->ev_lvl[l], 0);   // FPS + ball query of this level
+        cudaStreamWaitEvent(st, L.ev_lvl[l], 0);   // FPS + ball query of this level
         const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
         int coff = 0;
         for (int s = 0; s < 2; ++s) {
@@ -298,7 +307,7 @@ int run_head(rt_engine *e, const HeadW &hw, Ws &w, int clouds, int n, const RtSe
         e->launches += 1;
     }
     // feature propagation (lib/pointnet2_modules.py:129-158): interpolate, concat skip, 1-layer SharedMLP
-    cudaStreamWaitEvent(st, e->ev_nn, 0);
+    cudaStreamWaitEvent(st, L.ev_nn, 0);
     {   // FP3: l2 <- l3
         RT_TRY(rt_launch_interp3(clouds, S, S, 64, w.l3, 64, w.nn_idx[0], w.nn_w[0], w.interp, 64, st));
         RtRowGemm g{};
@@ -347,7 +356,7 @@ void mlp_out(RtMlpTc &m, float *out, int ldo, int ooff, int n_out) {
 }
 
 // PNHead on the tensor cores: per level  projection GEMM -> 2 x [gather + conv chain + max-pool] -> linear
-int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int clouds, int n, const RtMlpSeg *segs, int nseg,
+int run_head_tc(rt_engine *e, Lane &L, const HeadW &hw, const HeadPacks &pk, Ws &w, int clouds, int n, const RtMlpSeg *segs, int nseg,
                 const float *cloud_bias1, float *out, cudaStream_t st) {
     const int S = e->npoint;
     const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
@@ -374,9 +383,9 @@ int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int c
         mlp_layer(pg, pk.proj[l], nullptr, k0, c1tot, RT_ACT_NONE);
         mlp_out(pg, w.proj, c1tot, 0, c1tot);
         pg.status = w.status;
-        if (l > 0) cudaStreamWaitEvent(st, e->ev_lvl[l - 1], 0);
+        if (l > 0) cudaStreamWaitEvent(st, L.ev_lvl[l - 1], 0);
         RT_TRY(rt_launch_mlp_tc(pg, st));
-        cudaStreamWaitEvent(st, e->ev_lvl[l], 0);   // FPS + ball query of this level
+        cudaStreamWaitEvent(st, L.ev_lvl[l], 0);   // FPS + ball query of this level
         const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
         int coff = 0;
         for (int s = 0; s < 2; ++s) {
@@ -401,7 +410,7 @@ int run_head_tc(rt_engine *e, const HeadW &hw, const HeadPacks &pk, Ws &w, int c
         RT_TRY(rt_launch_mlp_tc(lg, st));
         e->launches += 4;
     }
-    cudaStreamWaitEvent(st, e->ev_nn, 0);
+    cudaStreamWaitEvent(st, L.ev_nn, 0);
     // the three-point interpolation is evaluated inside the GEMM's operand loader (no interp buffer, no extra launch)
     {   // FP3: l2 <- l3
         RtMlpTc m = mlp_rows((long long)clouds * S, nullptr, 0, 0);
@@ -515,6 +524,7 @@ int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const floa
     return RT_OK;
 }
 
+RT_API int rt_engine_num_lanes(const rt_engine *e, int b);
 RT_API int rt_engine_num_weights(void) { return kNumWeights; }
 
 RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weights, int nweights) {
@@ -525,6 +535,7 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
     RT_REQUIRE(e, "engine_create: out of host memory");
     memcpy(&e->w, weights, sizeof(EngineW));
     e->npoint = npoint;
+    if (const char *env = getenv("RT_ENGINE_FLAGS")) e->flags = atoi(env);   // A/B timing without touching the caller
     // pointers that may legitimately be null: pn_head has only the `ft` feature segment; levels 2-3 have no third conv
     const float *const *tab = reinterpret_cast<const float *const *>(&e->w);
     const int head = sizeof(HeadW) / sizeof(const float *);
@@ -540,19 +551,15 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
             return RT_ERR_INVALID;
         }
     }
-    for (int g = 0; g < 3; ++g) cudaStreamCreateWithFlags(&e->geo_stream[g], cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&e->ev_feat, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_cor, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_prop, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_aux, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
-    for (int l = 0; l < 3; ++l) {
-        cudaEventCreateWithFlags(&e->ev_lvl[l], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&e->ev_fps[l], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    for (Lane &L : e->lanes) {
+        cudaStreamCreateWithFlags(&L.main_stream, cudaStreamNonBlocking);
+        for (int g = 0; g < 3; ++g) cudaStreamCreateWithFlags(&L.geo_stream[g], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking);
+        cudaEvent_t *evs[] = {&L.ev_in, &L.ev_fps[0], &L.ev_fps[1], &L.ev_fps[2], &L.ev_lvl[0], &L.ev_lvl[1], &L.ev_lvl[2],
+                              &L.ev_nn, &L.ev_knn, &L.ev_feat, &L.ev_cor, &L.ev_prop, &L.ev_aux, &L.ev_done};
+        for (cudaEvent_t *ev : evs) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     }
-    cudaEventCreateWithFlags(&e->ev_nn, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_knn, cudaEventDisableTiming);
     const int rc = build_packs(e);
     if (rc != RT_OK) {
         if (e->arena) cudaFree(e->arena);
@@ -566,22 +573,35 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
 RT_API void rt_engine_destroy(rt_engine *e) {
     if (!e) return;
     if (e->arena) cudaFree(e->arena);
-    for (int g = 0; g < 3; ++g)
-        if (e->geo_stream[g]) cudaStreamDestroy(e->geo_stream[g]);
-    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
-    cudaEvent_t evs[13] = {e->ev_in, e->ev_lvl[0], e->ev_lvl[1], e->ev_lvl[2], e->ev_nn, e->ev_knn,
-                           e->ev_fps[0], e->ev_fps[1], e->ev_fps[2], e->ev_feat, e->ev_cor, e->ev_prop, e->ev_aux};
-    for (cudaEvent_t ev : evs)
-        if (ev) cudaEventDestroy(ev);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (Lane &L : e->lanes) {
+        if (L.main_stream) cudaStreamDestroy(L.main_stream);
+        for (int g = 0; g < 3; ++g)
+            if (L.geo_stream[g]) cudaStreamDestroy(L.geo_stream[g]);
+        if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
+        cudaEvent_t evs[] = {L.ev_in, L.ev_fps[0], L.ev_fps[1], L.ev_fps[2], L.ev_lvl[0], L.ev_lvl[1], L.ev_lvl[2],
+                             L.ev_nn, L.ev_knn, L.ev_feat, L.ev_cor, L.ev_prop, L.ev_aux, L.ev_done};
+        for (cudaEvent_t ev : evs)
+            if (ev) cudaEventDestroy(ev);
+    }
     delete e;
 }
 
+RT_API int rt_engine_num_lanes(const rt_engine *e, int b) { return (e && (e->flags & 4) && b >= 8) ? 2 : 1; }
+
 RT_API long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n) {
     if (!e || b < 1 || n < 1) return -1;
-    Carver c(nullptr);
     Ws w;
-    carve(c, w, b, n, e->npoint);
-    return (long long)c.off + 256;
+    if (rt_engine_num_lanes(e, b) == 1) {
+        Carver c(nullptr);
+        carve(c, w, b, n, e->npoint);
+        return (long long)c.off + 256;
+    }
+    const int b0 = (b + 1) / 2;
+    Carver c0(nullptr), c1(nullptr);
+    carve(c0, w, b0, n, e->npoint);
+    carve(c1, w, b - b0, n, e->npoint);
+    return (long long)(((c0.off + 255) & ~(size_t)255) + c1.off + 512);
 }
 
 RT_API int rt_engine_set_profile_events(rt_engine *e, void *start, void *stop) {
@@ -604,26 +624,24 @@ RT_API int rt_engine_set_flags(rt_engine *e, int flags) {
 RT_API int rt_engine_last_status(rt_engine *e, int *status_out) {
     RT_REQUIRE(e && status_out, "engine_last_status: null argument");
     *status_out = 0;
-    if (!e->last_status) return RT_OK;
-    cudaError_t err = cudaMemcpy(status_out, e->last_status, sizeof(int), cudaMemcpyDeviceToHost);
-    if (err != cudaSuccess) {
-        rt_set_error("engine_last_status: %s", cudaGetErrorString(err));
-        return (int)err;
+    for (const int *p : e->last_status) {
+        if (!p) continue;
+        int v = 0;
+        cudaError_t err = cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) {
+            rt_set_error("engine_last_status: %s", cudaGetErrorString(err));
+            return (int)err;
+        }
+        *status_out |= v;
     }
     return RT_OK;
 }
 
-RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
-                               const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
-                               float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
-                               long long workspace_bytes, void *stream) {
-    RT_REQUIRE(e && pc1 && pc2 && ft1 && ft2 && h_in && flow && h_out && cls && cor && f1 && f2 && prop && workspace,
-               "backbone_forward: null argument");
-    RT_REQUIRE(b >= 1 && n >= 1, "backbone_forward: b=%d n=%d", b, n);
-    RT_REQUIRE(2 * b <= 65535, "backbone_forward: batch > 32767");
-    RT_REQUIRE(workspace_bytes >= rt_engine_workspace_bytes(e, b, n), "backbone_forward: workspace too small");
-    RT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "backbone_forward: workspace must be 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+// One lane: b pairs of a call of b_total pairs.  All tensor pointers are already offset to the lane's first pair;
+// h_in / h_out are (5, b_total, 128), so their layer stride is h_stride = b_total * 128.
+static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_stride, int n, const float *pc1, const float *pc2,
+                        const float *ft1, const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                        float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace, cudaStream_t st) {
     Carver c(workspace);
     Ws w;
     carve(c, w, b, n, e->npoint);
@@ -637,26 +655,26 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft2, w.ft0 + half2, 2, 0, st));
     e->launches += 4;
     // fork: geometry depends only on xyz, so it runs on its own stream and the feature path joins stage by stage
-    cudaEventRecord(e->ev_in, st);
-    RT_TRY(run_geometry(e, w, b, n));
+    cudaEventRecord(L.ev_in, st);
+    RT_TRY(run_geometry(e, L, w, b, n));
 
     // feature_extraction_head: pn_head over both clouds of every pair at once (track4d.py:102-106)
     const bool tc_mlp = (e->flags & 2) != 0;
     cudaMemsetAsync(w.status, 0, 64 * sizeof(int), st);
-    e->last_status = w.status;
+    e->last_status[lane_idx] = w.status;
     if (tc_mlp) {
         RtMlpSeg seg_ft{w.ft0, 2, 2, nullptr, nullptr, 0, 0};
-        RT_TRY(run_head_tc(e, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+        RT_TRY(run_head_tc(e, L, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     } else {
         RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
-        RT_TRY(run_head(e, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+        RT_TRY(run_head(e, L, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     }
     RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
     // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95): off the critical path
-    cudaStream_t aux = tc_mlp ? e->aux_stream : st;
+    cudaStream_t aux = tc_mlp ? L.aux_stream : st;
     if (aux != st) {
-        cudaEventRecord(e->ev_feat, st);
-        cudaStreamWaitEvent(aux, e->ev_feat, 0);
+        cudaEventRecord(L.ev_feat, st);
+        cudaStreamWaitEvent(aux, L.ev_feat, 0);
     }
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat, 128, 0, f1, 256, 0, aux));
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat + half128, 128, 0, f2, 256, 0, aux));
@@ -688,21 +706,21 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
     }
-    cudaStreamWaitEvent(st, e->ev_knn, 0);   // join: everything the geometry stream produced is now ordered before `st`
+    cudaStreamWaitEvent(st, L.ev_knn, 0);   // join: everything the geometry stream produced is now ordered before `st`
     if (e->flags & 1) {
-        if (e->prof_start) cudaEventRecord(e->prof_start, st);
+        if (e->prof_start && lane_idx == 0) cudaEventRecord(e->prof_start, st);
         RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
                                     cv.wn1.bc, cv.wn1.wa, cv.wn1.ba, cv.wn1.wb, cv.wn1.bb, w.cost1, w.status, st));
-        if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
+        if (e->prof_stop && lane_idx == 0) cudaEventRecord(e->prof_stop, st);
     } else {
         RtGatherCombine gc{};
         gc.clouds = b; gc.npts = n; gc.ns = kKnn; gc.c = 256;
         gc.y = w.p2; gc.ldy = 256; gc.yoff = 0; gc.n_in = n; gc.idx = w.knn12; gc.xyz_in = x2; gc.xyz_c = x1;
         gc.wx = cv.w1_x; gc.bias = nullptr; gc.q = w.p1; gc.act = RT_ACT_LEAKY01; gc.out = w.xa;
         RT_TRY(rt_launch_gather_combine(gc, st));
-        if (e->prof_start) cudaEventRecord(e->prof_start, st);
+        if (e->prof_start && lane_idx == 0) cudaEventRecord(e->prof_start, st);
         RT_TRY(rt_launch_costvol_mlp(b * n * kKnn, w.xa, cv.w2, cv.b2, cv.w3, cv.b3, w.xa, w.xb, st));
-        if (e->prof_stop) cudaEventRecord(e->prof_stop, st);
+        if (e->prof_stop && lane_idx == 0) cudaEventRecord(e->prof_stop, st);
     }
     {
         RtWeightedSum ws{};
@@ -717,8 +735,8 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         RT_TRY(rt_launch_weighted_sum(ws, st));
     }
     if (aux != st) {
-        cudaEventRecord(e->ev_cor, st);
-        cudaStreamWaitEvent(aux, e->ev_cor, 0);
+        cudaEventRecord(L.ev_cor, st);
+        cudaStreamWaitEvent(aux, L.ev_cor, 0);
     }
     RT_TRY(rt_launch_rows_to_cm(b, 256, n, w.cor, 256, 0, cor, 256, 0, aux));
     e->launches += 10;
@@ -746,23 +764,23 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     if (tc_mlp) {
         RtMlpSeg segs[3] = {RtMlpSeg{w.ft0, 2, 2, nullptr, nullptr, 0, 0}, RtMlpSeg{w.feat, 128, 128, nullptr, nullptr, 0, 0},
                             RtMlpSeg{w.cor, 256, 256, nullptr, nullptr, 0, 0}};
-        RT_TRY(run_head_tc(e, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+        RT_TRY(run_head_tc(e, L, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     } else {
         RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},
                          RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
-        RT_TRY(run_head(e, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+        RT_TRY(run_head(e, L, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     }
     if (aux != st) {
-        cudaEventRecord(e->ev_prop, st);
-        cudaStreamWaitEvent(aux, e->ev_prop, 0);
+        cudaEventRecord(L.ev_prop, st);
+        cudaStreamWaitEvent(aux, L.ev_prop, 0);
     }
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, aux));
-    if (aux != st) cudaEventRecord(e->ev_aux, aux);
+    if (aux != st) cudaEventRecord(L.ev_aux, aux);
     RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
-    RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, st));
+    RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, h_stride, st));
     // FlowPredictor on cat(prop_features, broadcast GRU output)
     const FlowW &fp = e->w.fp;
-    RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + (size_t)4 * b * 128, 128, fp.b1, w.cb_b, st));
+    RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + 4 * h_stride, 128, fp.b1, w.cb_b, st));
     if (tc_mlp) {
         RtMlpTc m = mlp_rows(pts, w.prop, 128, 128);
         mlp_layer(m, e->packs.fw[0], nullptr, 128, 128, RT_ACT_RELU);
@@ -782,8 +800,46 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     }
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
     e->launches += 14;
-    if (aux != st) cudaStreamWaitEvent(st, e->ev_aux, 0);   // join the output stream
+    if (aux != st) cudaStreamWaitEvent(st, L.ev_aux, 0);   // join the output stream
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
+    return rt_check_launch("backbone_forward");
+}
+
+RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                               const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                               float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                               long long workspace_bytes, void *stream) {
+    RT_REQUIRE(e && pc1 && pc2 && ft1 && ft2 && h_in && flow && h_out && cls && cor && f1 && f2 && prop && workspace,
+               "backbone_forward: null argument");
+    RT_REQUIRE(b >= 1 && n >= 1, "backbone_forward: b=%d n=%d", b, n);
+    RT_REQUIRE(2 * b <= 65535, "backbone_forward: batch > 32767");
+    RT_REQUIRE(workspace_bytes >= rt_engine_workspace_bytes(e, b, n), "backbone_forward: workspace too small");
+    RT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "backbone_forward: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hs = (size_t)b * 128;
+    e->last_status[0] = e->last_status[1] = nullptr;
+    if (rt_engine_num_lanes(e, b) == 1)
+        return forward_lane(e, e->lanes[0], 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12,
+                            knn11, workspace, st);
+    // two lanes: pairs [0, b0) and [b0, b) run concurrently on their own stream sets, forked from / joined to `st`
+    const int b0 = (b + 1) / 2;
+    Carver c0(nullptr);
+    Ws w0;
+    carve(c0, w0, b0, n, e->npoint);
+    const size_t ws0 = (c0.off + 255) & ~(size_t)255;
+    cudaEventRecord(e->ev_fork, st);
+    for (int l = 0; l < 2; ++l) {
+        Lane &L = e->lanes[l];
+        const int bl = l ? b - b0 : b0;
+        const size_t o = l ? b0 : 0;   // first pair of the lane
+        cudaStreamWaitEvent(L.main_stream, e->ev_fork, 0);
+        RT_TRY(forward_lane(e, L, l, bl, hs, n, pc1 + o * 3 * n, pc2 + o * 3 * n, ft1 + o * 2 * n, ft2 + o * 2 * n, h_in + o * 128,
+                            flow + o * 3 * n, h_out + o * 128, cls + o * n, cor + o * 256 * n, f1 + o * 256 * n, f2 + o * 256 * n,
+                            prop + o * 128 * n, knn12 ? knn12 + o * n * kKnn : nullptr, knn11 ? knn11 + o * n * kKnn : nullptr,
+                            (char *)workspace + (l ? ws0 : 0), L.main_stream));
+        cudaEventRecord(L.ev_done, L.main_stream);
+        cudaStreamWaitEvent(st, L.ev_done, 0);
+    }
     return rt_check_launch("backbone_forward");
 }

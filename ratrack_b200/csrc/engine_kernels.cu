@@ -675,14 +675,14 @@ int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int 
     return rt_check_launch("broadcast_cm_kernel");
 }
 int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
-                  const float *bhh, float *h_out, cudaStream_t st) {
+                  const float *bhh, float *h_out, size_t h_stride, cudaStream_t st) {
     if (b <= 0) return RT_OK;
     // five dependent layer launches; layer l reads h_in[l] and the previous layer's output
     for (int l = 0; l < 5; ++l) {
-        const float *xin = l == 0 ? x : h_out + (size_t)(l - 1) * b * 128;
-        gru_layer_kernel<<<dim3(4, b), 192, 0, st>>>(b, xin, h_in + (size_t)l * b * 128, wih + (size_t)l * 128 * 384,
+        const float *xin = l == 0 ? x : h_out + (size_t)(l - 1) * h_stride;
+        gru_layer_kernel<<<dim3(4, b), 192, 0, st>>>(b, xin, h_in + (size_t)l * h_stride, wih + (size_t)l * 128 * 384,
                                                     whh + (size_t)l * 128 * 384, bih + l * 384, bhh + l * 384,
-                                                    h_out + (size_t)l * b * 128);
+                                                    h_out + (size_t)l * h_stride);
     }
     return rt_check_launch("gru_layer_kernel");
 }

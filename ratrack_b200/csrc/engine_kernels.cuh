@@ -85,9 +85,9 @@ int rt_launch_rows_to_cm(int b, int c, int n, const float *src, int lds, int sof
                          cudaStream_t st);
 // dst[(b, c, n)] = g[b, c] for all n (broadcast rows of the global feature into a channel-major output)
 int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int dst_c, int dst_coff, cudaStream_t st);
-// 5-layer GRU, one step: x (B,128), h_in (5,B,128) -> h_out (5,B,128); y = h_out[4]
+// 5-layer GRU, one step: x (b,128), h_in / h_out (5, *, 128) with layer stride h_stride floats; y = h_out[4]
 int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
-                  const float *bhh, float *h_out, cudaStream_t st);
+                  const float *bhh, float *h_out, size_t h_stride, cudaStream_t st);
 // cls[(b,n)] = sigmoid(lin_w . (W4 . h3[(b,n), :32]) + lin_b);  flow written by rowgemm + rows_to_cm
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b,
                        float *cls, cudaStream_t st);

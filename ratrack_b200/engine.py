@@ -166,10 +166,16 @@ class FusedBackbone:
             except Exception:
                 pass
 
-    def set_flags(self, costvol_tc: bool = True, mlp_tc: bool = True):
+    def set_flags(self, costvol_tc: bool = True, mlp_tc: bool = True, two_lanes: bool = False):
         """A/B switches: tcgen05 kernels (default) vs the fp32 SIMT kernels of the same dataflow, separately for the
-        cost-volume core (costvol_tc.cu) and for every other dense layer (mlp_tc.cu)."""
-        _cabi.call("rt_engine_set_flags", self._handle, (1 if costvol_tc else 0) | (2 if mlp_tc else 0))
+        cost-volume core (costvol_tc.cu) and for every other dense layer (mlp_tc.cu); two_lanes = run the two halves
+        of a batch (>= 8 pairs) concurrently on separate stream sets."""
+        _cabi.call("rt_engine_set_flags", self._handle,
+                   (1 if costvol_tc else 0) | (2 if mlp_tc else 0) | (4 if two_lanes else 0))
+        self._ws_key = None   # the workspace layout depends on the lane split
+
+    def num_lanes(self, batch):
+        return int(_cabi.lib().rt_engine_num_lanes(self._handle, int(batch)))
 
     def check_status(self):
         """Blocking.  Raises if the last forward flagged an fp16-range overflow in the tensor-core cost volume."""
@@ -231,12 +237,13 @@ class FusedBackbone:
         return flow, h_out, cls, cor, f1, f2, prop
 
 
-def roofline_of_dominant(batch, points, dom_ms, peaks):
+def roofline_of_dominant(batch, points, dom_ms, peaks, launch_pairs=None):
     """Roofline entry of bench.py for the dominant kernel: the dense cost-volume MLP
     (two 256 -> 256 layers over batch*points*16 rows; DESIGN.md "Kernels and rooflines").
     Algorithmic work = the fp32-accurate useful FLOPs, 2 layers x 2*rows*256*256; the denominator is the
     measured dense bf16 tensor throughput (sustained figure: the kernel is timed inside a long step)."""
-    rows = batch * points * 16
+    # the timed launch is lane 0's kernel: it covers launch_pairs of the batch's pairs (all of them with one lane)
+    rows = (launch_pairs or batch) * points * 16
     flops = 2 * 2.0 * rows * 256 * 256
     avg_ms = sum(dom_ms) / max(1, len(dom_ms))
     ach = flops / (avg_ms * 1e-3) / 1e12
@@ -247,7 +254,7 @@ def roofline_of_dominant(batch, points, dom_ms, peaks):
         import os
         t = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
                                         "costvol_traffic.json")))
-        if t["batch"] == batch and t["points"] == points:
+        if t["batch"] == (launch_pairs or batch) and t["points"] == points:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     except (OSError, KeyError, ValueError):
         pass

@@ -171,3 +171,26 @@ def test_fused_handles_odd_sizes():
         for nm, x, y in zip(["flow", "h", "cls", "cor", "f1", "f2", "prop"], a, b):
             scale = max(1.0, float(y.abs().max()))
             assert float((x - y).abs().max()) <= 2 * TOL[nm] * scale, (batch, n, nm)
+
+
+def test_two_lanes_equal_one_lane():
+    """Splitting a batch over two concurrent lanes must not change a single bit of any output (every pair is
+    independent; h is (5, B, 128) so the lanes write strided slices of it)."""
+    from ratrack_b200.engine import FusedBackbone
+
+    net, _ = _net(True)
+    d = synthetic.make_batch(9, 512, seed=3)     # odd batch: lanes of 5 and 4 pairs
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    h = torch.randn(5, 9, 128, device="cuda") * 0.1
+    eng = FusedBackbone(net)
+    outs = {}
+    for lanes in (False, True):
+        eng.set_flags(two_lanes=lanes)
+        assert eng.num_lanes(9) == (2 if lanes else 1)
+        with torch.no_grad():
+            outs[lanes] = [o.clone() for o in eng(t["pc1"], t["pc2"], t["ft1"], t["ft2"], h, want_knn=True)]
+            outs[lanes] += [k.clone() for k in eng.last_knn]
+        torch.cuda.synchronize()
+        eng.check_status()
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
