@@ -27,6 +27,7 @@ constexpr int CT_ROWS = 128, CT_PTS = 8, CT_NS = 16, CT_C = 256;
 constexpr int CT_KC = 32;                          // K per streamed weight chunk
 constexpr int CT_CHUNKS = 2 * (CT_C / CT_KC);      // 8 chunks per layer, 2 layers
 constexpr int CT_STAGES = 4;
+constexpr int CT_GROUPS = CT_C / CT_KC;            // K groups per layer: the unit of the A-operand hand-off (8)
 constexpr int CT_PLANE_BYTES = CT_C * CT_KC * 2;   // one fp16 plane of a chunk: 16 KB
 constexpr int CT_STAGE_BYTES = 2 * CT_PLANE_BYTES; // hi + lo
 constexpr int CT_WC_PLANE = CT_C * 16 * 2;         // WeightNet last layer, K padded 8 -> 16: 8 KB
@@ -45,7 +46,7 @@ constexpr int SM_BC = SM_B3 + CT_C * 4;
 constexpr int SM_WX = SM_BC + CT_C * 4;            // [3][256]
 constexpr int SM_WN = SM_WX + 3 * CT_C * 4;        // wa(24) ba(8) wb(64) bb(8)
 constexpr int SM_BAR = SM_WN + 128 * 4;
-constexpr int SM_TOTAL = SM_BAR + 16 * 8;
+constexpr int SM_TOTAL = SM_BAR + 32 * 8;
 
 struct CostVolTcArgs {
     int total_pts, n;
@@ -116,6 +117,8 @@ __device__ __forceinline__ uint64_t ct_desc(uint32_t saddr, uint32_t lbo, uint32
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
 }
+// K groups are consumed in the order both worker halves produce them: 0,4,1,5,... (half 0 owns groups 0-3, half 1 4-7)
+__device__ __forceinline__ int ct_group_at(int i) { return (i >> 1) + 4 * (i & 1); }
 // F16 x F16 -> F32, A and B K-major, M = 128, N = 256
 constexpr uint32_t CT_IDESC = (1u << 4) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_ROWS >> 4) << 24);
 
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
     float *s_wn = reinterpret_cast<float *>(smem + SM_WN);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + SM_BAR);
     uint64_t *bar_empty = bar_full + CT_STAGES;
-    uint64_t *bar_a = bar_empty + CT_STAGES;
-    uint64_t *bar_d = bar_a + 1;
+    uint64_t *bar_a = bar_empty + CT_STAGES;   // [CT_GROUPS]: A columns of one 32-wide K group are in TMEM
+    uint64_t *bar_d = bar_a + CT_GROUPS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_d + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             rt_mbar_init(&bar_full[s], 1);
             rt_mbar_init(&bar_empty[s], 1);
         }
-        rt_mbar_init(bar_a, CT_WORKER_WARPS);
+        for (int g = 0; g < CT_GROUPS; ++g) rt_mbar_init(&bar_a[g], CT_WORKER_WARPS / 2);  // the 4 warps owning that K half
         rt_mbar_init(bar_d, 1);
         rt_fence_mbar_init();
     }
@@ -227,8 +230,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 for (int c = 0; c < CT_CHUNKS; ++c) {
                     ct_mbar_wait(&bar_empty[stage], phase ^ 1);
                     rt_mbar_expect_tx(&bar_full[stage], CT_STAGE_BYTES);
+                    const int chunk = (c / CT_GROUPS) * CT_GROUPS + ct_group_at(c % CT_GROUPS);   // layer-major, MMA order
                     rt_bulk_g2s(s_stage + stage * CT_STAGE_BYTES,
-                                reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)c * CT_STAGE_BYTES, CT_STAGE_BYTES,
+                                reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)chunk * CT_STAGE_BYTES, CT_STAGE_BYTES,
                                 &bar_full[stage]);
                     if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -244,20 +248,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             const uint32_t wc_hi = rt_smem_u32(s_wc), wc_lo = wc_hi + CT_WC_PLANE;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int layer = 0; layer < 2; ++layer) {
-                    ct_mbar_wait(bar_a, a_phase);
-                    a_phase ^= 1;
-                    ct_fence_after();
-                    for (int c = 0; c < CT_C / CT_KC; ++c) {
+                    for (int c = 0; c < CT_GROUPS; ++c) {
+                        const int g = ct_group_at(c);
+                        ct_mbar_wait(&bar_a[g], a_phase);   // this K group of the A operand has landed in TMEM:
+                        ct_fence_after();                   // the MMAs start while the workers still produce later groups
                         ct_mbar_wait(&bar_full[stage], phase);
                         ct_fence_after();
                         const uint32_t base = rt_smem_u32(s_stage + stage * CT_STAGE_BYTES);
 #pragma unroll
                         for (int j = 0; j < CT_KC / 16; ++j) {
-                            const int kk = c * (CT_KC / 16) + j;
+                            const int kk = g * (CT_KC / 16) + j;
                             // chunk plane = [kc = K/8][row group = 32][8 rows][8 halfs]: kc stride 4096 B, row group 128 B
                             const uint64_t bhi = ct_desc(base + j * 8192, 4096, 128);
                             const uint64_t blo = ct_desc(base + CT_PLANE_BYTES + j * 8192, 4096, 128);
-                            ct_mma_ts(tD, tAhi + 8 * kk, bhi, CT_IDESC, kk > 0);
+                            ct_mma_ts(tD, tAhi + 8 * kk, bhi, CT_IDESC, (c | j) > 0);
                             ct_mma_ts(tD, tAlo + 8 * kk, bhi, CT_IDESC, 1);
                             ct_mma_ts(tD, tAhi + 8 * kk, blo, CT_IDESC, 1);
                         }
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_lo, 4096, 128), CT_IDESC, 1);
                     }
                     ct_commit(bar_d);
+                    a_phase ^= 1;
                 }
             }
         }
@@ -343,12 +348,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         cur.v[g] = vn[g];
                     }
                 }
+                if ((c0 & 16) != 0) {
+                    // a 32-column K group is complete: hand it to the MMA warp, which starts layer 2 on it right away
+                    ct_st_wait();
+                    ct_fence_before();
+                    rt_fence_proxy_async();  // s_aw stores -> async proxy (needed before the WeightNet MMA much later)
+                    __syncwarp();
+                    if (lane == 0) rt_mbar_arrive(&bar_a[c0 >> 5]);
+                }
             }
-            ct_st_wait();
-            ct_fence_before();
-            rt_fence_proxy_async();  // s_aw stores -> async proxy
-            __syncwarp();
-            if (lane == 0) rt_mbar_arrive(bar_a);
 
             // ---------- mid epilogue: layer-2 accumulator -> bias, LeakyReLU -> A operand of layer 3 ----------
             ct_mbar_wait(bar_d, d_phase);
@@ -369,8 +377,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             }
             ct_st_wait();
             ct_fence_before();
-            __syncwarp();
-            if (lane == 0) rt_mbar_arrive(bar_a);
+            // layer 3 overwrites the accumulator every worker is still reading: release all K groups only when all 8
+            // worker warps are done with it
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_WORKER_WARPS) : "memory");
+            if (lane == 0)
+                for (int g = 4 * hlf; g < 4 * hlf + 4; ++g) rt_mbar_arrive(&bar_a[g]);
             // next tile's index / xyz / first P1,P2 chunk: in flight during the layer-3 MMAs and the final epilogue
             const int p_out = p;
             const bool valid_out = valid;
