@@ -487,9 +487,9 @@ __global__ void __launch_bounds__(256) cloud_max_kernel(int npts, int c, const f
 __global__ void __launch_bounds__(256) cloud_matvec_kernel(int nout, int k, const float *__restrict__ w, int ldw,
                                                            const float *__restrict__ g, int ldg, const float *__restrict__ bias,
                                                            float *__restrict__ cb) {
-    // grid (cloud); one warp per output, lanes stride over k
+    // grid (cloud, output block of 8); one warp per output, lanes stride over k
     const int cloud = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = warp; o < nout; o += 8) {
+    for (int o = blockIdx.y * 8 + warp; o < nout && o < blockIdx.y * 8 + 8; o += 8) {
         float acc = 0.0f;
         for (int kk = lane; kk < k; kk += 32) acc = fmaf(__ldg(w + (long long)o * ldw + kk), __ldg(g + (long long)cloud * ldg + kk), acc);
 #pragma unroll
@@ -652,7 +652,7 @@ int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, fl
 int rt_launch_cloud_matvec(int clouds, int nout, int k, const float *w, int ldw, const float *g, int ldg, const float *bias,
                            float *cb, cudaStream_t st) {
     if (clouds <= 0) return RT_OK;
-    cloud_matvec_kernel<<<clouds, 256, 0, st>>>(nout, k, w, ldw, g, ldg, bias, cb);
+    cloud_matvec_kernel<<<dim3(clouds, rt_divup(nout, 8)), 256, 0, st>>>(nout, k, w, ldw, g, ldg, bias, cb);
     return rt_check_launch("cloud_matvec_kernel");
 }
 int rt_launch_cm_to_rows(int b, int c, int n, const float *src, float *dst, int ldd, int coff, cudaStream_t st) {

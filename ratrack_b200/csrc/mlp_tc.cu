@@ -143,7 +143,7 @@ __device__ __forceinline__ void mt_gather_issue(const RtMlpTc &a, long long tile
 template <int LOAD_MODE>
 __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_a, bar_d;
+    __shared__ __align__(8) uint64_t bar_a, bar_d, bar_w;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = (a.rows + 127) / 128;
@@ -153,11 +153,17 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
     w_off[0] = 0;
 #pragma unroll
     for (int l = 0; l < RT_MLP_MAX_LAYERS; ++l) w_off[l + 1] = w_off[l] + (l < a.nlayers ? 4 * a.layer[l].k * a.layer[l].n : 0);
-    for (int l = 0; l < a.nlayers; ++l) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.layer[l].wpack);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem + w_off[l]);
-        const int n16 = (w_off[l + 1] - w_off[l]) / 16;
-        for (int i = threadIdx.x; i < n16; i += MT_THREADS) dst[i] = __ldg(src + i);
+    // the bulk-copy engine (UBLKCP) brings every layer's weights in while the workers already fetch their first rows
+    if (threadIdx.x == 0) {
+        rt_mbar_init(&bar_w, 1);
+        rt_fence_mbar_init();
+        rt_mbar_expect_tx(&bar_w, (uint32_t)w_off[RT_MLP_MAX_LAYERS]);
+        for (int l = 0; l < a.nlayers; ++l) {
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(a.layer[l].wpack);
+            const int bytes = w_off[l + 1] - w_off[l];
+            for (int o = 0; o < bytes; o += 32768)
+                rt_bulk_g2s(smem + w_off[l] + o, src + o, (uint32_t)min(32768, bytes - o), &bar_w);
+        }
     }
     // per-layer biases -> shared memory (zeros when a layer has none), 256 floats per layer
     float *s_bias = reinterpret_cast<float *>(smem + w_off[RT_MLP_MAX_LAYERS]);
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t a_phase = 0;
+            mt_mbar_wait(&bar_w, 0);   // weights have landed in shared memory
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int l = 0; l < a.nlayers; ++l) {
                     mt_mbar_wait(&bar_a, a_phase);

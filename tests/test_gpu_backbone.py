@@ -159,7 +159,7 @@ def test_tensor_core_kernels_match_simt_chain():
 
 def test_fused_handles_odd_sizes():
     """N not a multiple of 4/8/16, N < npoints, batch 1 and 5: the engine vs the modular path on the same device."""
-    for batch, n in ((1, 333), (5, 700), (2, 256)):
+    for batch, n in ((1, 333), (5, 700), (2, 256), (2, 3000)):
         net, _ = _net(True)
         d = synthetic.make_batch(batch, n, seed=n)
         t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
