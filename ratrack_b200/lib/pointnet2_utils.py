@@ -1,19 +1,22 @@
-"""Seam B operators: same names, signatures, return shapes and differentiability as the reference's
-src/lib/pointnet2_utils.py, running on the sm_100a kernels of libratrack_b200.so.
+"""Seam B operators on the sm_100a kernels of libratrack_b200.so.
 
-furthest_point_sample(xyz, npoint) -> (B,npoint) i32          (reference :10-36)
-gather_operation(features, idx) -> (B,C,npoint)                (:39-73, grad -> features)
-knn(k, unknown, known) -> (sqrt dist (B,N,k), idx i32)         (:75-102)
-three_nn(unknown, known) -> (sqrt dist (B,n,3), idx i32)       (:104-133)
-three_interpolate(features, idx, weight) -> (B,C,n)            (:136-181, grad -> features)
-grouping_operation(features, idx) -> (B,C,npoint,nsample)      (:184-225, grad -> features)
-ball_query(radius, nsample, xyz, new_xyz) -> (B,npoint,nsample) i32   (:228-256)
-QueryAndGroup / GroupAll                                        (:259-318)
+Public surface = the names the reference's modules import from src/lib/pointnet2_utils.py, with the same
+argument order, return shapes / dtypes and differentiability:
 
-Index-producing ops return no gradients, exactly as in the reference.
+    furthest_point_sample(xyz (B,N,3), npoint)              -> (B,npoint) int32          reference :10-36
+    gather_operation(features (B,C,N), idx (B,M))           -> (B,C,M)     grad -> features        :39-73
+    knn(k, unknown (B,n,3), known (B,m,3))                  -> (dist (B,n,k), idx int32)            :75-102
+    three_nn(unknown (B,n,3), known (B,m,3))                -> (dist (B,n,3), idx int32)            :104-133
+    three_interpolate(features (B,C,m), idx, weight)        -> (B,C,n)     grad -> features        :136-181
+    grouping_operation(features (B,C,N), idx (B,P,S))       -> (B,C,P,S)   grad -> features        :184-225
+    ball_query(radius, nsample, xyz (B,N,3), new_xyz)       -> (B,npoint,nsample) int32            :228-256
+    QueryAndGroup, GroupAll                                                                         :259-318
+
+Index-producing ops carry no gradient in the reference (their backward returns None), so here they are plain
+functions evaluated without autograd; the two copy-type ops share one autograd Function (a gather and its
+scatter-add), three_interpolate has its own.  `dist` outputs are square roots of the kernels' squared distances,
+as in the reference (:97, :126).
 """
-from typing import Tuple
-
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -21,197 +24,156 @@ from torch.autograd import Function
 from .. import pointnet2_cuda as pointnet2
 
 
-def _need(t: torch.Tensor, what: str):
-    assert t.is_contiguous(), f"{what} must be contiguous"
+def _contig(t, what):
+    if not t.is_contiguous():
+        raise AssertionError(f"{what} must be contiguous")
+    return t
 
 
-class FurthestPointSampling(Function):
+def _new(shape, like, dtype):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ---- ops without gradients ---------------------------------------------------------------------------------
+@torch.no_grad()
+def furthest_point_sample(xyz, npoint):
+    B, N, _ = _contig(xyz, "xyz").shape
+    idx = _new((B, npoint), xyz, torch.int32)
+    running_min = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)   # reference :26
+    pointnet2.furthest_point_sampling_wrapper(B, N, npoint, xyz, running_min, idx)
+    return idx
+
+
+@torch.no_grad()
+def ball_query(radius, nsample, xyz, new_xyz):
+    B, N, _ = _contig(xyz, "xyz").shape
+    M = _contig(new_xyz, "new_xyz").shape[1]
+    idx = torch.zeros((B, M, nsample), dtype=torch.int32, device=xyz.device)   # rows without a hit stay 0 (:246)
+    pointnet2.ball_query_wrapper(B, N, M, radius, nsample, new_xyz, xyz, idx)
+    return idx
+
+
+def _nearest(wrapper, k, unknown, known):
+    B, n, _ = _contig(unknown, "unknown").shape
+    m = _contig(known, "known").shape[1]
+    d2 = _new((B, n, k), unknown, torch.float32)
+    idx = _new((B, n, k), unknown, torch.int32)
+    if wrapper is pointnet2.knn_wrapper:
+        wrapper(B, n, m, k, unknown, known, d2, idx)
+    else:
+        wrapper(B, n, m, unknown, known, d2, idx)
+    return torch.sqrt(d2), idx
+
+
+@torch.no_grad()
+def three_nn(unknown, known):
+    return _nearest(pointnet2.three_nn_wrapper, 3, unknown, known)
+
+
+@torch.no_grad()
+def knn(k, unknown, known):
+    return _nearest(pointnet2.knn_wrapper, k, unknown, known)
+
+
+# ---- copy-type ops with gradients ----------------------------------------------------------------------------
+class _IndexedCopy(Function):
+    """out[b,c,...] = features[b,c,idx[b,...]]; backward scatter-adds into a zero tensor (atomicAdd, as the reference)."""
+
     @staticmethod
-    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
-        _need(xyz, "xyz")
-        B, N, _ = xyz.size()
-        output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-        pointnet2.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, output)
-        ctx.mark_non_differentiable(output)
-        return output
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None
-
-
-furthest_point_sample = FurthestPointSampling.apply
-
-
-class GatherOperation(Function):
-    @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        _need(features, "features")
-        _need(idx, "idx")
-        B, npoint = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-        pointnet2.gather_points_wrapper(B, C, N, npoint, features, idx, output)
-        ctx.for_backwards = (idx, C, N)
-        return output
+    def forward(ctx, features, idx):
+        _contig(features, "features")
+        idx = _contig(idx, "idx").int()
+        B, C, N = features.shape
+        ctx.n_src = N
+        ctx.idx = idx
+        if idx.dim() == 2:
+            out = _new((B, C, idx.shape[1]), features, torch.float32)
+            pointnet2.gather_points_wrapper(B, C, N, idx.shape[1], features, idx, out)
+        else:
+            P, S = idx.shape[1:]
+            out = _new((B, C, P, S), features, torch.float32)
+            pointnet2.group_points_wrapper(B, C, N, P, S, features, idx, out)
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, C, N = ctx.for_backwards
-        B, npoint = idx.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
-        return grad_features, None
+        idx, g = ctx.idx, grad_out.contiguous()
+        B, C = g.shape[:2]
+        grad = torch.zeros((B, C, ctx.n_src), dtype=torch.float32, device=g.device)
+        if idx.dim() == 2:
+            pointnet2.gather_points_grad_wrapper(B, C, ctx.n_src, idx.shape[1], g, idx, grad)
+        else:
+            pointnet2.group_points_grad_wrapper(B, C, ctx.n_src, idx.shape[1], idx.shape[2], g, idx, grad)
+        return grad, None
 
 
-gather_operation = GatherOperation.apply
+def gather_operation(features, idx):
+    assert idx.dim() == 2
+    return _IndexedCopy.apply(features, idx)
 
 
-class KNN(Function):
+def grouping_operation(features, idx):
+    assert idx.dim() == 3
+    return _IndexedCopy.apply(features, idx)
+
+
+class _Interpolate3(Function):
     @staticmethod
-    def forward(ctx, k: int, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        _need(unknown, "unknown")
-        _need(known, "known")
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty((B, N, k), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, N, k), dtype=torch.int32, device=unknown.device)
-        pointnet2.knn_wrapper(B, N, m, k, unknown, known, dist2, idx)
-        ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
-
-    @staticmethod
-    def backward(ctx, a=None, b=None):
-        return None, None, None
-
-
-knn = KNN.apply
-
-
-class ThreeNN(Function):
-    @staticmethod
-    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        _need(unknown, "unknown")
-        _need(known, "known")
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
-        ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
+    def forward(ctx, features, idx, weight):
+        for t, nm in ((features, "features"), (idx, "idx"), (weight, "weight")):
+            _contig(t, nm)
+        B, C, m = features.shape
+        n = idx.shape[1]
+        ctx.saved = (idx, weight, m)
+        out = _new((B, C, n), features, torch.float32)
+        pointnet2.three_interpolate_wrapper(B, C, m, n, features, idx, weight, out)
+        return out
 
     @staticmethod
-    def backward(ctx, a=None, b=None):
-        return None, None
+    def backward(ctx, grad_out):
+        idx, weight, m = ctx.saved
+        g = grad_out.contiguous()
+        B, C, n = g.shape
+        grad = torch.zeros((B, C, m), dtype=torch.float32, device=g.device)
+        pointnet2.three_interpolate_grad_wrapper(B, C, n, m, g, idx, weight, grad)
+        return grad, None, None
 
 
-three_nn = ThreeNN.apply
+three_interpolate = _Interpolate3.apply
+
+# the reference's autograd class names, for code that spells `<Class>.apply`
+GatherOperation = GroupingOperation = _IndexedCopy
+ThreeInterpolate = _Interpolate3
 
 
-class ThreeInterpolate(Function):
-    @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-        _need(features, "features")
-        _need(idx, "idx")
-        _need(weight, "weight")
-        B, c, m = features.size()
-        n = idx.size(1)
-        ctx.three_interpolate_for_backward = (idx, weight, m)
-        output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-        pointnet2.three_interpolate_wrapper(B, c, m, n, features, idx, weight, output)
-        return output
-
-    @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
-        idx, weight, m = ctx.three_interpolate_for_backward
-        B, c, n = grad_out.size()
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-        pointnet2.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
-        return grad_features, None, None
-
-
-three_interpolate = ThreeInterpolate.apply
-
-
-class GroupingOperation(Function):
-    @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        _need(features, "features")
-        _need(idx, "idx")
-        idx = idx.int()
-        B, nfeatures, nsample = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-        pointnet2.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, output)
-        ctx.for_backwards = (idx, N)
-        return output
-
-    @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
-        idx, N = ctx.for_backwards
-        B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
-        return grad_features, None
-
-
-grouping_operation = GroupingOperation.apply
-
-
-class BallQuery(Function):
-    @staticmethod
-    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-        _need(new_xyz, "new_xyz")
-        _need(xyz, "xyz")
-        B, N, _ = xyz.size()
-        npoint = new_xyz.size(1)
-        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
-        ctx.mark_non_differentiable(idx)
-        return idx
-
-    @staticmethod
-    def backward(ctx, a=None):
-        return None, None, None, None
-
-
-ball_query = BallQuery.apply
-
-
+# ---- grouping modules ------------------------------------------------------------------------------------------
 class QueryAndGroup(nn.Module):
-    """ball_query -> grouped (xyz - centre) ++ grouped features, xyz channels first (reference :259-292)."""
+    """ball_query -> [grouped xyz - centre ; grouped features] with the xyz channels first (reference :259-292)."""
 
-    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+    def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+    def forward(self, xyz, new_xyz, features=None):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        rel = grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            return grouped_xyz
-        grouped_features = grouping_operation(features, idx)
-        if self.use_xyz:
-            return torch.cat([grouped_xyz, grouped_features], dim=1)
-        return grouped_features
+            return rel
+        grouped = grouping_operation(features, idx)
+        return torch.cat([rel, grouped], dim=1) if self.use_xyz else grouped
 
 
 class GroupAll(nn.Module):
-    """reference :295-318"""
+    """One group holding every point (reference :295-318)."""
 
-    def __init__(self, use_xyz: bool = True):
+    def __init__(self, use_xyz=True):
         super().__init__()
         self.use_xyz = use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+    def forward(self, xyz, new_xyz, features=None):
+        everything = xyz.transpose(1, 2).unsqueeze(2)
         if features is None:
-            return grouped_xyz
-        grouped_features = features.unsqueeze(2)
-        if self.use_xyz:
-            return torch.cat([grouped_xyz, grouped_features], dim=1)
-        return grouped_features
+            return everything
+        feats = features.unsqueeze(2)
+        return torch.cat([everything, feats], dim=1) if self.use_xyz else feats
