@@ -52,6 +52,7 @@ struct CostVolTcArgs {
     int total_pts, n;
     const float *p1, *p2, *xyz1, *xyz2;
     const int *knn;
+    const int *perm;   // processing order (slot -> point), see rt_launch_morton_perm; null = identity
     const float *w1x;
     const __half *wpack, *wcpack;
     const float *b2, *b3, *bc, *wa, *ba, *wb, *bb;
@@ -153,8 +154,9 @@ __device__ __forceinline__ void ct_issue_chunk(const CostVolTcArgs &a, const CtR
     }
 }
 __device__ __forceinline__ void ct_issue_row(const CostVolTcArgs &a, int tile, int row, int cbeg, CtRow &r) {
-    r.p = tile * CT_PTS + (row >> 4);
-    r.valid = r.p < a.total_pts;
+    const int slot = tile * CT_PTS + (row >> 4);
+    r.valid = slot < a.total_pts;
+    r.p = r.valid ? (a.perm ? __ldg(a.perm + slot) : slot) : a.total_pts;
     r.pc = r.valid ? r.p : a.total_pts - 1;
     const int cloud = r.pc / a.n;
     const int nbr = __ldg(a.knn + (size_t)r.pc * CT_NS + (row & 15));
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
 // engine-internal launcher.  wpack = [layer 2,3][8 chunks][hi,lo][kc 4][row group 32][8][8] fp16 of 2^10 * W;
 // wcpack = [hi,lo][kc 2][row group 32][8][8] fp16 of 2^10 * Wc (K 8 padded to 16).
 int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2, const float *xyz1, const float *xyz2,
-                         const int *knn, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
+                         const int *knn, const int *perm, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
                          const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
                          float *out, int *status, cudaStream_t st) {
     if (total_pts <= 0) return RT_OK;
@@ -467,7 +469,7 @@ int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = (total_pts + CT_PTS - 1) / CT_PTS;
-    CostVolTcArgs a{total_pts, n, p1, p2, xyz1, xyz2, knn, w1x, (const __half *)wpack, (const __half *)wcpack,
+    CostVolTcArgs a{total_pts, n, p1, p2, xyz1, xyz2, knn, perm, w1x, (const __half *)wpack, (const __half *)wcpack,
                     b2, b3, bc, wa, ba, wb, bb, out, status};
     costvol_tc_kernel<<<ntiles < sms ? ntiles : sms, CT_THREADS, SM_TOTAL, st>>>(a);
     return rt_check_launch("costvol_tc_kernel");

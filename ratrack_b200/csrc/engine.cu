@@ -18,11 +18,12 @@
 #include "engine_kernels.cuh"
 #include "mlp_tc.cuh"
 
+void rt_fps_set_exclusive(int on);  // fps.cu
 int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
                           float *xa, float *xb, cudaStream_t st);  // engine-internal, below
 // costvol_tc.cu: gather + 3-layer MLP + WeightNet-weighted neighbour sum on tcgen05
 int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2, const float *xyz1, const float *xyz2,
-                         const int *knn, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
+                         const int *knn, const int *perm, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
                          const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
                          float *out, int *status, cudaStream_t st);
 
@@ -86,10 +87,10 @@ struct Carver {
 
 struct Ws {
     float *xyz0, *ft0, *xyz[3], *temp;
-    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11;
+    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11, *perm1;
     float *nn_w[3];
     float *proj, *xa, *xb, *pooled, *l1, *l2, *l3, *l2p, *l1p, *interp, *feat, *prop;
-    float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h;
+    float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h, *gru_gh;
     int *status;
 };
 
@@ -110,6 +111,7 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     }
     w.knn12 = c.take<int>((size_t)b * n * kKnn);
     w.knn11 = c.take<int>((size_t)b * n * kKnn);
+    w.perm1 = c.take<int>((size_t)b * n);
     const size_t head_rows = B2 * S * 32 * 64;  // widest SA activation: ns=32 x 64 channels
     const size_t cv_rows = (size_t)b * n * kKnn * 256;
     const size_t xbuf = head_rows > cv_rows ? head_rows : cv_rows;
@@ -138,6 +140,7 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     w.h3 = c.take<float>((size_t)b * n * 32);
     w.flow_rows = c.take<float>((size_t)b * n * 3);
     w.gru_h = c.take<float>((size_t)5 * b * 128);
+    w.gru_gh = c.take<float>((size_t)5 * b * 384);
     w.status = c.take<int>(64);
 }
 
@@ -177,7 +180,7 @@ struct Lane {
     // output stream: API-layout transposes and the cls head hang off the feature path, nothing waits for them until the end
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
-                ev_nn = nullptr, ev_knn = nullptr, ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr,
+                ev_nn = nullptr, ev_knn = nullptr, ev_gh = nullptr, ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr,
                 ev_done = nullptr;
 };
 
@@ -190,9 +193,14 @@ struct rt_engine {
     long long launches = 0;
     Lane lanes[2];
     cudaEvent_t ev_fork = nullptr;
-    int flags = 3;                 // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
+    int flags = 59;                // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
                                    // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow;
                                    // bit 2 (off by default: measured 4 % slower at 32 pairs, neutral at 128): split batches of >= 8 pairs over two lanes
+                                   // bit 3: FPS CTAs claim a whole SM each (fps.cu launch_reg) so co-running kernels cannot stretch the chain
+                                   // bit 4: cost-volume kNN starts with the FPS chain instead of behind it (pair with bit 3)
+                                   // bit 6: the cost-volume kernels walk pc1 in Morton order (tiles of spatial neighbours share gathered rows)
+                                   // bit 5: the feature path runs on an engine-owned stream of middle priority (geometry above it, kNN
+                                   //        and API-layout outputs below it) forked from / joined to the caller's stream
     const int *last_status[2] = {nullptr, nullptr};
 };
 
@@ -206,6 +214,20 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     const float *lvl_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
     const int lvl_n[3] = {n, S, S};
     for (int g = 0; g < 3; ++g) cudaStreamWaitEvent(L.geo_stream[g], L.ev_in, 0);
+    const float *pc1 = w.xyz0, *pc2 = w.xyz0 + (size_t)b * n * 3;
+    const bool knn_early = (e->flags & 16) != 0;
+    // Morton processing order of pc1 for the cost-volume kernels (bit 6); needs xyz only
+    if (e->flags & 64) {
+        RT_TRY(rt_launch_morton_perm(b, n, pc1, w.perm1, s_knn));
+        e->launches += 1;
+    }
+    if (knn_early) {
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+        cudaEventRecord(L.ev_knn, s_knn);
+        e->launches += 2;
+    }
+    rt_fps_set_exclusive((e->flags & 8) ? 1 : 0);
     for (int l = 0; l < 3; ++l) {
         RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
         RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
@@ -219,6 +241,7 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
         cudaEventRecord(L.ev_lvl[l], s_nbr);
         e->launches += 5;
     }
+    rt_fps_set_exclusive(0);
     // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
     const float *unk[3] = {w.xyz[1], w.xyz[0], w.xyz0};
     const float *kn[3] = {w.xyz[2], w.xyz[1], w.xyz[0]};
@@ -232,12 +255,13 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     // cost-volume kNN: only after the FPS chain.  FPS is a chain of ~1500 dependent rounds on 2b CTAs; measured on
     // B200, any kernel sharing its SMs stretches every round 2-3x (438 us instead of 148 us for FPS-1 with the kNN
     // beside it), so the throughput-bound kNN is ordered behind it and overlaps the SA / FP kernels instead.
-    const float *pc1 = w.xyz0, *pc2 = w.xyz0 + (size_t)b * n * 3;
-    cudaStreamWaitEvent(s_knn, L.ev_fps[2], 0);
-    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
-    RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
-    cudaEventRecord(L.ev_knn, s_knn);
-    e->launches += 2;
+    if (!knn_early) {
+        cudaStreamWaitEvent(s_knn, L.ev_fps[2], 0);
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+        cudaEventRecord(L.ev_knn, s_knn);
+        e->launches += 2;
+    }
     return RT_OK;
 }
 
@@ -552,12 +576,19 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
         }
     }
     cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    // priorities: the latency-bound geometry chain (FPS, ball query, three_nn) first, the feature path next, the
+    // throughput-bound cost-volume kNN and the API-layout output copies last -- they fill whatever is idle
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    const int prio_mid = prio_greatest < prio_least - 1 ? prio_greatest + 1 : prio_greatest;
     for (Lane &L : e->lanes) {
-        cudaStreamCreateWithFlags(&L.main_stream, cudaStreamNonBlocking);
-        for (int g = 0; g < 3; ++g) cudaStreamCreateWithFlags(&L.geo_stream[g], cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&L.aux_stream, cudaStreamNonBlocking);
+        cudaStreamCreateWithPriority(&L.main_stream, cudaStreamNonBlocking, prio_mid);
+        cudaStreamCreateWithPriority(&L.geo_stream[0], cudaStreamNonBlocking, prio_greatest);
+        cudaStreamCreateWithPriority(&L.geo_stream[1], cudaStreamNonBlocking, prio_greatest);
+        cudaStreamCreateWithPriority(&L.geo_stream[2], cudaStreamNonBlocking, prio_least);
+        cudaStreamCreateWithPriority(&L.aux_stream, cudaStreamNonBlocking, prio_least);
         cudaEvent_t *evs[] = {&L.ev_in, &L.ev_fps[0], &L.ev_fps[1], &L.ev_fps[2], &L.ev_lvl[0], &L.ev_lvl[1], &L.ev_lvl[2],
-                              &L.ev_nn, &L.ev_knn, &L.ev_feat, &L.ev_cor, &L.ev_prop, &L.ev_aux, &L.ev_done};
+                              &L.ev_nn, &L.ev_knn, &L.ev_gh, &L.ev_feat, &L.ev_cor, &L.ev_prop, &L.ev_aux, &L.ev_done};
         for (cudaEvent_t *ev : evs) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     }
     const int rc = build_packs(e);
@@ -580,7 +611,7 @@ RT_API void rt_engine_destroy(rt_engine *e) {
             if (L.geo_stream[g]) cudaStreamDestroy(L.geo_stream[g]);
         if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
         cudaEvent_t evs[] = {L.ev_in, L.ev_fps[0], L.ev_fps[1], L.ev_fps[2], L.ev_lvl[0], L.ev_lvl[1], L.ev_lvl[2],
-                             L.ev_nn, L.ev_knn, L.ev_feat, L.ev_cor, L.ev_prop, L.ev_aux, L.ev_done};
+                             L.ev_nn, L.ev_knn, L.ev_gh, L.ev_feat, L.ev_cor, L.ev_prop, L.ev_aux, L.ev_done};
         for (cudaEvent_t ev : evs)
             if (ev) cudaEventDestroy(ev);
     }
@@ -657,6 +688,10 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     // fork: geometry depends only on xyz, so it runs on its own stream and the feature path joins stage by stage
     cudaEventRecord(L.ev_in, st);
     RT_TRY(run_geometry(e, L, w, b, n));
+    // hidden half of the GRU (depends on h_in only): off the critical path, on the output stream
+    cudaStreamWaitEvent(L.aux_stream, L.ev_in, 0);
+    RT_TRY(rt_launch_gru_hh(b, h_in, e->w.gru.whh, e->w.gru.bhh, h_stride, w.gru_gh, L.aux_stream));
+    cudaEventRecord(L.ev_gh, L.aux_stream);
 
     // feature_extraction_head: pn_head over both clouds of every pair at once (track4d.py:102-106)
     const bool tc_mlp = (e->flags & 2) != 0;
@@ -709,7 +744,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     cudaStreamWaitEvent(st, L.ev_knn, 0);   // join: everything the geometry stream produced is now ordered before `st`
     if (e->flags & 1) {
         if (e->prof_start && lane_idx == 0) cudaEventRecord(e->prof_start, st);
-        RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
+        RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, (e->flags & 64) ? w.perm1 : nullptr, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
                                     cv.wn1.bc, cv.wn1.wa, cv.wn1.ba, cv.wn1.wb, cv.wn1.bb, w.cost1, w.status, st));
         if (e->prof_stop && lane_idx == 0) cudaEventRecord(e->prof_stop, st);
     } else {
@@ -728,6 +763,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         ws.idx = w.knn12; ws.xyz_in = x2; ws.xyz_c = x1;
         ws.wa = cv.wn1.wa; ws.ba = cv.wn1.ba; ws.wb = cv.wn1.wb; ws.bb = cv.wn1.bb; ws.wc = cv.wn1.wc; ws.bc = cv.wn1.bc;
         ws.v = w.xa; ws.out = w.cost1;
+        ws.perm = (e->flags & 64) ? w.perm1 : nullptr;
         if (!(e->flags & 1)) RT_TRY(rt_launch_weighted_sum(ws, st));
         ws.gather_v = 1; ws.idx = w.knn11; ws.xyz_in = x1;
         ws.wa = cv.wn2.wa; ws.ba = cv.wn2.ba; ws.wb = cv.wn2.wb; ws.bb = cv.wn2.bb; ws.wc = cv.wn2.wc; ws.bc = cv.wn2.bc;
@@ -777,7 +813,8 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, aux));
     if (aux != st) cudaEventRecord(L.ev_aux, aux);
     RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
-    RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.whh, e->w.gru.bih, e->w.gru.bhh, h_out, h_stride, st));
+    cudaStreamWaitEvent(st, L.ev_gh, 0);
+    RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.bih, w.gru_gh, h_out, h_stride, st));
     // FlowPredictor on cat(prop_features, broadcast GRU output)
     const FlowW &fp = e->w.fp;
     RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + 4 * h_stride, 128, fp.b1, w.cb_b, st));
@@ -799,7 +836,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 3, w.h3, 32, 32, fp.w4, nullptr, RT_ACT_NONE, w.flow_rows, 3), st));
     }
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
-    e->launches += 14;
+    e->launches += 11;
     if (aux != st) cudaStreamWaitEvent(st, L.ev_aux, 0);   // join the output stream
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
@@ -819,9 +856,19 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     cudaStream_t st = (cudaStream_t)stream;
     const size_t hs = (size_t)b * 128;
     e->last_status[0] = e->last_status[1] = nullptr;
-    if (rt_engine_num_lanes(e, b) == 1)
-        return forward_lane(e, e->lanes[0], 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12,
-                            knn11, workspace, st);
+    if (rt_engine_num_lanes(e, b) == 1) {
+        if (!(e->flags & 32))
+            return forward_lane(e, e->lanes[0], 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12,
+                                knn11, workspace, st);
+        Lane &L = e->lanes[0];
+        cudaEventRecord(e->ev_fork, st);
+        cudaStreamWaitEvent(L.main_stream, e->ev_fork, 0);
+        RT_TRY(forward_lane(e, L, 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12, knn11,
+                            workspace, L.main_stream));
+        cudaEventRecord(L.ev_done, L.main_stream);
+        cudaStreamWaitEvent(st, L.ev_done, 0);
+        return rt_check_launch("backbone_forward");
+    }
     // two lanes: pairs [0, b0) and [b0, b) run concurrently on their own stream sets, forked from / joined to `st`
     const int b0 = (b + 1) / 2;
     Carver c0(nullptr);

@@ -117,14 +117,28 @@ __global__ void __launch_bounds__(256) maxpool_rows_kernel(long long groups, int
 // neighbour) evaluates the 3->8->8 trunk into shared memory; phase 2: one thread per channel.
 constexpr int WS_PTS = 8;
 
+// two fp32 FMAs in one instruction (SASS FFMA2): each half is an ordinary round-to-nearest fmaf
+__device__ __forceinline__ float2 rt_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
 __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
-    extern __shared__ float s_h2[];  // WS_PTS * ns * 8
+    extern __shared__ __align__(16) float s_h2[];  // WS_PTS * ns * 8 trunk outputs, each stored twice (h, h): FFMA2 operands
     __shared__ int s_idx[WS_PTS * 32];
-    const long long cp0 = (long long)blockIdx.x * WS_PTS;
+    const long long cp0 = (long long)blockIdx.x * WS_PTS;   // first SLOT of the CTA; slot -> point through a.perm
     const long long ncp = (long long)a.clouds * a.npts;
     const int pairs = WS_PTS * a.ns;
+    __shared__ long long s_cp[WS_PTS];
+    if (threadIdx.x < WS_PTS) {
+        const long long slot = cp0 + threadIdx.x;
+        s_cp[threadIdx.x] = slot < ncp ? (a.perm ? (long long)__ldg(a.perm + slot) : slot) : ncp;
+    }
+    __syncthreads();
     for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
-        const long long cp = cp0 + t / a.ns;
+        const long long cp = s_cp[t / a.ns];
         float h2[8];
         int j = 0;
         if (cp < ncp) {
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
             for (int o = 0; o < 8; ++o) h2[o] = 0.0f;
         }
 #pragma unroll
-        for (int o = 0; o < 8; ++o) s_h2[t * 8 + o] = h2[o];
+        for (int o = 0; o < 8; ++o) reinterpret_cast<float2 *>(s_h2)[t * 8 + o] = make_float2(h2[o], h2[o]);
         s_idx[t] = j;
     }
     __syncthreads();
@@ -163,18 +177,21 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
         const int pslots = blockDim.x / lanes;      // points processed concurrently
         const int cg = threadIdx.x % lanes, ps = threadIdx.x / lanes;
         if (ps < pslots) {
-            float wc[4][8], bc[4];
+            // channel pairs (4cg, 4cg+1) and (4cg+2, 4cg+3): the 8 -> c layer runs as packed FFMA2, same per-channel
+            // operation order as a scalar fmaf chain (w = bc; w = fma(wc[k], h2[k], w), k ascending)
+            float2 wc[2][8], bc[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) wc[j][k] = __ldg(a.wc + (4 * cg + j) * 8 + k);
-                bc[j] = __ldg(a.bc + 4 * cg + j);
+                for (int k = 0; k < 8; ++k)
+                    wc[j][k] = make_float2(__ldg(a.wc + (4 * cg + 2 * j) * 8 + k), __ldg(a.wc + (4 * cg + 2 * j + 1) * 8 + k));
+                bc[j] = make_float2(__ldg(a.bc + 4 * cg + 2 * j), __ldg(a.bc + 4 * cg + 2 * j + 1));
             }
             for (int p = ps; p < WS_PTS; p += pslots) {
-                const long long cp = cp0 + p;
+                const long long cp = s_cp[p];
                 if (cp >= ncp) break;
                 const int cloud = (int)(cp / a.npts);
-                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float2 acc[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
                 for (int s0 = 0; s0 < a.ns; s0 += 8) {
                     float4 vv[8];
 #pragma unroll
@@ -191,19 +208,22 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
                     for (int u = 0; u < 8; ++u) {
                         const int s = s0 + u;
                         if (s < a.ns) {
-                            const float *h2 = s_h2 + (p * a.ns + s) * 8;
-                            const float vx[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                            const float4 *h2 = reinterpret_cast<const float4 *>(s_h2) + (p * a.ns + s) * 4;   // 8 x (h, h)
+                            float2 w0 = bc[0], w1 = bc[1];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float w = bc[j];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) w = fmaf(wc[j][k], h2[k], w);
-                                acc[j] = fmaf(fmaxf(w, 0.0f), vx[j], acc[j]);
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                const float4 hh = h2[k2];
+                                w0 = rt_ffma2(wc[0][2 * k2], make_float2(hh.x, hh.y), w0);
+                                w1 = rt_ffma2(wc[1][2 * k2], make_float2(hh.x, hh.y), w1);
+                                w0 = rt_ffma2(wc[0][2 * k2 + 1], make_float2(hh.z, hh.w), w0);
+                                w1 = rt_ffma2(wc[1][2 * k2 + 1], make_float2(hh.z, hh.w), w1);
                             }
+                            acc[0] = rt_ffma2(make_float2(fmaxf(w0.x, 0.0f), fmaxf(w0.y, 0.0f)), make_float2(vv[u].x, vv[u].y), acc[0]);
+                            acc[1] = rt_ffma2(make_float2(fmaxf(w1.x, 0.0f), fmaxf(w1.y, 0.0f)), make_float2(vv[u].z, vv[u].w), acc[1]);
                         }
                     }
                 }
-                reinterpret_cast<float4 *>(a.out + cp * a.c)[cg] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<float4 *>(a.out + cp * a.c)[cg] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
             }
         }
         return;
@@ -214,15 +234,15 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
         for (int k = 0; k < 8; ++k) wc[k] = __ldg(a.wc + ch * 8 + k);
         const float bc = __ldg(a.bc + ch);
         for (int p = 0; p < WS_PTS; ++p) {
-            const long long cp = cp0 + p;
+            const long long cp = s_cp[p];
             if (cp >= ncp) break;
             const int cloud = (int)(cp / a.npts);
             float acc = 0.0f;
             for (int s = 0; s < a.ns; ++s) {
-                const float *h2 = s_h2 + (p * a.ns + s) * 8;
+                const float *h2 = s_h2 + (p * a.ns + s) * 16;   // (h, h) pairs
                 float w = bc;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[k], w);
+                for (int k = 0; k < 8; ++k) w = fmaf(wc[k], h2[2 * k], w);
                 const float v = a.gather_v ? __ldg(a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c + ch)
                                            : __ldg(a.v + (cp * a.ns + s) * a.c + ch);
                 acc = fmaf(fmaxf(w, 0.0f), v, acc);
@@ -332,6 +352,9 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
             s_pts[t] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
         }
         __syncthreads();
+        // ---- phase 1, query by query: distances of the tile, pruning threshold, survivors into 4 register slots ----
+        uint32_t sd[KW_QPW][4], si[KW_QPW][4], nd[KW_QPW], ni[KW_QPW];
+        bool slow[KW_QPW];
 #pragma unroll
         for (int u = 0; u < KW_QPW; ++u) {
             uint32_t d[32];   // distance bits (d >= 0, so uint order == float order); +inf marks "absent / taken"
@@ -346,10 +369,11 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                     d[i] = 0x7f800000u;
                 }
             }
-            uint32_t cd = car_d[u], ci = car_i[u], nd = 0x7f800000u, ni = 0xffffffffu;
-            // ---- prune: U = k-th smallest of the 32 lane minima.  The k lanes with the smallest minima each own a
+            nd[u] = 0x7f800000u;
+            ni[u] = 0xffffffffu;
+            // prune: U = k-th smallest of the 32 lane minima.  The k lanes with the smallest minima each own a
             // candidate <= U, so the k nearest are all <= U; typically only ~k..2k candidates survive.
-            uint32_t lmin = cd;
+            uint32_t lmin = car_d[u];
 #pragma unroll
             for (int i = 0; i < 32; ++i) lmin = min(lmin, d[i]);
             uint32_t sv = lmin;   // bitonic sort of the 32 lane minima across the warp (ascending by lane)
@@ -362,22 +386,26 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                     sv = (asc == low) ? min(sv, other) : max(sv, other);
                 }
             const uint32_t U = __shfl_sync(0xffffffffu, sv, k - 1);
-            // survivors of this lane, in index order, into 4 register slots
-            uint32_t sd0 = 0x7f800000u, sd1 = sd0, sd2 = sd0, sd3 = sd0, si0 = 0, si1 = 0, si2 = 0, si3 = 0;
+            // survivors of this lane, in index order
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { sd[u][c] = 0x7f800000u; si[u][c] = 0; }
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 if (d[i] <= U && d[i] != 0x7f800000u) {
                     const uint32_t id = (uint32_t)(base + lane + 32 * i);
-                    if (cnt == 0) { sd0 = d[i]; si0 = id; }
-                    else if (cnt == 1) { sd1 = d[i]; si1 = id; }
-                    else if (cnt == 2) { sd2 = d[i]; si2 = id; }
-                    else if (cnt == 3) { sd3 = d[i]; si3 = id; }
+                    if (cnt == 0) { sd[u][0] = d[i]; si[u][0] = id; }
+                    else if (cnt == 1) { sd[u][1] = d[i]; si[u][1] = id; }
+                    else if (cnt == 2) { sd[u][2] = d[i]; si[u][2] = id; }
+                    else if (cnt == 3) { sd[u][3] = d[i]; si[u][3] = id; }
                     ++cnt;
                 }
             }
-            if (__any_sync(0xffffffffu, cnt > 4)) {
-                // rare (heavy ties / clustered duplicates): extract from the full register tile
+            slow[u] = __any_sync(0xffffffffu, cnt > 4);
+            if (slow[u]) {
+                // rare (heavy ties / clustered duplicates): extract from the full register tile while it is live
+                uint32_t cd = car_d[u];
+                const uint32_t ci = car_i[u];
                 for (int r = 0; r < k; ++r) {
                     uint32_t ld = cd, li = ci;
                     int lslot = -1;
@@ -392,31 +420,38 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                         for (int i = 0; i < 32; ++i)
                             if (i == lslot) d[i] = 0x7f800000u;
                     }
-                    if (lane == r) { nd = md; ni = mi; }
+                    if (lane == r) { nd[u] = md; ni[u] = mi; }
                 }
-            } else {
-                for (int r = 0; r < k; ++r) {
-                    // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
-                    uint32_t ld = cd, li = ci;
-                    int lslot = -1;
-                    if (sd0 < ld) { ld = sd0; li = si0; lslot = 0; }
-                    if (sd1 < ld) { ld = sd1; li = si1; lslot = 1; }
-                    if (sd2 < ld) { ld = sd2; li = si2; lslot = 2; }
-                    if (sd3 < ld) { ld = sd3; li = si3; lslot = 3; }
-                    const uint32_t md = rt_redux_min_u32(ld);
-                    const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
-                    if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
-                        if (lslot < 0) cd = 0x7f800000u;
-                        else if (lslot == 0) sd0 = 0x7f800000u;
-                        else if (lslot == 1) sd1 = 0x7f800000u;
-                        else if (lslot == 2) sd2 = 0x7f800000u;
-                        else sd3 = 0x7f800000u;
-                    }
-                    if (lane == r) { nd = md; ni = mi; }
-                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sd[u][c] = 0x7f800000u;   // phase 2 has nothing left to do for this query
+                car_d[u] = 0x7f800000u;
             }
-            car_d[u] = nd;
-            car_i[u] = ni;
+        }
+        // ---- phase 2: the k extraction rounds of all KW_QPW queries side by side (independent redux chains) ----
+        for (int r = 0; r < k; ++r) {
+#pragma unroll
+            for (int u = 0; u < KW_QPW; ++u) {
+                // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
+                uint32_t ld = car_d[u], li = car_i[u];
+                int lslot = -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (sd[u][c] < ld) { ld = sd[u][c]; li = si[u][c]; lslot = c; }
+                const uint32_t md = rt_redux_min_u32(ld);
+                const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
+                if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
+                    if (lslot < 0) car_d[u] = 0x7f800000u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c == lslot) sd[u][c] = 0x7f800000u;
+                }
+                if (lane == r && !slow[u]) { nd[u] = md; ni[u] = mi; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KW_QPW; ++u) {
+            car_d[u] = nd[u];
+            car_i[u] = ni[u];
         }
     }
 #pragma unroll
@@ -528,39 +563,63 @@ __global__ void __launch_bounds__(256) broadcast_cm_kernel(int c, int n, const f
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row[i] = v;
 }
 
-// One GRU layer, sequence length 1 (torch.nn.GRU equations).  grid (4, B): a CTA owns 32 hidden units of one batch
-// element; 192 threads = 6 dot products (r,z,n rows of W_ih and of W_hh) x 32 units, each 128 long.  Weights arrive
-// TRANSPOSED (128 x 384) so the 32 threads of a warp read 32 consecutive rows of one k: coalesced.
-__global__ void __launch_bounds__(192) gru_layer_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
-                                                        const float *__restrict__ wih_t, const float *__restrict__ whh_t,
-                                                        const float *__restrict__ bih, const float *__restrict__ bhh,
-                                                        float *__restrict__ h_out) {
-    __shared__ float s_x[128], s_h[128], s_g[6][32];
-    const int b = blockIdx.y, j0 = blockIdx.x * 32, t = threadIdx.x;
-    if (t < 128) {
-        s_x[t] = x[(long long)b * 128 + t];
-        s_h[t] = h_in[(long long)b * 128 + t];
-    }
+// Weights of the GRU kernels below arrive TRANSPOSED (128 x 384) so consecutive threads read consecutive rows of one k.
+// hidden half of all five GRU layers: gh[l][b][row] = W_hh[l][row,:] . h_in[l][b] + b_hh[l][row].  grid (3, B, 5) x 128.
+__global__ void __launch_bounds__(128) gru_hh_kernel(int bsz, const float *__restrict__ h_in, const float *__restrict__ whh_t,
+                                                     const float *__restrict__ bhh, size_t h_stride, float *__restrict__ gh) {
+    __shared__ float s_h[128];
+    const int l = blockIdx.z, b = blockIdx.y, row = blockIdx.x * 128 + threadIdx.x;
+    s_h[threadIdx.x] = h_in[(size_t)l * h_stride + (size_t)b * 128 + threadIdx.x];
     __syncthreads();
-    const int part = t >> 5, jj = t & 31;          // part 0..2: W_ih gates r,z,n; 3..5: W_hh gates r,z,n
-    const int row = (part % 3) * 128 + j0 + jj;
-    const float *w = (part < 3 ? wih_t : whh_t) + row;
-    const float *v = part < 3 ? s_x : s_h;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;   // four partial sums: shorter dependent chains
+    const float *w = whh_t + (size_t)l * 128 * 384 + row;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll 8
     for (int k = 0; k < 128; k += 4) {
-        a0 = fmaf(__ldg(w + (k + 0) * 384), v[k + 0], a0);
-        a1 = fmaf(__ldg(w + (k + 1) * 384), v[k + 1], a1);
-        a2 = fmaf(__ldg(w + (k + 2) * 384), v[k + 2], a2);
-        a3 = fmaf(__ldg(w + (k + 3) * 384), v[k + 3], a3);
+        a0 = fmaf(__ldg(w + (k + 0) * 384), s_h[k + 0], a0);
+        a1 = fmaf(__ldg(w + (k + 1) * 384), s_h[k + 1], a1);
+        a2 = fmaf(__ldg(w + (k + 2) * 384), s_h[k + 2], a2);
+        a3 = fmaf(__ldg(w + (k + 3) * 384), s_h[k + 3], a3);
     }
-    s_g[part][jj] = (a0 + a1) + (a2 + a3) + __ldg((part < 3 ? bih : bhh) + row);
+    gh[((size_t)l * bsz + b) * 384 + row] = (a0 + a1) + (a2 + a3) + __ldg(bhh + l * 384 + row);
+}
+
+// input half + gates of all five layers of one batch element: 384 threads = the r, z, n rows of W_ih.
+__global__ void __launch_bounds__(384) gru_chain_kernel(int bsz, const float *__restrict__ x, const float *__restrict__ h_in,
+                                                        const float *__restrict__ wih_t, const float *__restrict__ bih,
+                                                        const float *__restrict__ gh, float *__restrict__ h_out, size_t h_stride) {
+    __shared__ float s_x[128], s_gi[384];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 128) s_x[t] = x[(size_t)b * 128 + t];
     __syncthreads();
-    if (t < 32) {
-        const float r = 1.0f / (1.0f + expf(-(s_g[0][t] + s_g[3][t])));
-        const float z = 1.0f / (1.0f + expf(-(s_g[1][t] + s_g[4][t])));
-        const float nn = tanhf(s_g[2][t] + r * s_g[5][t]);
-        h_out[(long long)b * 128 + j0 + t] = (1.0f - z) * nn + z * s_h[j0 + t];
+    for (int l = 0; l < 5; ++l) {
+        const float *w = wih_t + (size_t)l * 128 * 384 + t;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        // the chain is bound by the latency of streaming 196 KB of weights per layer from L2: keep 32 loads in flight
+#pragma unroll 1
+        for (int k0 = 0; k0 < 128; k0 += 32) {
+            float wv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) wv[i] = __ldg(w + (k0 + i) * 384);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                a0 = fmaf(wv[i + 0], s_x[k0 + i + 0], a0);
+                a1 = fmaf(wv[i + 1], s_x[k0 + i + 1], a1);
+                a2 = fmaf(wv[i + 2], s_x[k0 + i + 2], a2);
+                a3 = fmaf(wv[i + 3], s_x[k0 + i + 3], a3);
+            }
+        }
+        s_gi[t] = (a0 + a1) + (a2 + a3) + __ldg(bih + l * 384 + t);
+        __syncthreads();
+        if (t < 128) {
+            const float *g = gh + ((size_t)l * bsz + b) * 384;
+            const float r = 1.0f / (1.0f + expf(-(s_gi[t] + g[t])));
+            const float z = 1.0f / (1.0f + expf(-(s_gi[128 + t] + g[128 + t])));
+            const float nn = tanhf(s_gi[256 + t] + r * g[256 + t]);
+            const float h = (1.0f - z) * nn + z * h_in[(size_t)l * h_stride + (size_t)b * 128 + t];
+            h_out[(size_t)l * h_stride + (size_t)b * 128 + t] = h;
+            s_x[t] = h;
+        }
+        __syncthreads();
     }
 }
 
@@ -580,6 +639,82 @@ __global__ void __launch_bounds__(256) cls_tail_kernel(long long rows, const flo
     }
     const float y = fmaf(__ldg(lin_w + 2), o[2], fmaf(__ldg(lin_w + 1), o[1], __ldg(lin_w + 0) * o[0])) + __ldg(lin_b);
     cls[r] = 1.0f / (1.0f + expf(-y));
+}
+
+// Morton-order permutation of one cloud per CTA: bounding box -> 10 bits per axis -> interleave -> bitonic sort of
+// (code << 32 | index) in shared memory.  Any xyz (NaN included) still yields a permutation: the index rides in the key.
+constexpr int MP_MAX = 4096;
+__device__ __forceinline__ uint32_t mp_spread3(uint32_t v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) morton_perm_kernel(int n, int npad, const float *__restrict__ xyz_all, int *__restrict__ perm) {
+    extern __shared__ unsigned long long s_key[];   // npad
+    __shared__ float s_lo[3][8], s_hi[3][8];
+    const int cloud = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = t; i < n; i += 256)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(xyz + i * 3 + a);
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { s_lo[a][warp] = lo[a]; s_hi[a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = s_lo[a][0], h = s_hi[a][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { l = fminf(l, s_lo[a][w]); h = fmaxf(h, s_hi[a][w]); }
+        lo[a] = l;
+        scale[a] = (h > l) ? 1023.0f / (h - l) : 0.0f;
+    }
+    for (int i = t; i < npad; i += 256) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            uint32_t q[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float f = (__ldg(xyz + i * 3 + a) - lo[a]) * scale[a];
+                q[a] = (uint32_t)fminf(fmaxf(f, 0.0f), 1023.0f);   // NaN -> 0 (fmaxf drops it)
+            }
+            const uint32_t code = mp_spread3(q[0]) | (mp_spread3(q[1]) << 1) | (mp_spread3(q[2]) << 2);
+            key = ((unsigned long long)code << 32) | (uint32_t)i;
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < npad; i += 256) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = s_key[i], y = s_key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_key[i] = y; s_key[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = t; i < n; i += 256) perm[(size_t)cloud * n + i] = cloud * n + (int)(uint32_t)(s_key[i] & 0xffffffffull);
+}
+__global__ void __launch_bounds__(256) iota_kernel(long long n, int *__restrict__ p) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = (int)i;
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float *p, long long n, float v) {
@@ -614,7 +749,7 @@ int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st) {
     const long long ncp = (long long)a.clouds * a.npts;
     if (ncp <= 0) return RT_OK;
     RT_REQUIRE(a.ns <= 32, "weighted_sum: nsample > 32");
-    weighted_sum_kernel<<<rt_divup(ncp, WS_PTS), 256, WS_PTS * a.ns * 8 * sizeof(float), st>>>(a);
+    weighted_sum_kernel<<<rt_divup(ncp, WS_PTS), 256, WS_PTS * a.ns * 16 * sizeof(float), st>>>(a);
     return rt_check_launch("weighted_sum_kernel");
 }
 int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st) {
@@ -674,23 +809,40 @@ int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int 
     broadcast_cm_kernel<<<grid, 256, 0, st>>>(c, n, g, dst, dst_c, dst_coff);
     return rt_check_launch("broadcast_cm_kernel");
 }
-int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
-                  const float *bhh, float *h_out, size_t h_stride, cudaStream_t st) {
+// 5-layer GRU, sequence length 1 (torch.nn.GRU equations; reference: FlowDecoder.torchGRU, model_utils.py:279,294-297).
+// Only the input half of every layer (W_ih . x_l, x_l = h_out[l-1]) is a dependent chain; the hidden half
+// (W_hh . h_in[l] + b_hh) depends on the call's inputs alone, so rt_launch_gru_hh evaluates it for all five layers at
+// the start of the step on a side stream, and the chain kernel (one CTA per batch element, all five layers, one
+// launch instead of five) only adds the input half.  Summation order of every dot product = gru_layer_kernel's.
+int rt_launch_gru_hh(int b, const float *h_in, const float *whh, const float *bhh, size_t h_stride, float *gh, cudaStream_t st) {
     if (b <= 0) return RT_OK;
-    // five dependent layer launches; layer l reads h_in[l] and the previous layer's output
-    for (int l = 0; l < 5; ++l) {
-        const float *xin = l == 0 ? x : h_out + (size_t)(l - 1) * h_stride;
-        gru_layer_kernel<<<dim3(4, b), 192, 0, st>>>(b, xin, h_in + (size_t)l * h_stride, wih + (size_t)l * 128 * 384,
-                                                    whh + (size_t)l * 128 * 384, bih + l * 384, bhh + l * 384,
-                                                    h_out + (size_t)l * h_stride);
-    }
-    return rt_check_launch("gru_layer_kernel");
+    gru_hh_kernel<<<dim3(3, b, 5), 128, 0, st>>>(b, h_in, whh, bhh, h_stride, gh);
+    return rt_check_launch("gru_hh_kernel");
+}
+int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *bih, const float *gh, float *h_out,
+                  size_t h_stride, cudaStream_t st) {
+    if (b <= 0) return RT_OK;
+    gru_chain_kernel<<<b, 384, 0, st>>>(b, x, h_in, wih, bih, gh, h_out, h_stride);
+    return rt_check_launch("gru_chain_kernel");
 }
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b, float *cls,
                        cudaStream_t st) {
     if (rows <= 0) return RT_OK;
     cls_tail_kernel<<<rt_divup(rows, 256), 256, 0, st>>>(rows, h3, w4, lin_w, lin_b, cls);
     return rt_check_launch("cls_tail_kernel");
+}
+int rt_launch_morton_perm(int clouds, int n, const float *xyz, int *perm, cudaStream_t st) {
+    if (clouds <= 0 || n <= 0) return RT_OK;
+    RT_REQUIRE((long long)clouds * n < (1ll << 31), "morton_perm: too many points");
+    if (n > MP_MAX) {   // larger clouds keep the input order (still correct, just no locality gain)
+        const long long total = (long long)clouds * n;
+        iota_kernel<<<grid_for(total, 256), 256, 0, st>>>(total, perm);
+        return rt_check_launch("iota_kernel");
+    }
+    int npad = 32;
+    while (npad < n) npad *= 2;
+    morton_perm_kernel<<<clouds, 256, npad * sizeof(unsigned long long), st>>>(n, npad, xyz, perm);
+    return rt_check_launch("morton_perm_kernel");
 }
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return RT_OK;

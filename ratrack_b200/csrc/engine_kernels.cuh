@@ -59,6 +59,7 @@ struct RtWeightedSum {
     const float *wa, *ba, *wb, *bb, *wc, *bc;  // (8x3),(8),(8x8),(8),(c x 8),(c)
     const float *v;
     float *out;
+    const int *perm;   // optional processing order: slot s of the grid handles point perm[s] (global row index); null = identity
 };
 int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st);
 
@@ -86,12 +87,18 @@ int rt_launch_rows_to_cm(int b, int c, int n, const float *src, int lds, int sof
 // dst[(b, c, n)] = g[b, c] for all n (broadcast rows of the global feature into a channel-major output)
 int rt_launch_broadcast_cm(int b, int c, int n, const float *g, float *dst, int dst_c, int dst_coff, cudaStream_t st);
 // 5-layer GRU, one step: x (b,128), h_in / h_out (5, *, 128) with layer stride h_stride floats; y = h_out[4]
-int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *whh, const float *bih,
-                  const float *bhh, float *h_out, size_t h_stride, cudaStream_t st);
+int rt_launch_gru_hh(int b, const float *h_in, const float *whh, const float *bhh, size_t h_stride, float *gh, cudaStream_t st);
+int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *bih, const float *gh, float *h_out,
+                  size_t h_stride, cudaStream_t st);
 // cls[(b,n)] = sigmoid(lin_w . (W4 . h3[(b,n), :32]) + lin_b);  flow written by rowgemm + rows_to_cm
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b,
                        float *cls, cudaStream_t st);
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st);
+// Spatial processing order: perm[cloud*n + j] = cloud*n + (index of the j-th point of the cloud along a 30-bit Morton curve).
+// Kernels that gather neighbour rows walk their points in this order so that the points of a tile share neighbours (L1 / L2
+// hits instead of repeated 1 KB row fetches); every point is still computed independently and written to its own row, so the
+// results are bit-identical to the identity order.
+int rt_launch_morton_perm(int clouds, int n, const float *xyz, int *perm, cudaStream_t st);
 // neighbors.cu: ball query of two radii over the same centres in one launch
 int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
                           int *idx_b, const float *new_xyz, const float *xyz, cudaStream_t st);

@@ -24,6 +24,9 @@
 
 namespace {
 
+int g_fps_exclusive = 0;
+constexpr size_t kFpsHogBytes = 226 * 1024;   // + static + the 1 KB per-CTA reserve = the SM's 228 KB: no other CTA fits beside it
+
 __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
     unsigned r = 0;
     for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
@@ -186,17 +189,24 @@ __global__ void __launch_bounds__(256) fps_generic_kernel(int n, int m, int bs, 
 
 template <int T, int Q, int PH>
 int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t st) {
-    const size_t smem = (size_t)n * 3 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set && smem > 40 * 1024) {
-        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_set = true;
+    size_t smem = (size_t)n * 3 * sizeof(float);
+    // SM-exclusive mode (rt_fps_set_exclusive): every round of this kernel is a dependent latency chain, and any CTA
+    // sharing the SM stretches each round 2-3x (measured on B200).  Asking for (nearly) the whole shared memory of the
+    // SM keeps every other CTA off it, so the chain runs at its stand-alone speed whatever else is in flight.
+    if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
+    static size_t attr_bytes = 0;
+    if (smem > 40 * 1024 && smem > attr_bytes) {
+        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        attr_bytes = kFpsHogBytes;
     }
     fps_reg_kernel<T, Q, PH><<<b, T, smem, st>>>(n, m, xyz, temp, idx);
     return rt_check_launch("fps_reg_kernel");
 }
 
 }  // namespace
+
+// engine-internal: 1 = FPS CTAs claim a whole SM each (see launch_reg)
+void rt_fps_set_exclusive(int on) { g_fps_exclusive = on; }
 
 // C-ABI.  replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47)
 RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream) {

@@ -69,21 +69,21 @@ __device__ __forceinline__ uint64_t mt_desc(uint32_t saddr, uint32_t lbo, uint32
 __device__ __forceinline__ uint32_t mt_idesc(int n) {  // F16 x F16 -> F32, K-major, M = 128
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ float mt_act(float v, int act) {
-    if (act == RT_ACT_RELU) return fmaxf(v, 0.0f);
-    if (act == RT_ACT_LEAKY01) return v > 0.0f ? v : 0.1f * v;
-    return v;
-}
-__device__ __forceinline__ void mt_split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
-    amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+// branch-free activation: max(v, slope * v) with slope 0 (ReLU), 0.1 (LeakyReLU) or 1 (none)
+__device__ __forceinline__ float mt_slope(int act) { return act == RT_ACT_RELU ? 0.0f : (act == RT_ACT_LEAKY01 ? 0.1f : 1.0f); }
+__device__ __forceinline__ float mt_act(float v, float slope) { return fmaxf(v, v * slope); }
+// range guard: the running max of |hi| is kept as a half2 (one HMNMX2 per pair); an fp32 input beyond the fp16 range
+// rounds to inf and trips it
+__device__ __forceinline__ void mt_split2(float x0, float x1, uint32_t &hi, uint32_t &lo, __half2 &amax) {
     const __half2 h = __floats2half2_rn(x0, x1);
+    amax = __hmax2(amax, __habs2(h));
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 // 16 fp32 values -> hi/lo fp16 planes, 8 TMEM columns each
-__device__ __forceinline__ void mt_store16(const float *v, uint32_t t_hi, uint32_t t_lo, float &amax) {
+__device__ __forceinline__ void mt_store16(const float *v, uint32_t t_hi, uint32_t t_lo, __half2 &amax) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) mt_split2(v[2 * i], v[2 * i + 1], hi[i], lo[i], amax);
@@ -128,15 +128,16 @@ struct MtGatherRow {
     float dx, dy, dz;
 };
 __device__ __forceinline__ void mt_gather_issue(const RtMlpTc &a, long long tile, int row_in_tile, MtGatherRow &r) {
-    long long row = tile * 128 + row_in_tile;
-    if (row >= a.rows) row = a.rows - 1;
-    const long long cp = row / a.ns;                 // (cloud, centre)
-    const int cloud = (int)(cp / a.npts);
+    uint32_t row = (uint32_t)tile * 128u + (uint32_t)row_in_tile;
+    if (row >= (uint32_t)a.rows) row = (uint32_t)a.rows - 1u;
+    const uint32_t cp = row >> a.ns_shift;            // (cloud, centre)
+    const uint32_t cloud = cp / (uint32_t)a.npts;
     const int j = __ldg(a.idx + row);
     const long long g = (long long)cloud * a.n_in + j;
-    r.dx = __ldg(a.xyz_in + g * 3 + 0) - __ldg(a.xyz_c + cp * 3 + 0);
-    r.dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(a.xyz_c + cp * 3 + 1);
-    r.dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(a.xyz_c + cp * 3 + 2);
+    const float *pc = a.xyz_c + (size_t)cp * 3;
+    r.dx = __ldg(a.xyz_in + g * 3 + 0) - __ldg(pc + 0);
+    r.dy = __ldg(a.xyz_in + g * 3 + 1) - __ldg(pc + 1);
+    r.dz = __ldg(a.xyz_in + g * 3 + 2) - __ldg(pc + 2);
     r.yrow = a.y + g * a.ldy + a.yoff;
 }
 
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         const int row_in_tile = 32 * q + lane;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         uint32_t d_phase = 0;
-        float amax = 0.0f;
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         MtGatherRow pre;
         if (LOAD_MODE == RT_MLP_LOAD_GATHER && (long long)blockIdx.x < ntiles) mt_gather_issue(a, blockIdx.x, row_in_tile, pre);
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -288,8 +289,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float4 w = s_gc[c0 + i];
-                        const float t = v[i] + fmaf(w.z, pre.dz, fmaf(w.y, pre.dy, w.x * pre.dx)) + w.w;
-                        v[i] = fmaxf(t, 0.0f);
+                        v[i] = fmaxf(fmaf(w.z, pre.dz, fmaf(w.y, pre.dy, fmaf(w.x, pre.dx, v[i] + w.w))), 0.0f);
                     }
                     mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
                 }
@@ -305,20 +305,33 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                 mt_mbar_wait(&bar_d, d_phase);
                 d_phase ^= 1;
                 mt_fence_after();
-                const int n = a.layer[l].n, act = a.layer[l].act;
+                const int n = a.layer[l].n;
+                const float slope = mt_slope(a.layer[l].act);
                 const float *bias = s_bias + l * 256;
-                const float *cb = (l == 0 && a.cloud_bias) ? a.cloud_bias + (rc / a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
+                const float *cb = (l == 0 && a.cloud_bias)
+                                      ? a.cloud_bias + (size_t)((uint32_t)rc / (uint32_t)a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
                 const bool last = l == a.nlayers - 1;
                 for (int c0 = 16 * hlf; c0 < n; c0 += 32) {
                     uint32_t r[16];
                     mt_ld16(tD + lane_base + c0, r);
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float t = fmaf(__uint_as_float(r[i]), MT_WINV, bias[c0 + i]);
-                        if (cb) t += __ldg(cb + c0 + i);
-                        v[i] = mt_act(t, act);
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 bq = *reinterpret_cast<const float4 *>(bias + c0 + 4 * g);
+                        v[4 * g + 0] = fmaf(__uint_as_float(r[4 * g + 0]), MT_WINV, bq.x);
+                        v[4 * g + 1] = fmaf(__uint_as_float(r[4 * g + 1]), MT_WINV, bq.y);
+                        v[4 * g + 2] = fmaf(__uint_as_float(r[4 * g + 2]), MT_WINV, bq.z);
+                        v[4 * g + 3] = fmaf(__uint_as_float(r[4 * g + 3]), MT_WINV, bq.w);
                     }
+                    if (cb) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 cq = __ldg(reinterpret_cast<const float4 *>(cb + c0) + g);
+                            v[4 * g + 0] += cq.x; v[4 * g + 1] += cq.y; v[4 * g + 2] += cq.z; v[4 * g + 3] += cq.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = mt_act(v[i], slope);
                     if (!last) {
                         mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
                     } else if (a.out_mode == RT_MLP_OUT_ROWS) {
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                             default: break;
                         }
                         if (valid && writer) {
-                            float *o = a.out + (row / a.ns) * a.ldo + a.ooff + c0 + col0;
+                            float *o = a.out + (size_t)((uint32_t)row >> a.ns_shift) * a.ldo + a.ooff + c0 + col0;
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
                                 if (i < cnt && c0 + col0 + i < a.n_out) o[i] = v[i];
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
             }
             mt_fence_before();
         }
-        if (!(amax < 65000.0f) && a.status) atomicOr(a.status, 2);
+        if (!(fmaxf(__low2float(amax), __high2float(amax)) < 65000.0f) && a.status) atomicOr(a.status, 2);
     }
     mt_fence_before();
     __syncthreads();
@@ -394,8 +407,14 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     } else {
         RT_REQUIRE(a.c1 == a.layer[0].k && a.c1 <= 64 && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
     }
-    if (a.out_mode == RT_MLP_OUT_MAXPOOL || a.load_mode == RT_MLP_LOAD_GATHER)
+    RT_REQUIRE(a.rows < (1ll << 31) - 256, "mlp_tc: %lld rows (32-bit row arithmetic)", a.rows);
+    RT_REQUIRE(!a.cloud_bias || ((a.cloud_bias_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.cloud_bias) & 15) == 0),
+               "mlp_tc: cloud_bias must be 16-byte aligned with a leading dimension that is a multiple of 4");
+    a.ns_shift = 0;
+    if (a.out_mode == RT_MLP_OUT_MAXPOOL || a.load_mode == RT_MLP_LOAD_GATHER) {
         RT_REQUIRE(a.ns >= 1 && a.ns <= 32 && (a.ns & (a.ns - 1)) == 0, "mlp_tc: ns=%d must be a power of two <= 32", a.ns);
+        while ((1 << a.ns_shift) < a.ns) ++a.ns_shift;
+    }
     const int need = dmax + kmax;  // accumulator columns + two A planes of kmax/2 columns
     RT_REQUIRE(need <= 512, "mlp_tc: %d TMEM columns needed", need);
     int cols = 32;

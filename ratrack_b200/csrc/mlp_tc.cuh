@@ -42,7 +42,7 @@ struct RtMlpTc {
     float *out;                // rows: out[row * ldo + ooff + c]; maxpool: out[(row / ns) * ldo + ooff + c], c < n_out
     int ldo, ooff, n_out;
     int *status;               // optional device status word (bit 1: fp16 range exceeded)
-    int tmem_cols, d_cols, a_cols;  // filled by the launcher
+    int tmem_cols, d_cols, a_cols, ns_shift;  // filled by the launcher
 };
 int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st);
 

@@ -24,17 +24,47 @@ constexpr int BQ_QPB = 64;
 
 // Two radii in one pass (the MSG set-abstraction layers always query the same centres with two radii): the distance
 // of a candidate is evaluated once and feeds two independent ordered compactions.  nsample_b == 0 disables the second.
+// A warp walks its queries two at a time over the same 32 candidates (one set of shared-memory loads, two independent
+// dependency chains); the common step -- no candidate of the 32 inside the larger radius of either query -- costs one
+// ballot per query and no branch into the compaction code.  The tile is padded to a multiple of 32 with +inf points
+// (never inside any radius), so the scan has no tail test.
+struct BqState { int ca, cb, fa, fb; };
+
+__device__ __forceinline__ void bq_compact(bool hit_a, bool hit_b, int cand, int lane, int nsample_a, int nsample_b, int *oa,
+                                           int *ob, BqState &st) {
+    if (st.ca < nsample_a) {
+        const uint32_t vote = __ballot_sync(0xffffffffu, hit_a);
+        if (vote) {
+            if (st.fa < 0) st.fa = cand - lane + __ffs(vote) - 1;
+            const int slot = st.ca + __popc(vote & ((1u << lane) - 1u));
+            if (hit_a && slot < nsample_a) oa[slot] = cand;
+            st.ca += __popc(vote);
+        }
+    }
+    if (st.cb < nsample_b) {
+        const uint32_t vote = __ballot_sync(0xffffffffu, hit_b);
+        if (vote) {
+            if (st.fb < 0) st.fb = cand - lane + __ffs(vote) - 1;
+            const int slot = st.cb + __popc(vote & ((1u << lane) - 1u));
+            if (hit_b && slot < nsample_b) ob[slot] = cand;
+            st.cb += __popc(vote);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, float radius_a, int nsample_a, int *__restrict__ idx_a,
                                                                 float radius_b, int nsample_b, int *__restrict__ idx_b,
                                                                 const float *__restrict__ new_xyz,
                                                                 const float *__restrict__ xyz) {
-    extern __shared__ __align__(16) float s_pts[];  // min(n, TILE_PTS)*3
+    extern __shared__ __align__(16) float s_pts[];  // roundup32(min(n, TILE_PTS))*3
     __shared__ __align__(8) uint64_t s_bar;
     const int cloud = blockIdx.y;
     const float *pts = xyz + (size_t)cloud * n * 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float r2a = __fmul_rn(radius_a, radius_a), r2b = __fmul_rn(radius_b, radius_b);
+    const float r2max = nsample_b > 0 ? fmaxf(r2a, r2b) : r2a;
     constexpr int QPW = BQ_QPB / (BQ_THREADS / 32);
+    static_assert(QPW % 2 == 0, "queries are walked in pairs");
 
     if (threadIdx.x == 0) {
         rt_mbar_init(&s_bar, 1);
@@ -44,7 +74,7 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
 
     const int q0 = blockIdx.x * BQ_QPB + warp * QPW;
     float qx[QPW], qy[QPW], qz[QPW];
-    int cnt_a[QPW], first_a[QPW], cnt_b[QPW], first_b[QPW];
+    BqState st[QPW];
 #pragma unroll
     for (int i = 0; i < QPW; ++i) {
         const int q = q0 + i;
@@ -53,121 +83,154 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
         qx[i] = __ldg(c + 0);
         qy[i] = __ldg(c + 1);
         qz[i] = __ldg(c + 2);
-        cnt_a[i] = ok ? 0 : nsample_a;  // out-of-range queries are "done"
-        cnt_b[i] = ok ? 0 : nsample_b;
-        first_a[i] = first_b[i] = -1;
+        st[i].ca = ok ? 0 : nsample_a;  // out-of-range queries are "done"
+        st[i].cb = ok ? 0 : nsample_b;
+        st[i].fa = st[i].fb = -1;
     }
 
     uint32_t parity = 0;
     for (int base = 0; base < n; base += TILE_PTS) {
         const int tn = min(TILE_PTS, n - base);
+        const int tpad = (tn + 31) & ~31;
         if (base > 0) __syncthreads();  // everyone finished reading the previous tile
+        for (int t = tn * 3 + threadIdx.x; t < tpad * 3; t += BQ_THREADS) s_pts[t] = __int_as_float(0x7f800000);
         rt_stage_floats(s_pts, pts + (size_t)base * 3, tn * 3, &s_bar, parity);
         parity ^= 1;
 #pragma unroll
-        for (int i = 0; i < QPW; ++i) {
-            int ca = cnt_a[i], cb = cnt_b[i], fa = first_a[i], fb = first_b[i];
-            if (ca >= nsample_a && cb >= nsample_b) continue;  // warp-uniform
-            int *oa = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a;
-            int *ob = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b;
-            for (int k0 = 0; k0 < tn && (ca < nsample_a || cb < nsample_b); k0 += 32) {
+        for (int i = 0; i < QPW; i += 2) {
+            BqState s0 = st[i], s1 = st[i + 1];
+            bool live0 = s0.ca < nsample_a || s0.cb < nsample_b, live1 = s1.ca < nsample_a || s1.cb < nsample_b;  // warp-uniform
+            if (!live0 && !live1) continue;
+            int *oa0 = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a, *oa1 = oa0 + nsample_a;
+            int *ob0 = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b, *ob1 = ob0 + nsample_b;
+            for (int k0 = 0; k0 < tpad && (live0 || live1); k0 += 32) {
                 const int k = k0 + lane;
-                bool hit_a = false, hit_b = false;
-                if (k < tn) {
-                    const float d2 = rt_sqdist(qx[i], qy[i], qz[i], s_pts[k * 3 + 0], s_pts[k * 3 + 1], s_pts[k * 3 + 2]);
-                    hit_a = d2 < r2a;
-                    hit_b = d2 < r2b;
+                const float px = s_pts[k * 3 + 0], py = s_pts[k * 3 + 1], pz = s_pts[k * 3 + 2];
+                const float d0 = rt_sqdist(qx[i], qy[i], qz[i], px, py, pz);
+                const float d1 = rt_sqdist(qx[i + 1], qy[i + 1], qz[i + 1], px, py, pz);
+                const bool any0 = __any_sync(0xffffffffu, d0 < r2max), any1 = __any_sync(0xffffffffu, d1 < r2max);
+                if (any0 && live0) {
+                    bq_compact(d0 < r2a, d0 < r2b, base + k, lane, nsample_a, nsample_b, oa0, ob0, s0);
+                    live0 = s0.ca < nsample_a || s0.cb < nsample_b;
                 }
-                if (ca < nsample_a) {
-                    const uint32_t vote = __ballot_sync(0xffffffffu, hit_a);
-                    if (vote) {
-                        if (fa < 0) fa = base + k0 + __ffs(vote) - 1;
-                        const int slot = ca + __popc(vote & ((1u << lane) - 1u));
-                        if (hit_a && slot < nsample_a) oa[slot] = base + k;
-                        ca += __popc(vote);
-                    }
-                }
-                if (cb < nsample_b) {
-                    const uint32_t vote = __ballot_sync(0xffffffffu, hit_b);
-                    if (vote) {
-                        if (fb < 0) fb = base + k0 + __ffs(vote) - 1;
-                        const int slot = cb + __popc(vote & ((1u << lane) - 1u));
-                        if (hit_b && slot < nsample_b) ob[slot] = base + k;
-                        cb += __popc(vote);
-                    }
+                if (any1 && live1) {
+                    bq_compact(d1 < r2a, d1 < r2b, base + k, lane, nsample_a, nsample_b, oa1, ob1, s1);
+                    live1 = s1.ca < nsample_a || s1.cb < nsample_b;
                 }
             }
-            cnt_a[i] = ca; cnt_b[i] = cb;
-            first_a[i] = fa; first_b[i] = fb;
+            st[i] = s0;
+            st[i + 1] = s1;
         }
     }
     // pad unused slots with the first hit; queries with no hit leave the caller's buffer untouched
 #pragma unroll
     for (int i = 0; i < QPW; ++i) {
         if (q0 + i >= m) continue;
-        if (first_a[i] >= 0) {
+        if (st[i].fa >= 0) {
             int *out = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a;
-            for (int s = cnt_a[i] + lane; s < nsample_a; s += 32) out[s] = first_a[i];
+            for (int s = st[i].ca + lane; s < nsample_a; s += 32) out[s] = st[i].fa;
         }
-        if (first_b[i] >= 0) {
+        if (st[i].fb >= 0) {
             int *out = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b;
-            for (int s = cnt_b[i] + lane; s < nsample_b; s += 32) out[s] = first_b[i];
+            for (int s = st[i].cb + lane; s < nsample_b; s += 32) out[s] = st[i].fb;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// three_nn: one thread per unknown point; known cloud in shared-memory tiles.
-constexpr int NN_THREADS = 128;
+// three_nn: NN_G = 8 lanes per unknown point, NN_QPG = 2 points per lane group, known cloud in shared-memory tiles.
+// Lane g of a group scans candidates g, g+8, ... (ascending, so its private best-3 list obeys the reference's strict-'<'
+// cascade: among equal distances the lower index sits in the better slot); the eight lists are then merged by three
+// rounds of "group minimum of (distance bits, index)", which is the same lexicographic order the reference's serial
+// scan produces.  8x the warps of a thread-per-point scan: the per-candidate dependent chain is hidden by occupancy.
+constexpr int NN_THREADS = 128;   // knn_kernel below: one thread per query
+constexpr int NN3_THREADS = 256, NN_G = 8, NN_QPG = 2;
+constexpr int NN3_QPB = NN3_THREADS / NN_G * NN_QPG;   // 64 unknown points per CTA
 
-__global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(int n, int m, const float *__restrict__ unknown,
-                                                              const float *__restrict__ known,
-                                                              float *__restrict__ dist2, int *__restrict__ idx) {
+__global__ void __launch_bounds__(NN3_THREADS) three_nn_kernel(int n, int m, const float *__restrict__ unknown,
+                                                               const float *__restrict__ known,
+                                                               float *__restrict__ dist2, int *__restrict__ idx) {
     extern __shared__ __align__(16) float s_pts[];
     __shared__ __align__(8) uint64_t s_bar;
     const int cloud = blockIdx.y;
-    const int j = blockIdx.x * NN_THREADS + threadIdx.x;
-    const bool ok = j < n;
-    const float *u = unknown + ((size_t)cloud * n + (ok ? j : 0)) * 3;
-    const float ux = __ldg(u + 0), uy = __ldg(u + 1), uz = __ldg(u + 2);
+    const int g = threadIdx.x & (NN_G - 1);
+    const int q0 = blockIdx.x * NN3_QPB + (threadIdx.x / NN_G) * NN_QPG;
+    float ux[NN_QPG], uy[NN_QPG], uz[NN_QPG];
+    const float inf = __int_as_float(0x7f800000);
+    // the reference keeps double-typed bests initialised to 1e40: every finite fp32 distance is smaller, +inf/NaN never
+    // are -- identical to fp32 bests initialised to +inf.
+    float b1[NN_QPG], b2[NN_QPG], b3[NN_QPG];
+    int i1[NN_QPG], i2[NN_QPG], i3[NN_QPG];
+#pragma unroll
+    for (int u = 0; u < NN_QPG; ++u) {
+        const int j = min(q0 + u, n - 1);
+        const float *p = unknown + ((size_t)cloud * n + j) * 3;
+        ux[u] = __ldg(p + 0); uy[u] = __ldg(p + 1); uz[u] = __ldg(p + 2);
+        b1[u] = b2[u] = b3[u] = inf;
+        i1[u] = i2[u] = i3[u] = 0;
+    }
     if (threadIdx.x == 0) {
         rt_mbar_init(&s_bar, 1);
         rt_fence_mbar_init();
     }
     __syncthreads();
-    // the reference keeps double-typed bests initialised to 1e40: every finite fp32 distance is
-    // smaller, +inf/NaN never are -- identical to fp32 bests initialised to +inf.
-    float b1 = __int_as_float(0x7f800000), b2 = b1, b3 = b1;
-    int i1 = 0, i2 = 0, i3 = 0;
     uint32_t parity = 0;
     for (int base = 0; base < m; base += TILE_PTS) {
         const int tn = min(TILE_PTS, m - base);
         if (base > 0) __syncthreads();
         rt_stage_floats(s_pts, known + ((size_t)cloud * m + base) * 3, tn * 3, &s_bar, parity);
         parity ^= 1;
-#pragma unroll 4
-        for (int k = 0; k < tn; ++k) {
-            const float d = rt_sqdist(ux, uy, uz, s_pts[k * 3 + 0], s_pts[k * 3 + 1], s_pts[k * 3 + 2]);
-            if (d < b3) {
-                const int kk = base + k;
-                if (d < b1) {
-                    b3 = b2; i3 = i2;
-                    b2 = b1; i2 = i1;
-                    b1 = d; i1 = kk;
-                } else if (d < b2) {
-                    b3 = b2; i3 = i2;
-                    b2 = d; i2 = kk;
-                } else {
-                    b3 = d; i3 = kk;
+#pragma unroll 2
+        for (int k = g; k < tn; k += NN_G) {
+            const float px = s_pts[k * 3 + 0], py = s_pts[k * 3 + 1], pz = s_pts[k * 3 + 2];
+            const int kk = base + k;
+#pragma unroll
+            for (int u = 0; u < NN_QPG; ++u) {
+                const float d = rt_sqdist(ux[u], uy[u], uz[u], px, py, pz);
+                if (d < b3[u]) {
+                    if (d < b1[u]) {
+                        b3[u] = b2[u]; i3[u] = i2[u];
+                        b2[u] = b1[u]; i2[u] = i1[u];
+                        b1[u] = d; i1[u] = kk;
+                    } else if (d < b2[u]) {
+                        b3[u] = b2[u]; i3[u] = i2[u];
+                        b2[u] = d; i2[u] = kk;
+                    } else {
+                        b3[u] = d; i3[u] = kk;
+                    }
                 }
             }
         }
     }
-    if (ok) {
-        float *od = dist2 + ((size_t)cloud * n + j) * 3;
-        int *oi = idx + ((size_t)cloud * n + j) * 3;
-        od[0] = b1; od[1] = b2; od[2] = b3;
-        oi[0] = i1; oi[1] = i2; oi[2] = i3;
+    // merge the eight private lists: d >= 0 and never NaN here, so the float bits order like the values
+#pragma unroll
+    for (int u = 0; u < NN_QPG; ++u) {
+        float od[3];
+        int oi[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const unsigned long long mine = ((unsigned long long)__float_as_uint(b1[u]) << 32) | (unsigned)i1[u];
+            unsigned long long best = mine;
+#pragma unroll
+            for (int o = NN_G / 2; o >= 1; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other < best ? other : best;
+            }
+            od[r] = __uint_as_float((unsigned)(best >> 32));
+            oi[r] = (int)(unsigned)(best & 0xffffffffull);
+            // exactly one lane owns a finite winner (indices are unique); sentinels (+inf, 0) tie harmlessly
+            if (mine == best && b1[u] < inf) {
+                b1[u] = b2[u]; i1[u] = i2[u];
+                b2[u] = b3[u]; i2[u] = i3[u];
+                b3[u] = inf; i3[u] = 0;
+            }
+        }
+        if (g == 0 && q0 + u < n) {
+            float *pd = dist2 + ((size_t)cloud * n + q0 + u) * 3;
+            int *pi = idx + ((size_t)cloud * n + q0 + u) * 3;
+            pd[0] = od[0]; pd[1] = od[1]; pd[2] = od[2];
+            pi[0] = oi[0]; pi[1] = oi[1]; pi[2] = oi[2];
+        }
     }
 }
 
@@ -259,6 +322,7 @@ __global__ void __launch_bounds__(NN_THREADS) knn_kernel(int n, int m, int k, co
 }
 
 inline size_t tile_bytes(int n) { return (size_t)min(n, TILE_PTS) * 3 * sizeof(float); }
+inline size_t tile_bytes_pad32(int n) { return (size_t)((min(n, TILE_PTS) + 31) & ~31) * 3 * sizeof(float); }
 
 }  // namespace
 
@@ -269,7 +333,7 @@ RT_API int rt_ball_query(int b, int n, int m, float radius, int nsample, const f
     if (b == 0 || m == 0 || nsample == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     dim3 grid(rt_divup(m, BQ_QPB), b);
-    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
+    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
                                                                                  new_xyz, xyz);
     return rt_check_launch("ball_query_kernel");
 }
@@ -280,7 +344,7 @@ int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, in
     if (b == 0 || m == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535 && nsample_a > 0 && nsample_b > 0, "ball_query2: bad arguments");
     dim3 grid(rt_divup(m, BQ_QPB), b);
-    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
+    ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
                                                               new_xyz, xyz);
     return rt_check_launch("ball_query_kernel(2 radii)");
 }
@@ -291,8 +355,8 @@ RT_API int rt_three_nn(int b, int n, int m, const float *unknown, const float *k
     RT_REQUIRE(b >= 0 && n >= 0 && m >= 0 && unknown && known && dist2 && idx, "three_nn: bad arguments");
     if (b == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "three_nn: batch > 65535");
-    dim3 grid(rt_divup(n, NN_THREADS), b);
-    three_nn_kernel<<<grid, NN_THREADS, tile_bytes(m), (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    dim3 grid(rt_divup(n, NN3_QPB), b);
+    three_nn_kernel<<<grid, NN3_THREADS, tile_bytes(m), (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
     return rt_check_launch("three_nn_kernel");
 }
 

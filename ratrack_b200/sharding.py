@@ -36,3 +36,31 @@ def gather_flow(flow_local: torch.Tensor, counts):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return [o[:c] for o, c in zip(out, counts)]
+
+
+def allreduce_gradients(params, average: bool = True, group=None):
+    """Data-parallel gradient reduction of the training step: ONE all_reduce over a flat fp32 bucket of every
+    parameter gradient (1.8 M floats = 7.3 MB for the whole model: latency-bound on NVLink, so a single bucket),
+    then scatter back.  Replaces the reference's single-process nn.DataParallel gradient gather
+    (reference: src/models/model.py:38-40).  Parameters without a gradient contribute zeros so that every rank
+    reduces the same layout.  Returns the number of elements reduced."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return sum(p.numel() for p in params)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off: off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return off

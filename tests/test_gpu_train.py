@@ -1,0 +1,106 @@
+"""GPU parity of one TRAINING step of the hot path (train-mode BatchNorm forward, reference losses, backward through
+the CUDA grad kernels) against golden values produced by the unmodified reference Python + its own loss module
+(tests/golden/train_step_*.npz, generator oracle/gen_golden_train.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from ratrack_b200 import losses, synthetic
+from ratrack_b200.model_utils import Track4DBackbone
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+# fp32 on a different device with different summation orders (cuBLAS/cuDNN vs MKL, atomicAdd scatter order):
+# loss terms to 2e-5 relative, gradient norms to 2e-3 relative, individual gradients to 2e-3 of the tensor's max
+# (train-mode BatchNorm divides by batch standard deviations, which amplifies 1e-6-level differences).
+TOL_LOSS, TOL_NORM, TOL_GRAD = 2e-5, 2e-3, 2e-3
+
+
+class Args:
+    npoints = 512
+
+
+def _step(net, d, g, batch):
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128, device="cuda"))
+    flow, cls, prop = out[0], out[2], out[6]
+    pc1_wrap = t["pc1"] + flow                                                      # models/track4d.py:52
+    sf = losses.flow_loss(pc1_wrap, torch.from_numpy(g["gt_flow"]).cuda(), reduction="first")
+    gt_cls = torch.from_numpy(g["gt_cls"]).cuda()
+    seg = sum(losses.motion_seg_loss(cls[b:b + 1], gt_cls[b]) for b in range(batch)) / batch
+    aff = torch.sigmoid(prop[0, :12].mean(dim=1))                                   # stand-in entries, as in the generator
+    trk = losses.affinity_loss(aff, torch.from_numpy(g["aff_gt"]).cuda())
+    total = 0.5 * sf + 0.5 * trk + 1.0 * seg
+    return out, sf, seg, trk, total
+
+
+@pytest.mark.parametrize("name,batch,n", [("train_step_n256_b1.npz", 1, 256), ("train_step_n512_b2.npz", 2, 512)])
+def test_train_step_vs_reference_golden(name, batch, n, monkeypatch):
+    g = np.load(os.path.join(GOLDEN, name))
+    net = Track4DBackbone(Args())
+    net.load_state_dict(synthetic.make_state_dict(net, seed=1234), strict=False)
+    net = net.cuda().train()
+    d = synthetic.make_batch(batch, n, seed=1234)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    # torch.topk leaves ties undefined (exact duplicate points straddling the 16th place): our neighbour sets must be
+    # tie-equivalent to the reference's, and the step itself replays the reference's choice so that every later
+    # tensor and gradient is comparable one to one
+    from test_gpu_backbone import knn_sets_equivalent
+    import ratrack_b200.model_utils as mu
+
+    knn = net.cost_volume_neighbours(t["pc1"], t["pc2"])
+    d12, bad12 = knn_sets_equivalent(d["pc1"], d["pc2"], knn[0].cpu().numpy(), g["knn12"])
+    d11, bad11 = knn_sets_equivalent(d["pc1"], d["pc1"], knn[1].cpu().numpy(), g["knn11"])
+    assert bad12 == 0 and bad11 == 0, (d12, bad12, d11, bad11)
+    replay = [torch.from_numpy(g["knn12"]).long().cuda(), torch.from_numpy(g["knn11"]).long().cuda()]
+    monkeypatch.setattr(mu, "knn_point", lambda nsample, xyz, new_xyz: replay.pop(0))
+    out, sf, seg, trk, total = _step(net, d, g, batch)
+    total.backward()
+    torch.cuda.synchronize()
+    for nm, ours, ref in (("sf", sf, g["sf"]), ("seg", seg, g["seg"]), ("trk", trk, g["trk"]), ("total", total, g["total"])):
+        assert abs(float(ours) - float(ref)) <= TOL_LOSS * max(1.0, abs(float(ref))), (nm, float(ours), float(ref))
+    assert np.abs(out[0].detach().cpu().numpy() - g["flow"]).max() <= 1e-4 * max(1.0, np.abs(g["flow"]).max())
+    assert np.abs(out[2].detach().cpu().numpy() - g["cls"]).max() <= 1e-4
+    params = dict(net.named_parameters())
+    worst = 0.0
+    for k, ref_norm in zip(g["grad_names"], g["grad_norms"]):
+        k = str(k)
+        if k not in params:        # affinity / bin_score / dead modules are not part of this path
+            continue
+        gr = params[k].grad
+        assert gr is not None, k
+        rel = abs(float(gr.double().norm()) - ref_norm) / max(ref_norm, 1e-6 * float(g["grad_norms"].max()))
+        worst = max(worst, rel)
+        assert rel <= TOL_NORM, (k, float(gr.norm()), ref_norm)
+    for key in g.files:
+        if key.startswith("grad:"):
+            k = key[5:]
+            ref = g[key]
+            err = np.abs(params[k].grad.cpu().numpy() - ref).max()
+            assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-6), (k, err, np.abs(ref).max())
+        if key.startswith("bn:"):
+            ref = g[key]
+            got = net.state_dict()[key[3:]].cpu().numpy()
+            assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), key
+    print(f"{name}: neighbour rows at ties {d12}+{d11}; worst relative gradient-norm error {worst:.2e}")
+
+
+def test_train_step_is_deterministic_given_same_inputs():
+    """Two identical steps give the same loss and (up to atomicAdd ordering in the scatter kernels) the same gradients."""
+    g = np.load(os.path.join(GOLDEN, "train_step_n256_b1.npz"))
+    d = synthetic.make_batch(1, 256, seed=1234)
+    res = []
+    for _ in range(2):
+        net = Track4DBackbone(Args())
+        net.load_state_dict(synthetic.make_state_dict(net, seed=1234), strict=False)
+        net = net.cuda().train()
+        _, sf, seg, trk, total = _step(net, d, g, 1)
+        total.backward()
+        res.append((float(total), net.pn_head.sa1.mlps[0][0].conv.weight.grad.clone()))
+    assert res[0][0] == res[1][0]
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())

@@ -1,9 +1,12 @@
 #!/bin/bash
-# A/B of engine flags on the same box: 7 = all on, 3 = single lane
+# A/B of engine scheduling flags (RT_ENGINE_FLAGS bits: 1 costvol_tc, 2 mlp_tc, 4 two lanes, 8 FPS SM-exclusive,
+# 16 early kNN, 32 own prioritised main stream) + parity of the backbone tests under the default flags
 mkdir -p gpurun_out
-for rep in 1 2; do
-for f in 7 3; do
-RT_ENGINE_FLAGS=$f timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('flags $f rep $rep', round(d['value']), 'frames/s', round(d['ms_per_step'],3), 'ms  e2e', round(d['e2e']['value']), ' costvol ms', round(d['roofline']['avg_launch_ms'],3))"
-done; done
-RT_ENGINE_FLAGS=7 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu --batch 128 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('B128 flags 7', round(d['value']), 'frames/s', round(d['ms_per_step'],3))"
-RT_ENGINE_FLAGS=3 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu --batch 128 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('B128 flags 3', round(d['value']), 'frames/s', round(d['ms_per_step'],3))"
+timeout 900 python -m pytest tests/test_gpu_backbone.py -m gpu -q --tb=short 2>&1 | tail -n 6 > gpurun_out/pytest_backbone.log
+tail -n 3 gpurun_out/pytest_backbone.log
+line() { python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), 'frames/s', round(d['ms_per_step'],3), 'ms  e2e', round(d['e2e']['value']), ' costvol ms', round(d['roofline']['avg_launch_ms'],3))"; }
+for f in ${AB_FLAGS:-3 35 11 43 27 59}; do
+  for rep in 1 2; do
+    RT_ENGINE_FLAGS=$f timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu 2>/dev/null | line "flags=$f rep$rep"
+  done
+done | tee gpurun_out/ab.log
