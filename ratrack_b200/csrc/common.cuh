@@ -110,6 +110,15 @@ __device__ __forceinline__ void rt_stage_floats(float *s_dst, const float *g_src
     __syncthreads();
 }
 
+// 256-bit read-only global load (SASS LDG.E.ENL2.256): one instruction per 32-byte sector.  For thread-per-row access
+// patterns (every lane in a different row) the L1 data pipe spends a wavefront per lane per instruction whatever its
+// width, so twice the bytes per instruction halve the wavefronts.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void rt_ldg256(const float *p, float4 &lo, float4 &hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t rt_redux_max_u32(uint32_t v) {
     uint32_t r;
     asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));

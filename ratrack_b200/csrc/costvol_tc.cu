@@ -147,11 +147,11 @@ struct CtRow {
 __device__ __forceinline__ void ct_issue_chunk(const CostVolTcArgs &a, const CtRow &r, int c0, float4 *u, float4 *v) {
     const float4 *p1r = reinterpret_cast<const float4 *>(a.p1 + (size_t)r.pc * CT_C + c0);
     const float4 *p2r = reinterpret_cast<const float4 *>(a.p2 + r.g2 * CT_C + c0);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        u[g] = __ldg(p2r + g);
-        v[g] = __ldg(p1r + g);
-    }
+    // 256-bit loads: every lane reads a different neighbour row, so the L1 data pipe pays per instruction, not per byte
+    rt_ldg256(reinterpret_cast<const float *>(p2r), u[0], u[1]);
+    rt_ldg256(reinterpret_cast<const float *>(p2r + 2), u[2], u[3]);
+    rt_ldg256(reinterpret_cast<const float *>(p1r), v[0], v[1]);
+    rt_ldg256(reinterpret_cast<const float *>(p1r + 2), v[2], v[3]);
 }
 __device__ __forceinline__ void ct_issue_row(const CostVolTcArgs &a, int tile, int row, int cbeg, CtRow &r) {
     const int slot = tile * CT_PTS + (row >> 4);

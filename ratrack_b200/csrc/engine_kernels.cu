@@ -125,7 +125,7 @@ __device__ __forceinline__ float2 rt_ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
-__global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
+__global__ void __launch_bounds__(256) weighted_sum_generic_kernel(RtWeightedSum a) {
     extern __shared__ __align__(16) float s_h2[];  // WS_PTS * ns * 8 trunk outputs, each stored twice (h, h): FFMA2 operands
     __shared__ int s_idx[WS_PTS * 32];
     const long long cp0 = (long long)blockIdx.x * WS_PTS;   // first SLOT of the CTA; slot -> point through a.perm
@@ -252,6 +252,122 @@ __global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
     }
 }
 
+// Persistent variant for c % 4 == 0, c <= 256 (the cost volume: c = 256).  A CTA loops over groups of WS_PTS points; the
+// 8 -> c weights of its channel pairs stay in REGISTERS for the whole kernel and the trunk weights in shared memory,
+// loaded once per CTA -- in the one-group-per-CTA kernel above the per-CTA reload of wc (a 128-byte-strided, fully
+// uncoalesced read: 32 L1 wavefronts per load) made up 85 % of the L1 data-pipe traffic that bounds this operation.
+__global__ void __launch_bounds__(256) weighted_sum_kernel(RtWeightedSum a) {
+    extern __shared__ __align__(16) float s_h2[];  // WS_PTS * ns * 8 trunk outputs, each stored twice (h, h): FFMA2 operands
+    __shared__ int s_idx[WS_PTS * 32];
+    __shared__ long long s_cp[WS_PTS];
+    __shared__ float s_w[104];                     // wa (24) ba (8) wb (64) bb (8)
+    const long long ncp = (long long)a.clouds * a.npts;
+    const long long ngroups = (ncp + WS_PTS - 1) / WS_PTS;
+    const int pairs = WS_PTS * a.ns;
+    const int lanes = a.c >> 2;                 // threads per point: 4 channels each
+    const int pslots = blockDim.x / lanes;      // points processed side by side
+    const int cg = threadIdx.x % lanes, ps = threadIdx.x / lanes;
+    if (threadIdx.x < 24) s_w[threadIdx.x] = __ldg(a.wa + threadIdx.x);
+    if (threadIdx.x < 8) s_w[24 + threadIdx.x] = __ldg(a.ba + threadIdx.x);
+    if (threadIdx.x < 64) s_w[32 + threadIdx.x] = __ldg(a.wb + threadIdx.x);
+    if (threadIdx.x < 8) s_w[96 + threadIdx.x] = __ldg(a.bb + threadIdx.x);
+    // channel pairs (4cg, 4cg+1) and (4cg+2, 4cg+3): the 8 -> c layer runs as packed FFMA2, same per-channel
+    // operation order as a scalar fmaf chain (w = bc; w = fma(wc[k], h2[k], w), k ascending)
+    float2 wc[2][8], bc[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            wc[j][k] = make_float2(__ldg(a.wc + (4 * cg + 2 * j) * 8 + k), __ldg(a.wc + (4 * cg + 2 * j + 1) * 8 + k));
+        bc[j] = make_float2(__ldg(a.bc + 4 * cg + 2 * j), __ldg(a.bc + 4 * cg + 2 * j + 1));
+    }
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long cp0 = grp * WS_PTS;   // first SLOT of the group; slot -> point through a.perm
+        __syncthreads();                      // previous group's phase 2 is done with s_h2 / s_idx / s_cp (and s_w is written)
+        if (threadIdx.x < WS_PTS) {
+            const long long slot = cp0 + threadIdx.x;
+            s_cp[threadIdx.x] = slot < ncp ? (a.perm ? (long long)__ldg(a.perm + slot) : slot) : ncp;
+        }
+        __syncthreads();
+        // phase 1: one thread per (point, neighbour) evaluates the 3 -> 8 -> 8 trunk
+        for (int t = threadIdx.x; t < pairs; t += blockDim.x) {
+            const long long cp = s_cp[t / a.ns];
+            float h2[8];
+            int j = 0;
+            if (cp < ncp) {
+                const int cloud = (int)(cp / a.npts);
+                j = __ldg(a.idx + cp * a.ns + (t % a.ns));
+                const float *pi = a.xyz_in + ((long long)cloud * a.n_in + j) * 3;
+                const float *pc = a.xyz_c + cp * 3;
+                const float d[3] = {__ldg(pi + 0) - __ldg(pc + 0), __ldg(pi + 1) - __ldg(pc + 1), __ldg(pi + 2) - __ldg(pc + 2)};
+                float h1[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    float v = s_w[24 + o];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v = fmaf(s_w[o * 3 + k], d[k], v);
+                    h1[o] = fmaxf(v, 0.0f);
+                }
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    float v = s_w[96 + o];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v = fmaf(s_w[32 + o * 8 + k], h1[k], v);
+                    h2[o] = fmaxf(v, 0.0f);
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) h2[o] = 0.0f;
+            }
+#pragma unroll
+            for (int o = 0; o < 8; ++o) reinterpret_cast<float2 *>(s_h2)[t * 8 + o] = make_float2(h2[o], h2[o]);
+            s_idx[t] = j;
+        }
+        __syncthreads();
+        // phase 2: 128-bit gathers of the value rows, weights from the trunk outputs, sum over the neighbours
+        if (ps < pslots) {
+            for (int p = ps; p < WS_PTS; p += pslots) {
+                const long long cp = s_cp[p];
+                if (cp >= ncp) break;
+                const int cloud = (int)(cp / a.npts);
+                float2 acc[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                for (int s0 = 0; s0 < a.ns; s0 += 8) {
+                    float4 vv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        vv[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (s < a.ns) {
+                            const float *row = a.gather_v ? a.v + ((long long)cloud * a.n_in + s_idx[p * a.ns + s]) * a.c
+                                                          : a.v + (cp * a.ns + s) * a.c;
+                            vv[u] = __ldg(reinterpret_cast<const float4 *>(row) + cg);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s = s0 + u;
+                        if (s < a.ns) {
+                            const float4 *h2 = reinterpret_cast<const float4 *>(s_h2) + (p * a.ns + s) * 4;   // 8 x (h, h)
+                            float2 w0 = bc[0], w1 = bc[1];
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                const float4 hh = h2[k2];
+                                w0 = rt_ffma2(wc[0][2 * k2], make_float2(hh.x, hh.y), w0);
+                                w1 = rt_ffma2(wc[1][2 * k2], make_float2(hh.x, hh.y), w1);
+                                w0 = rt_ffma2(wc[0][2 * k2 + 1], make_float2(hh.z, hh.w), w0);
+                                w1 = rt_ffma2(wc[1][2 * k2 + 1], make_float2(hh.z, hh.w), w1);
+                            }
+                            acc[0] = rt_ffma2(make_float2(fmaxf(w0.x, 0.0f), fmaxf(w0.y, 0.0f)), make_float2(vv[u].x, vv[u].y), acc[0]);
+                            acc[1] = rt_ffma2(make_float2(fmaxf(w1.x, 0.0f), fmaxf(w1.y, 0.0f)), make_float2(vv[u].z, vv[u].w), acc[1]);
+                        }
+                    }
+                }
+                reinterpret_cast<float4 *>(a.out + cp * a.c)[cg] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // expanded-form kNN: one thread per query, search cloud staged as (x, y, z, |p|^2) in shared memory.
 constexpr int KX_THREADS = 128, KX_TILE = 1024;
@@ -352,9 +468,6 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
             s_pts[t] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
         }
         __syncthreads();
-        // ---- phase 1, query by query: distances of the tile, pruning threshold, survivors into 4 register slots ----
-        uint32_t sd[KW_QPW][4], si[KW_QPW][4], nd[KW_QPW], ni[KW_QPW];
-        bool slow[KW_QPW];
 #pragma unroll
         for (int u = 0; u < KW_QPW; ++u) {
             uint32_t d[32];   // distance bits (d >= 0, so uint order == float order); +inf marks "absent / taken"
@@ -369,11 +482,10 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                     d[i] = 0x7f800000u;
                 }
             }
-            nd[u] = 0x7f800000u;
-            ni[u] = 0xffffffffu;
-            // prune: U = k-th smallest of the 32 lane minima.  The k lanes with the smallest minima each own a
+            uint32_t cd = car_d[u], ci = car_i[u], nd = 0x7f800000u, ni = 0xffffffffu;
+            // ---- prune: U = k-th smallest of the 32 lane minima.  The k lanes with the smallest minima each own a
             // candidate <= U, so the k nearest are all <= U; typically only ~k..2k candidates survive.
-            uint32_t lmin = car_d[u];
+            uint32_t lmin = cd;
 #pragma unroll
             for (int i = 0; i < 32; ++i) lmin = min(lmin, d[i]);
             uint32_t sv = lmin;   // bitonic sort of the 32 lane minima across the warp (ascending by lane)
@@ -386,26 +498,22 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                     sv = (asc == low) ? min(sv, other) : max(sv, other);
                 }
             const uint32_t U = __shfl_sync(0xffffffffu, sv, k - 1);
-            // survivors of this lane, in index order
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { sd[u][c] = 0x7f800000u; si[u][c] = 0; }
+            // survivors of this lane, in index order, into 4 register slots
+            uint32_t sd0 = 0x7f800000u, sd1 = sd0, sd2 = sd0, sd3 = sd0, si0 = 0, si1 = 0, si2 = 0, si3 = 0;
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 if (d[i] <= U && d[i] != 0x7f800000u) {
                     const uint32_t id = (uint32_t)(base + lane + 32 * i);
-                    if (cnt == 0) { sd[u][0] = d[i]; si[u][0] = id; }
-                    else if (cnt == 1) { sd[u][1] = d[i]; si[u][1] = id; }
-                    else if (cnt == 2) { sd[u][2] = d[i]; si[u][2] = id; }
-                    else if (cnt == 3) { sd[u][3] = d[i]; si[u][3] = id; }
+                    if (cnt == 0) { sd0 = d[i]; si0 = id; }
+                    else if (cnt == 1) { sd1 = d[i]; si1 = id; }
+                    else if (cnt == 2) { sd2 = d[i]; si2 = id; }
+                    else if (cnt == 3) { sd3 = d[i]; si3 = id; }
                     ++cnt;
                 }
             }
-            slow[u] = __any_sync(0xffffffffu, cnt > 4);
-            if (slow[u]) {
-                // rare (heavy ties / clustered duplicates): extract from the full register tile while it is live
-                uint32_t cd = car_d[u];
-                const uint32_t ci = car_i[u];
+            if (__any_sync(0xffffffffu, cnt > 4)) {
+                // rare (heavy ties / clustered duplicates): extract from the full register tile
                 for (int r = 0; r < k; ++r) {
                     uint32_t ld = cd, li = ci;
                     int lslot = -1;
@@ -420,38 +528,31 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
                         for (int i = 0; i < 32; ++i)
                             if (i == lslot) d[i] = 0x7f800000u;
                     }
-                    if (lane == r) { nd[u] = md; ni[u] = mi; }
+                    if (lane == r) { nd = md; ni = mi; }
                 }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sd[u][c] = 0x7f800000u;   // phase 2 has nothing left to do for this query
-                car_d[u] = 0x7f800000u;
-            }
-        }
-        // ---- phase 2: the k extraction rounds of all KW_QPW queries side by side (independent redux chains) ----
-        for (int r = 0; r < k; ++r) {
-#pragma unroll
-            for (int u = 0; u < KW_QPW; ++u) {
-                // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
-                uint32_t ld = car_d[u], li = car_i[u];
-                int lslot = -1;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (sd[u][c] < ld) { ld = sd[u][c]; li = si[u][c]; lslot = c; }
-                const uint32_t md = rt_redux_min_u32(ld);
-                const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
-                if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
-                    if (lslot < 0) car_d[u] = 0x7f800000u;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c == lslot) sd[u][c] = 0x7f800000u;
+            } else {
+                for (int r = 0; r < k; ++r) {
+                    // lane-local minimum: carried entry first (older => lower index wins ties), then slots in index order
+                    uint32_t ld = cd, li = ci;
+                    int lslot = -1;
+                    if (sd0 < ld) { ld = sd0; li = si0; lslot = 0; }
+                    if (sd1 < ld) { ld = sd1; li = si1; lslot = 1; }
+                    if (sd2 < ld) { ld = sd2; li = si2; lslot = 2; }
+                    if (sd3 < ld) { ld = sd3; li = si3; lslot = 3; }
+                    const uint32_t md = rt_redux_min_u32(ld);
+                    const uint32_t mi = rt_redux_min_u32(ld == md ? li : 0xffffffffu);
+                    if (ld == md && li == mi) {           // exactly one lane owns the winner: retire it
+                        if (lslot < 0) cd = 0x7f800000u;
+                        else if (lslot == 0) sd0 = 0x7f800000u;
+                        else if (lslot == 1) sd1 = 0x7f800000u;
+                        else if (lslot == 2) sd2 = 0x7f800000u;
+                        else sd3 = 0x7f800000u;
+                    }
+                    if (lane == r) { nd = md; ni = mi; }
                 }
-                if (lane == r && !slow[u]) { nd[u] = md; ni[u] = mi; }
             }
-        }
-#pragma unroll
-        for (int u = 0; u < KW_QPW; ++u) {
-            car_d[u] = nd[u];
-            car_i[u] = ni[u];
+            car_d[u] = nd;
+            car_i[u] = ni;
         }
     }
 #pragma unroll
@@ -749,8 +850,18 @@ int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st) {
     const long long ncp = (long long)a.clouds * a.npts;
     if (ncp <= 0) return RT_OK;
     RT_REQUIRE(a.ns <= 32, "weighted_sum: nsample > 32");
-    weighted_sum_kernel<<<rt_divup(ncp, WS_PTS), 256, WS_PTS * a.ns * 16 * sizeof(float), st>>>(a);
-    return rt_check_launch("weighted_sum_kernel");
+    const size_t smem = WS_PTS * a.ns * 16 * sizeof(float);
+    if ((a.c & 3) == 0 && a.c >= 4 && a.c <= 256) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long ngroups = (ncp + WS_PTS - 1) / WS_PTS;
+        const long long grid = ngroups < 2ll * sms ? ngroups : 2ll * sms;   // 2 resident CTAs per SM (126 registers x 256 threads)
+        weighted_sum_kernel<<<(int)grid, 256, smem, st>>>(a);
+        return rt_check_launch("weighted_sum_kernel");
+    }
+    weighted_sum_generic_kernel<<<rt_divup(ncp, WS_PTS), 256, smem, st>>>(a);
+    return rt_check_launch("weighted_sum_generic_kernel");
 }
 int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st) {
     if (clouds <= 0 || n <= 0) return RT_OK;

@@ -245,11 +245,25 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                         for (int o = 0; o < ks; o += 16, c0 += 16) {
                             if (((c0 >> 4) & 1) != hlf) continue;
                             float v[16];
+                            float4 q0[4], q1[4], q2[4];
+                            if ((a.seg[s].ldx & 7) == 0) {   // rows are 32-byte aligned: 256-bit loads
+#pragma unroll
+                                for (int g = 0; g < 4; g += 2) {
+                                    rt_ldg256(r0 + o + 4 * g, q0[g], q0[g + 1]);
+                                    rt_ldg256(r1 + o + 4 * g, q1[g], q1[g + 1]);
+                                    rt_ldg256(r2 + o + 4 * g, q2[g], q2[g + 1]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    q0[g] = __ldg(reinterpret_cast<const float4 *>(r0 + o) + g);
+                                    q1[g] = __ldg(reinterpret_cast<const float4 *>(r1 + o) + g);
+                                    q2[g] = __ldg(reinterpret_cast<const float4 *>(r2 + o) + g);
+                                }
+                            }
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const float4 p0 = __ldg(reinterpret_cast<const float4 *>(r0 + o) + g);
-                                const float4 p1 = __ldg(reinterpret_cast<const float4 *>(r1 + o) + g);
-                                const float4 p2 = __ldg(reinterpret_cast<const float4 *>(r2 + o) + g);
+                                const float4 p0 = q0[g], p1 = q1[g], p2 = q2[g];
                                 v[4 * g + 0] = __fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x)));
                                 v[4 * g + 1] = __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y)));
                                 v[4 * g + 2] = __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z)));
@@ -265,10 +279,17 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                         if (((c0 >> 4) & 1) != hlf) continue;
                         float v[16];
                         if (vec && o + 16 <= ks) {
+                            float4 t[4];
+                            if ((a.seg[s].ldx & 7) == 0) {
+                                rt_ldg256(x + o, t[0], t[1]);
+                                rt_ldg256(x + o + 8, t[2], t[3]);
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) t[g] = __ldg(reinterpret_cast<const float4 *>(x + o) + g);
+                            }
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const float4 t = __ldg(reinterpret_cast<const float4 *>(x + o) + g);
-                                v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+                                v[4 * g] = t[g].x; v[4 * g + 1] = t[g].y; v[4 * g + 2] = t[g].z; v[4 * g + 3] = t[g].w;
                             }
                         } else {
 #pragma unroll
@@ -281,10 +302,17 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                 // index, xyz difference and row pointer were fetched during the previous tile; the row itself now
                 for (int c0 = 16 * hlf; c0 < a.c1; c0 += 32) {
                     float v[16];
+                    float4 t[4];
+                    if ((a.ldy & 7) == 0 && (a.yoff & 7) == 0) {
+                        rt_ldg256(pre.yrow + c0, t[0], t[1]);
+                        rt_ldg256(pre.yrow + c0 + 8, t[2], t[3]);
+                    } else {
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) t[gq] = __ldg(reinterpret_cast<const float4 *>(pre.yrow + c0) + gq);
+                    }
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(pre.yrow + c0) + gq);
-                        v[4 * gq] = t.x; v[4 * gq + 1] = t.y; v[4 * gq + 2] = t.z; v[4 * gq + 3] = t.w;
+                        v[4 * gq] = t[gq].x; v[4 * gq + 1] = t[gq].y; v[4 * gq + 2] = t[gq].z; v[4 * gq + 3] = t[gq].w;
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -408,6 +436,13 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
         RT_REQUIRE(a.c1 == a.layer[0].k && a.c1 <= 64 && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
     }
     RT_REQUIRE(a.rows < (1ll << 31) - 256, "mlp_tc: %lld rows (32-bit row arithmetic)", a.rows);
+    if (a.load_mode == RT_MLP_LOAD_ROWS) {
+        for (int s = 0; s < a.nseg; ++s)
+            RT_REQUIRE((a.seg[s].ldx & 3) != 0 || (reinterpret_cast<uintptr_t>(a.seg[s].x) & 31) == 0,
+                       "mlp_tc: segment %d must be 32-byte aligned", s);
+    } else {
+        RT_REQUIRE((reinterpret_cast<uintptr_t>(a.y) & 31) == 0, "mlp_tc: y must be 32-byte aligned");
+    }
     RT_REQUIRE(!a.cloud_bias || ((a.cloud_bias_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.cloud_bias) & 15) == 0),
                "mlp_tc: cloud_bias must be 16-byte aligned with a leading dimension that is a multiple of 4");
     a.ns_shift = 0;
