@@ -119,6 +119,25 @@ __device__ __forceinline__ void rt_ldg256(const float *p, float4 &lo, float4 &hi
                  : "l"(p));
 }
 
+// packed fp32 pairs (SASS FFMA2 / FMUL2 / FADD2): every half is an ordinary round-to-nearest IEEE operation, so results are
+// bit-identical to the scalar forms; one issue slot instead of two
+__device__ __forceinline__ float2 rt_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 rt_fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 rt_fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
 __device__ __forceinline__ uint32_t rt_redux_max_u32(uint32_t v) {
     uint32_t r;
     asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));

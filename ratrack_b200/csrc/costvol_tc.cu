@@ -123,7 +123,11 @@ __device__ __forceinline__ int ct_group_at(int i) { return (i >> 1) + 4 * (i & 1
 // F16 x F16 -> F32, A and B K-major, M = 128, N = 256
 constexpr uint32_t CT_IDESC = (1u << 4) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_ROWS >> 4) << 24);
 
-__device__ __forceinline__ float leaky01(float v) { return v > 0.0f ? v : 0.1f * v; }
+__device__ __forceinline__ float leaky01(float v) { return fmaxf(v, 0.1f * v); }   // LeakyReLU(0.1): two instructions, no select
+__device__ __forceinline__ float2 leaky01x2(float2 v) {
+    const float2 m = rt_fmul2(v, make_float2(0.1f, 0.1f));
+    return make_float2(fmaxf(v.x, m.x), fmaxf(v.y, m.y));
+}
 
 // x = hi + lo with two fp16 (x0 in the low half: K even)
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             const int p = cur.p;
             const bool valid = cur.valid;
             const float dx = cur.dx, dy = cur.dy, dz = cur.dz;
+            const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
             if (hlf == 0) {
                 // WeightNet trunk 3 -> 8 -> 8 (ReLU), result = A operand (K = 8, padded to 16) of the last-layer MMA
                 float h1[8], h2[8];
@@ -334,12 +339,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                     const float4 wx = *reinterpret_cast<const float4 *>(s_wx + c);
                     const float4 wy = *reinterpret_cast<const float4 *>(s_wx + CT_C + c);
                     const float4 wz = *reinterpret_cast<const float4 *>(s_wx + 2 * CT_C + c);
-                    const float x0 = leaky01(u.x + fmaf(wz.x, dz, fmaf(wy.x, dy, wx.x * dx)) + v1.x);
-                    const float x1 = leaky01(u.y + fmaf(wz.y, dz, fmaf(wy.y, dy, wx.y * dx)) + v1.y);
-                    const float x2 = leaky01(u.z + fmaf(wz.z, dz, fmaf(wy.z, dy, wx.z * dx)) + v1.z);
-                    const float x3 = leaky01(u.w + fmaf(wz.w, dz, fmaf(wy.w, dy, wx.w * dx)) + v1.w);
-                    split2(x0, x1, hi[2 * g], lo[2 * g], amax);
-                    split2(x2, x3, hi[2 * g + 1], lo[2 * g + 1], amax);
+                    // packed pairs, same per-channel operation order as the scalar form
+                    // leaky(u + fma(wz, dz, fma(wy, dy, wx * dx)) + v1)
+                    float2 ta = rt_fmul2(make_float2(wx.x, wx.y), dx2), tb = rt_fmul2(make_float2(wx.z, wx.w), dx2);
+                    ta = rt_ffma2(make_float2(wy.x, wy.y), dy2, ta);
+                    tb = rt_ffma2(make_float2(wy.z, wy.w), dy2, tb);
+                    ta = rt_ffma2(make_float2(wz.x, wz.y), dz2, ta);
+                    tb = rt_ffma2(make_float2(wz.z, wz.w), dz2, tb);
+                    ta = rt_fadd2(rt_fadd2(make_float2(u.x, u.y), ta), make_float2(v1.x, v1.y));
+                    tb = rt_fadd2(rt_fadd2(make_float2(u.z, u.w), tb), make_float2(v1.z, v1.w));
+                    ta = leaky01x2(ta);
+                    tb = leaky01x2(tb);
+                    split2(ta.x, ta.y, hi[2 * g], lo[2 * g], amax);
+                    split2(tb.x, tb.y, hi[2 * g + 1], lo[2 * g + 1], amax);
                 }
                 ct_st8(tAhi + lane_base + c0 / 2, hi);
                 ct_st8(tAlo + lane_base + c0 / 2, lo);
@@ -370,9 +382,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 ct_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float x0 = leaky01(fmaf(__uint_as_float(r[2 * i]), CT_WINV, s_b2[c0 + 2 * i]));
-                    const float x1 = leaky01(fmaf(__uint_as_float(r[2 * i + 1]), CT_WINV, s_b2[c0 + 2 * i + 1]));
-                    split2(x0, x1, hi[i], lo[i], amax);
+                    const float2 b = *reinterpret_cast<const float2 *>(s_b2 + c0 + 2 * i);
+                    const float2 x = leaky01x2(rt_ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
+                                                        make_float2(CT_WINV, CT_WINV), b));
+                    split2(x.x, x.y, hi[i], lo[i], amax);
                 }
                 ct_st16(tAhi + lane_base + c0 / 2, hi);
                 ct_st16(tAlo + lane_base + c0 / 2, lo);
@@ -400,10 +413,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 ct_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = leaky01(fmaf(__uint_as_float(rd[i]), CT_WINV, s_b3[c0 + i]));
-                    const float w = fmaxf(fmaf(__uint_as_float(rw[i]), CT_WINV, s_bc[c0 + i]), 0.0f);
-                    v[i] = w * x;
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 winv = make_float2(CT_WINV, CT_WINV);
+                    const float2 x = leaky01x2(rt_ffma2(make_float2(__uint_as_float(rd[i]), __uint_as_float(rd[i + 1])), winv,
+                                                        *reinterpret_cast<const float2 *>(s_b3 + c0 + i)));
+                    const float2 wl = rt_ffma2(make_float2(__uint_as_float(rw[i]), __uint_as_float(rw[i + 1])), winv,
+                                               *reinterpret_cast<const float2 *>(s_bc + c0 + i));
+                    const float2 pr = rt_fmul2(make_float2(fmaxf(wl.x, 0.0f), fmaxf(wl.y, 0.0f)), x);
+                    v[i] = pr.x;
+                    v[i + 1] = pr.y;
                 }
                 // butterfly over the 16 lanes of a point: every step halves what a lane keeps
 #pragma unroll

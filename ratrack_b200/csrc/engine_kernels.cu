@@ -117,13 +117,6 @@ __global__ void __launch_bounds__(256) maxpool_rows_kernel(long long groups, int
 // neighbour) evaluates the 3->8->8 trunk into shared memory; phase 2: one thread per channel.
 constexpr int WS_PTS = 8;
 
-// two fp32 FMAs in one instruction (SASS FFMA2): each half is an ordinary round-to-nearest fmaf
-__device__ __forceinline__ float2 rt_ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
-                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2 *>(&rd);
-}
 
 __global__ void __launch_bounds__(256) weighted_sum_generic_kernel(RtWeightedSum a) {
     extern __shared__ __align__(16) float s_h2[];  // WS_PTS * ns * 8 trunk outputs, each stored twice (h, h): FFMA2 operands

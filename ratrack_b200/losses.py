@@ -38,10 +38,10 @@ def motion_seg_loss(pred_cls, gt_cls, nan_to_zero=False):
         gt = gt.unsqueeze(0).expand_as(pred_cls)
     pos = (gt == True).to(torch.float32)  # noqa: E712  (the reference's own comparison)
     neg = (gt == False).to(torch.float32)  # noqa: E712
-    p = pred_cls.float()
-    # nn.BCELoss clamps log at -100
-    bce_pos = -torch.clamp(torch.log(p), min=-100.0)
-    bce_neg = -torch.clamp(torch.log1p(-p), min=-100.0)
+    # element-wise nn.BCELoss (log clamped at -100, analytic backward that stays finite at p = 0 or 1 exactly -- a sigmoid
+    # output saturates to 1.0 in fp32 -- which a hand-written -log(p) / -log1p(-p) would not)
+    bce = F.binary_cross_entropy(pred_cls.float(), pos, reduction="none")
+    bce_pos = bce_neg = bce
     n_pos, n_neg = pos.sum(), neg.sum()
     loss = 0.4 * (bce_pos * pos).sum() / n_pos.clamp_min(1.0) + 0.6 * (bce_neg * neg).sum() / n_neg.clamp_min(1.0)
     valid = (n_pos > 0) & (n_neg > 0)

@@ -45,3 +45,16 @@ def test_affinity_ground_truth_and_loss():
     ref = torch.nn.functional.binary_cross_entropy(aff, gt)
     assert float(losses.affinity_loss(aff, gt)) == float(ref)
     assert float(losses.affinity_loss(torch.zeros(0), torch.zeros(0))) == 0.0
+
+
+def test_seg_loss_gradient_is_finite_at_saturated_probabilities():
+    """A sigmoid output reaches exactly 0.0 / 1.0 in fp32; nn.BCELoss (the reference's choice, loss.py:131) keeps the gradient
+    finite there, and so must the mirror (a -log1p(-p) chain would produce 0 * inf = NaN and poison the whole step)."""
+    cls = torch.tensor([[1.0, 0.0, 0.3, 1.0]], requires_grad=True)
+    gt = torch.tensor([True, False, True, False])
+    loss = losses.motion_seg_loss(cls, gt)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(cls.grad).all()
+    ref_pos = torch.nn.BCELoss()(cls.detach()[:, gt], torch.ones(1, 2))
+    ref_neg = torch.nn.BCELoss()(cls.detach()[:, ~gt], torch.zeros(1, 2))
+    assert abs(float(loss) - float(0.4 * ref_pos + 0.6 * ref_neg)) < 1e-5
