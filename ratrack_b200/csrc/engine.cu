@@ -229,17 +229,24 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     }
     rt_fps_set_exclusive((e->flags & 8) ? 1 : 0);
     for (int l = 0; l < 3; ++l) {
-        RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
-        RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
-        RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], s_fps));
+        // one launch per level on the dependent chain: min-distance init, sampling and the gather of new_xyz are fused
+        int rc = rt_launch_fps_fused(B2, lvl_n[l], S, lvl_in[l], w.fps[l], w.xyz[l], s_fps);
+        if (rc == RT_ERR_UNSUPPORTED) {   // cloud too large for the register-resident kernel
+            RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
+            RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
+            RT_TRY(rt_launch_gather_rows(B2, S, lvl_n[l], 3, lvl_in[l], w.fps[l], w.xyz[l], s_fps));
+            e->launches += 2;
+            rc = RT_OK;
+        }
+        RT_TRY(rc);
         cudaEventRecord(L.ev_fps[l], s_fps);
         cudaStreamWaitEvent(s_nbr, L.ev_fps[l], 0);
-        // both radii of the level in one pass; w.bq[l][0] and [1] are adjacent in the workspace: one memset
-        cudaMemsetAsync(w.bq[l][0], 0, (size_t)((char *)(w.bq[l][1] + (size_t)B2 * S * kLevels[l].ns[1]) - (char *)w.bq[l][0]), s_nbr);
+        // both radii of the level in one pass; rows without a hit are zero-filled by the kernel (the reference zero-fills
+        // the buffer from Python, lib/pointnet2_utils.py:246)
         RT_TRY(rt_launch_ball_query2(B2, lvl_n[l], S, kLevels[l].radius[0], kLevels[l].ns[0], w.bq[l][0], kLevels[l].radius[1],
-                                     kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], s_nbr));
+                                     kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], 1, s_nbr));
         cudaEventRecord(L.ev_lvl[l], s_nbr);
-        e->launches += 5;
+        e->launches += 2;
     }
     rt_fps_set_exclusive(0);
     // FP3: unknown xyz[1] <- known xyz[2];  FP2: xyz[0] <- xyz[1];  FP1: xyz0 <- xyz[0]
@@ -386,29 +393,25 @@ int run_head_tc(rt_engine *e, Lane &L, const HeadW &hw, const HeadPacks &pk, Ws 
     const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
     const int lvl_n[3] = {n, S, S};
     float *lvl_out[3] = {w.l1, w.l2, w.l3};
-    const float *lvl_feat_in[3] = {nullptr, w.l1, w.l2};
-    const int lvl_cin[3] = {0, 32, 64};
     const SaScaleW *sw[3] = {hw.l1, hw.l2, hw.l3};
     const float *lin_b[3] = {hw.lin1_b, hw.lin2_b, hw.lin3_b};
     for (int l = 0; l < 3; ++l) {
         const LevelCfg &cfg = kLevels[l];
         const int c1tot = cfg.c1[0] + cfg.c1[1];
-        RtMlpTc pg{};
-        int k0 = 0;
         if (l == 0) {
-            pg = mlp_rows((long long)clouds * n, nullptr, 0, 0);
+            // projection of the level-1 input features through the feature columns of both scales' first conv
+            // (levels 2 and 3: fused with the previous level's Linear, below)
+            RtMlpTc pg = mlp_rows((long long)clouds * n, nullptr, 0, 0);
+            int k0 = 0;
             pg.nseg = nseg;
             for (int i = 0; i < nseg; ++i) { pg.seg[i] = segs[i]; k0 += (segs[i].k + 15) / 16 * 16; }
             pg.cloud_bias = cloud_bias1; pg.rows_per_cloud = n; pg.cloud_bias_ld = c1tot;
-        } else {
-            pg = mlp_rows((long long)clouds * lvl_n[l], lvl_feat_in[l], lvl_cin[l], lvl_cin[l]);
-            k0 = lvl_cin[l];
+            mlp_layer(pg, pk.proj[0], nullptr, k0, c1tot, RT_ACT_NONE);
+            mlp_out(pg, w.proj, c1tot, 0, c1tot);
+            pg.status = w.status;
+            RT_TRY(rt_launch_mlp_tc(pg, st));
+            e->launches += 1;
         }
-        mlp_layer(pg, pk.proj[l], nullptr, k0, c1tot, RT_ACT_NONE);
-        mlp_out(pg, w.proj, c1tot, 0, c1tot);
-        pg.status = w.status;
-        if (l > 0) cudaStreamWaitEvent(st, L.ev_lvl[l - 1], 0);
-        RT_TRY(rt_launch_mlp_tc(pg, st));
         cudaStreamWaitEvent(st, L.ev_lvl[l], 0);   // FPS + ball query of this level
         const int pooled_c = (cfg.c3[0] ? cfg.c3[0] : cfg.c2[0]) + (cfg.c3[1] ? cfg.c3[1] : cfg.c2[1]);
         int coff = 0;
@@ -427,12 +430,21 @@ int run_head_tc(rt_engine *e, Lane &L, const HeadW &hw, const HeadPacks &pk, Ws 
             RT_TRY(rt_launch_mlp_tc(m, st));
             coff += clast;
         }
+        // Linear after the max-pool; for levels 1 and 2 the next level's projection rides in the same launch as a second
+        // layer (the Linear's fp32 output is kept too: the FP layers read it as skip features)
         RtMlpTc lg = mlp_rows((long long)clouds * S, w.pooled, pooled_c, pooled_c);
         mlp_layer(lg, pk.lin[l], lin_b[l], pooled_c, cfg.lin_out, RT_ACT_NONE);
-        mlp_out(lg, lvl_out[l], cfg.lin_out, 0, cfg.lin_out);
+        if (l < 2) {
+            const int c1next = kLevels[l + 1].c1[0] + kLevels[l + 1].c1[1];
+            mlp_layer(lg, pk.proj[l + 1], nullptr, cfg.lin_out, c1next, RT_ACT_NONE);
+            lg.mid_out = lvl_out[l]; lg.mid_ldo = cfg.lin_out; lg.mid_layer = 0;
+            mlp_out(lg, w.proj, c1next, 0, c1next);
+        } else {
+            mlp_out(lg, lvl_out[l], cfg.lin_out, 0, cfg.lin_out);
+        }
         lg.status = w.status;
         RT_TRY(rt_launch_mlp_tc(lg, st));
-        e->launches += 4;
+        e->launches += 3;
     }
     cudaStreamWaitEvent(st, L.ev_nn, 0);
     // the three-point interpolation is evaluated inside the GEMM's operand loader (no interp buffer, no extra launch)

@@ -101,4 +101,6 @@ int rt_launch_fill(float *p, long long n, float v, cudaStream_t st);
 int rt_launch_morton_perm(int clouds, int n, const float *xyz, int *perm, cudaStream_t st);
 // neighbors.cu: ball query of two radii over the same centres in one launch
 int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
-                          int *idx_b, const float *new_xyz, const float *xyz, cudaStream_t st);
+                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st);
+// fps.cu: FPS from the reference's initial state that also emits new_xyz = xyz[idx]; RT_ERR_UNSUPPORTED -> use the 3-launch path
+int rt_launch_fps_fused(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st);

@@ -35,9 +35,13 @@ __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
 
 // T threads; each thread owns PPT = Q*PH points.  bs = T*Q is the reference CTA size.
 // Slot s (priority order) = a*PH + ph  ->  point k = r + (bitrev_q(a) + Q*ph)*T,  r = bitrev_logT(t).
-template <int T, int Q, int PH>
+// FUSED (engine-internal): the running min-distance starts at the reference's 1e10 in registers and is never stored
+// (no temp buffer, no fill kernel), and the coordinates of every selected point are written to new_xyz as it is picked
+// (no gather kernel) -- two dependent launches fewer per level on the latency-critical FPS chain.
+template <int T, int Q, int PH, bool FUSED>
 __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all,
-                                                    float *__restrict__ temp_all, int *__restrict__ idx_all) {
+                                                    float *__restrict__ temp_all, int *__restrict__ idx_all,
+                                                    float *__restrict__ new_xyz_all) {
     constexpr int PPT = Q * PH;
     constexpr int NW = (T + 31) / 32;
     constexpr int LOGT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;
@@ -49,8 +53,9 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *_
 
     const int cloud = blockIdx.x;
     const float *xyz = xyz_all + (size_t)cloud * n * 3;
-    float *temp = temp_all + (size_t)cloud * n;
+    float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n;
     int *idx = idx_all + (size_t)cloud * m;
+    float *new_xyz = FUSED ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
 
@@ -73,11 +78,12 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *_
         px[s] = s_xyz[kk * 3 + 0];
         py[s] = s_xyz[kk * 3 + 1];
         pz[s] = s_xyz[kk * 3 + 2];
-        td[s] = (k < n) ? temp[k] : -2.0f;  // padding never beats the reference's initial best of -1
+        td[s] = (k < n) ? (FUSED ? 1e10f : temp[k]) : -2.0f;  // padding never beats the reference's initial best of -1
     }
 
     int old = 0;
     if (t == 0) idx[0] = 0;
+    if (FUSED && t < 3) new_xyz[t] = s_xyz[t];
 
     for (int j = 1; j < m; ++j) {
         const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
@@ -127,11 +133,14 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *_
         }
         old = win;
         if (t == 0) idx[j] = old;
+        if (FUSED && t < 3) new_xyz[j * 3 + t] = s_xyz[old * 3 + t];
     }
 
+    if (!FUSED) {
 #pragma unroll
-    for (int s = 0; s < PPT; ++s)
-        if (pk[s] >= 0) temp[pk[s]] = td[s];
+        for (int s = 0; s < PPT; ++s)
+            if (pk[s] >= 0) temp[pk[s]] = td[s];
+    }
 }
 
 // Generic kernel: any n >= 1, temp kept in global memory (L1/L2 resident), 256 threads.
@@ -187,8 +196,8 @@ __global__ void __launch_bounds__(256) fps_generic_kernel(int n, int m, int bs, 
     }
 }
 
-template <int T, int Q, int PH>
-int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t st) {
+template <int T, int Q, int PH, bool FUSED>
+int launch_reg2(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
     size_t smem = (size_t)n * 3 * sizeof(float);
     // SM-exclusive mode (rt_fps_set_exclusive): every round of this kernel is a dependent latency chain, and any CTA
     // sharing the SM stretches each round 2-3x (measured on B200).  Asking for (nearly) the whole shared memory of the
@@ -196,11 +205,16 @@ int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, cud
     if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
     static size_t attr_bytes = 0;
     if (smem > 40 * 1024 && smem > attr_bytes) {
-        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
         attr_bytes = kFpsHogBytes;
     }
-    fps_reg_kernel<T, Q, PH><<<b, T, smem, st>>>(n, m, xyz, temp, idx);
+    fps_reg_kernel<T, Q, PH, FUSED><<<b, T, smem, st>>>(n, m, xyz, temp, idx, new_xyz);
     return rt_check_launch("fps_reg_kernel");
+}
+template <int T, int Q, int PH>
+int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
+    return new_xyz ? launch_reg2<T, Q, PH, true>(b, n, m, xyz, temp, idx, new_xyz, st)
+                   : launch_reg2<T, Q, PH, false>(b, n, m, xyz, temp, idx, nullptr, st);
 }
 
 }  // namespace
@@ -208,23 +222,20 @@ int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, cud
 // engine-internal: 1 = FPS CTAs claim a whole SM each (see launch_reg)
 void rt_fps_set_exclusive(int on) { g_fps_exclusive = on; }
 
-// C-ABI.  replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47)
-RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream) {
-    RT_REQUIRE(b >= 0 && n >= 1 && xyz && temp && idx, "furthest_point_sampling: bad arguments (b=%d n=%d)", b, n);
-    if (m <= 0 || b == 0) return RT_OK;  // reference kernel returns early on m <= 0
-    cudaStream_t st = (cudaStream_t)stream;
+// register-resident variants; returns 1 when one was launched, 0 when the shape needs the generic kernel, < 0 / > 0 on error
+static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st, int *launched) {
     const int bs = rt_ref_block_size(n);
     const int ph = (n + bs - 1) / bs;
-    // register-resident variants: T threads, Q = bs / T residues per thread, PH = ceil(n / bs) passes.
-    // T = 256 halves the per-thread work of a round (the rounds are a pure latency chain); RT_FPS_THREADS=128
-    // selects the 4-warp variant for A/B timing.
+    // T threads, Q = bs / T residues per thread, PH = ceil(n / bs) passes.  T = 256 halves the per-thread work of a round
+    // (the rounds are a pure latency chain); RT_FPS_THREADS=128 selects the 4-warp variant for A/B timing.
     static int pref_t = 0;
     if (!pref_t) {
         const char *env = getenv("RT_FPS_THREADS");
         pref_t = (env && atoi(env) == 128) ? 128 : 256;
     }
+    *launched = 1;
 #define RT_FPS_CASE(TT, QQ, PP) \
-    if (t == TT && q == QQ && ph == PP) return launch_reg<TT, QQ, PP>(b, n, m, xyz, temp, idx, st);
+    if (t == TT && q == QQ && ph == PP) return launch_reg<TT, QQ, PP>(b, n, m, xyz, temp, idx, new_xyz, st);
     if (bs >= 128 && ph <= 4) {
         const int t = (bs >= 256 && pref_t == 256) ? 256 : 128;
         const int q = bs / t;
@@ -236,11 +247,34 @@ RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, flo
         RT_FPS_CASE(128, 4, 1) RT_FPS_CASE(128, 4, 2)
         RT_FPS_CASE(128, 8, 1) RT_FPS_CASE(128, 8, 2)
         if (bs == 1024 && ph <= 4) {  // 2048 < n <= 4096 with the 128-thread preference: 256 threads x 16 points
-            if (ph == 3) return launch_reg<256, 4, 3>(b, n, m, xyz, temp, idx, st);
-            return launch_reg<256, 4, 4>(b, n, m, xyz, temp, idx, st);
+            if (ph == 3) return launch_reg<256, 4, 3>(b, n, m, xyz, temp, idx, new_xyz, st);
+            return launch_reg<256, 4, 4>(b, n, m, xyz, temp, idx, new_xyz, st);
         }
     }
 #undef RT_FPS_CASE
+    *launched = 0;
+    return RT_OK;
+}
+
+// engine-internal: FPS from the reference's initial state (temp = 1e10) that also emits new_xyz (b,m,3) = xyz[idx].
+// Returns RT_ERR_UNSUPPORTED when the shape has no register-resident variant (caller falls back to fill + FPS + gather).
+int rt_launch_fps_fused(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st) {
+    if (m <= 0 || b == 0) return RT_OK;
+    int launched = 0;
+    const int rc = fps_dispatch(b, n, m, xyz, nullptr, idx, new_xyz, st, &launched);
+    if (rc != RT_OK) return rc;
+    return launched ? RT_OK : RT_ERR_UNSUPPORTED;
+}
+
+// C-ABI.  replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47)
+RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream) {
+    RT_REQUIRE(b >= 0 && n >= 1 && xyz && temp && idx, "furthest_point_sampling: bad arguments (b=%d n=%d)", b, n);
+    if (m <= 0 || b == 0) return RT_OK;  // reference kernel returns early on m <= 0
+    cudaStream_t st = (cudaStream_t)stream;
+    int launched = 0;
+    const int rc = fps_dispatch(b, n, m, xyz, temp, idx, nullptr, st, &launched);
+    if (rc != RT_OK || launched) return rc;
+    const int bs = rt_ref_block_size(n);
     int logbs = 0;
     while ((1 << logbs) < bs) ++logbs;
     RT_REQUIRE((n >> logbs) < (1 << 21), "furthest_point_sampling: n too large");

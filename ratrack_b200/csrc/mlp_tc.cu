@@ -362,6 +362,12 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     for (int i = 0; i < 16; ++i) v[i] = mt_act(v[i], slope);
                     if (!last) {
                         mt_store16(v, tAhi + lane_base + c0 / 2, tAlo + lane_base + c0 / 2, amax);
+                        if (a.mid_out && l == a.mid_layer && valid) {
+                            float *o = a.mid_out + row * a.mid_ldo + c0;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                reinterpret_cast<float4 *>(o)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        }
                     } else if (a.out_mode == RT_MLP_OUT_ROWS) {
                         if (valid) {
                             float *o = a.out + row * a.ldo + a.ooff + c0;
@@ -436,6 +442,9 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
         RT_REQUIRE(a.c1 == a.layer[0].k && a.c1 <= 64 && (a.ldy & 3) == 0 && (a.yoff & 3) == 0, "mlp_tc: gather layout");
     }
     RT_REQUIRE(a.rows < (1ll << 31) - 256, "mlp_tc: %lld rows (32-bit row arithmetic)", a.rows);
+    RT_REQUIRE(!a.mid_out || (a.mid_layer >= 0 && a.mid_layer < a.nlayers - 1 && (a.mid_ldo & 3) == 0 &&
+                              (reinterpret_cast<uintptr_t>(a.mid_out) & 15) == 0),
+               "mlp_tc: mid output needs a non-final layer, ld %% 4 == 0 and 16-byte alignment");
     if (a.load_mode == RT_MLP_LOAD_ROWS) {
         for (int s = 0; s < a.nseg; ++s)
             RT_REQUIRE((a.seg[s].ldx & 3) != 0 || (reinterpret_cast<uintptr_t>(a.seg[s].x) & 31) == 0,

@@ -41,6 +41,8 @@ struct RtMlpTc {
     int rows_per_cloud, cloud_bias_ld;
     float *out;                // rows: out[row * ldo + ooff + c]; maxpool: out[(row / ns) * ldo + ooff + c], c < n_out
     int ldo, ooff, n_out;
+    float *mid_out;            // optional: the (activated) output of layer `mid_layer` (not the last) is also written as fp32 rows,
+    int mid_ldo, mid_layer;    //           mid_out[row * mid_ldo + c], c < layer[mid_layer].n -- two chained GEMMs, both results kept
     int *status;               // optional device status word (bit 1: fp16 range exceeded)
     int tmem_cols, d_cols, a_cols, ns_shift;  // filled by the launcher
 };

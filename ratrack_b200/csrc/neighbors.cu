@@ -55,7 +55,7 @@ __device__ __forceinline__ void bq_compact(bool hit_a, bool hit_b, int cand, int
 __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, float radius_a, int nsample_a, int *__restrict__ idx_a,
                                                                 float radius_b, int nsample_b, int *__restrict__ idx_b,
                                                                 const float *__restrict__ new_xyz,
-                                                                const float *__restrict__ xyz) {
+                                                                const float *__restrict__ xyz, int zero_fill) {
     extern __shared__ __align__(16) float s_pts[];  // roundup32(min(n, TILE_PTS))*3
     __shared__ __align__(8) uint64_t s_bar;
     const int cloud = blockIdx.y;
@@ -122,17 +122,20 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
             st[i + 1] = s1;
         }
     }
-    // pad unused slots with the first hit; queries with no hit leave the caller's buffer untouched
+    // pad unused slots with the first hit; queries with no hit leave the caller's buffer untouched (the reference's
+    // Python zero-fills it first) unless `zero_fill` asks this kernel to write the zeros itself (engine: no memset launch)
 #pragma unroll
     for (int i = 0; i < QPW; ++i) {
         if (q0 + i >= m) continue;
-        if (st[i].fa >= 0) {
+        if (st[i].fa >= 0 || zero_fill) {
             int *out = idx_a + ((size_t)cloud * m + (q0 + i)) * nsample_a;
-            for (int s = st[i].ca + lane; s < nsample_a; s += 32) out[s] = st[i].fa;
+            const int fill = st[i].fa >= 0 ? st[i].fa : 0;
+            for (int s = st[i].ca + lane; s < nsample_a; s += 32) out[s] = fill;
         }
-        if (st[i].fb >= 0) {
+        if (st[i].fb >= 0 || zero_fill) {
             int *out = idx_b + ((size_t)cloud * m + (q0 + i)) * nsample_b;
-            for (int s = st[i].cb + lane; s < nsample_b; s += 32) out[s] = st[i].fb;
+            const int fill = st[i].fb >= 0 ? st[i].fb : 0;
+            for (int s = st[i].cb + lane; s < nsample_b; s += 32) out[s] = fill;
         }
     }
 }
@@ -334,18 +337,18 @@ RT_API int rt_ball_query(int b, int n, int m, float radius, int nsample, const f
     RT_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
-                                                                                 new_xyz, xyz);
+                                                                                 new_xyz, xyz, 0);
     return rt_check_launch("ball_query_kernel");
 }
 
 // engine-internal: two radii over the same centres in one launch (same results as two rt_ball_query calls)
 int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
-                          int *idx_b, const float *new_xyz, const float *xyz, cudaStream_t st) {
+                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st) {
     if (b == 0 || m == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535 && nsample_a > 0 && nsample_b > 0, "ball_query2: bad arguments");
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
-                                                              new_xyz, xyz);
+                                                              new_xyz, xyz, zero_fill);
     return rt_check_launch("ball_query_kernel(2 radii)");
 }
 
