@@ -130,6 +130,12 @@ int rt_engine_last_status(rt_engine *e, int *status_out);
 /* kernels launched by this engine since creation */
 long long rt_engine_launch_count(const rt_engine *e);
 
+/* stage profile: on != 0 makes the next forwards record CUDA timing events at their stage boundaries (feature-path
+ * stream); rt_engine_stage_times blocks on the last forward and writes up to `cap` intervals in milliseconds (and their
+ * names, static strings) -- returns how many.  Measurement aid: no effect on results. */
+int rt_engine_stage_profile(rt_engine *e, int on);
+int rt_engine_stage_times(rt_engine *e, float *ms, const char **names, int cap);
+
 /* pc1, pc2 (b,3,n); ft1, ft2 (b,2,n); h_in (5,b,128)  ->  flow (b,3,n), h_out (5,b,128), cls (b,n),
  * cor (b,256,n), f1, f2 (b,256,n), prop (b,128,n): the 7-tuple of Track4D.backbone (track4d.py:86).
  * knn12 / knn11 (b,n,16) int32, optional (NULL to skip): the cost volume's neighbour sets pc1->pc2, pc1->pc1

@@ -28,6 +28,7 @@ SIGNATURES = {
     "rt_engine_create": [ctypes.POINTER(ctypes.c_void_p), _I, ctypes.POINTER(ctypes.c_void_p), _I],
     "rt_engine_set_profile_events": [_P, _P, _P],
     "rt_engine_set_flags": [_P, _I],
+    "rt_engine_stage_profile": [_P, _I],
     "rt_engine_last_status": [_P, ctypes.POINTER(ctypes.c_int)],
     "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
 }
@@ -38,6 +39,7 @@ OTHER = {
     "rt_engine_workspace_bytes": ([_P, _I, _I], ctypes.c_longlong),
     "rt_engine_launch_count": ([_P], ctypes.c_longlong),
     "rt_engine_num_lanes": ([_P, _I], ctypes.c_int),
+    "rt_engine_stage_times": ([_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p), _I], ctypes.c_int),
 }
 
 _lib = None

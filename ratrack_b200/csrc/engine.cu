@@ -180,7 +180,7 @@ struct Lane {
     // output stream: API-layout transposes and the cls head hang off the feature path, nothing waits for them until the end
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_fps[3] = {nullptr, nullptr, nullptr}, ev_lvl[3] = {nullptr, nullptr, nullptr},
-                ev_nn = nullptr, ev_knn = nullptr, ev_gh = nullptr, ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr,
+                ev_nn = nullptr, ev_knn = nullptr, ev_knn11 = nullptr, ev_sa3 = nullptr, ev_gh = nullptr, ev_feat = nullptr, ev_cor = nullptr, ev_prop = nullptr, ev_aux = nullptr,
                 ev_done = nullptr;
 };
 
@@ -198,13 +198,29 @@ struct rt_engine {
                                    // bit 2 (off by default: measured 4 % slower at 32 pairs, neutral at 128): split batches of >= 8 pairs over two lanes
                                    // bit 3: FPS CTAs claim a whole SM each (fps.cu launch_reg) so co-running kernels cannot stretch the chain
                                    // bit 4: cost-volume kNN starts with the FPS chain instead of behind it (pair with bit 3)
+                                   // bit 7: with bit 3, two clouds share one FPS CTA (2b clouds block b SMs instead of 2b)
                                    // bit 6: the cost-volume kernels walk pc1 in Morton order (tiles of spatial neighbours share gathered rows)
                                    // bit 5: the feature path runs on an engine-owned stream of middle priority (geometry above it, kNN
                                    //        and API-layout outputs below it) forked from / joined to the caller's stream
     const int *last_status[2] = {nullptr, nullptr};
+    // optional stage profile (rt_engine_stage_profile): timing events recorded on the feature-path stream of lane 0 at the
+    // boundaries of the forward, so the critical path can be read without a profiler's launch overhead distorting it
+    static constexpr int kStages = 16;
+    cudaEvent_t stage_ev[kStages] = {};
+    int stage_n = 0;
+    bool stage_on = false;
 };
 
 namespace {
+
+// name of the interval that ENDS at mark i (mark 0 = inputs are row-major, geometry forked)
+const char *const kStageNames[] = {"inputs->rows", "pn_head SA1 (waits for FPS-1 + ball query 1)", "pn_head SA2", "pn_head SA3", "pn_head FP",
+                                   "global max + P1/P2 projections", "wait for the cost-volume kNN", "cost volume (costvol_tc)",
+                                   "patch-to-patch sum", "mse SA1", "mse SA2", "mse SA3", "mse FP", "cloud max + GRU",
+                                   "flow head + output join", "-"};
+inline void stage_mark(rt_engine *e, int lane_idx, cudaStream_t st) {
+    if (e->stage_on && lane_idx == 0 && e->stage_n < rt_engine::kStages) cudaEventRecord(e->stage_ev[e->stage_n++], st);
+}
 
 // geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN.
 // Every stage records an event the feature path (and the dependent geometry stages) wait on.
@@ -221,13 +237,20 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
         RT_TRY(rt_launch_morton_perm(b, n, pc1, w.perm1, s_knn));
         e->launches += 1;
     }
+    // bit 8: the self-kNN (pc1 -> pc1) is needed only by the patch-to-patch sum: it is launched by the feature path after
+    // the last SA level of pn_head (run_self_knn) and fills the under-occupied FP / projection stages instead of competing
+    // with the SA kernels
+    const bool knn11_late = (e->flags & 256) != 0 && (e->flags & 2) != 0;   // the hook lives in the tensor-core head
     if (knn_early) {
         RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
-        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
         cudaEventRecord(L.ev_knn, s_knn);
+        if (!knn11_late) {
+            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+            cudaEventRecord(L.ev_knn11, s_knn);
+        }
         e->launches += 2;
     }
-    rt_fps_set_exclusive((e->flags & 8) ? 1 : 0);
+    rt_fps_set_exclusive(((e->flags & 8) ? 1 : 0) | ((e->flags & 128) ? 2 : 0));
     for (int l = 0; l < 3; ++l) {
         // one launch per level on the dependent chain: min-distance init, sampling and the gather of new_xyz are fused
         int rc = rt_launch_fps_fused(B2, lvl_n[l], S, lvl_in[l], w.fps[l], w.xyz[l], s_fps);
@@ -265,8 +288,11 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     if (!knn_early) {
         cudaStreamWaitEvent(s_knn, L.ev_fps[2], 0);
         RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
-        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
         cudaEventRecord(L.ev_knn, s_knn);
+        if (!knn11_late) {
+            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+            cudaEventRecord(L.ev_knn11, s_knn);
+        }
         e->launches += 2;
     }
     return RT_OK;
@@ -387,8 +413,8 @@ void mlp_out(RtMlpTc &m, float *out, int ldo, int ooff, int n_out) {
 }
 
 // PNHead on the tensor cores: per level  projection GEMM -> 2 x [gather + conv chain + max-pool] -> linear
-int run_head_tc(rt_engine *e, Lane &L, const HeadW &hw, const HeadPacks &pk, Ws &w, int clouds, int n, const RtMlpSeg *segs, int nseg,
-                const float *cloud_bias1, float *out, cudaStream_t st) {
+int run_head_tc(rt_engine *e, Lane &L, int lane_idx, const HeadW &hw, const HeadPacks &pk, Ws &w, int clouds, int n, const RtMlpSeg *segs,
+                int nseg, const float *cloud_bias1, float *out, cudaStream_t st, bool self_knn_after_sa = false) {
     const int S = e->npoint;
     const float *lvl_xyz_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
     const int lvl_n[3] = {n, S, S};
@@ -445,6 +471,13 @@ int run_head_tc(rt_engine *e, Lane &L, const HeadW &hw, const HeadPacks &pk, Ws 
         lg.status = w.status;
         RT_TRY(rt_launch_mlp_tc(lg, st));
         e->launches += 3;
+        stage_mark(e, lane_idx, st);
+        if (l == 2 && self_knn_after_sa) {   // late self-kNN: from here on the feature path runs small kernels
+            cudaEventRecord(L.ev_sa3, st);
+            cudaStreamWaitEvent(L.geo_stream[2], L.ev_sa3, 0);
+            RT_TRY(rt_launch_knn_expanded(clouds / 2, n, n, kKnn, w.xyz0, w.xyz0, w.knn11, L.geo_stream[2]));
+            cudaEventRecord(L.ev_knn11, L.geo_stream[2]);
+        }
     }
     cudaStreamWaitEvent(st, L.ev_nn, 0);
     // the three-point interpolation is evaluated inside the GEMM's operand loader (no interp buffer, no extra launch)
@@ -600,7 +633,7 @@ RT_API int rt_engine_create(rt_engine **out, int npoint, const void *const *weig
         cudaStreamCreateWithPriority(&L.geo_stream[2], cudaStreamNonBlocking, prio_least);
         cudaStreamCreateWithPriority(&L.aux_stream, cudaStreamNonBlocking, prio_least);
         cudaEvent_t *evs[] = {&L.ev_in, &L.ev_fps[0], &L.ev_fps[1], &L.ev_fps[2], &L.ev_lvl[0], &L.ev_lvl[1], &L.ev_lvl[2],
-                              &L.ev_nn, &L.ev_knn, &L.ev_gh, &L.ev_feat, &L.ev_cor, &L.ev_prop, &L.ev_aux, &L.ev_done};
+                              &L.ev_nn, &L.ev_knn, &L.ev_knn11, &L.ev_sa3, &L.ev_gh, &L.ev_feat, &L.ev_cor, &L.ev_prop, &L.ev_aux, &L.ev_done};
         for (cudaEvent_t *ev : evs) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     }
     const int rc = build_packs(e);
@@ -617,13 +650,15 @@ RT_API void rt_engine_destroy(rt_engine *e) {
     if (!e) return;
     if (e->arena) cudaFree(e->arena);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (cudaEvent_t ev : e->stage_ev)
+        if (ev) cudaEventDestroy(ev);
     for (Lane &L : e->lanes) {
         if (L.main_stream) cudaStreamDestroy(L.main_stream);
         for (int g = 0; g < 3; ++g)
             if (L.geo_stream[g]) cudaStreamDestroy(L.geo_stream[g]);
         if (L.aux_stream) cudaStreamDestroy(L.aux_stream);
         cudaEvent_t evs[] = {L.ev_in, L.ev_fps[0], L.ev_fps[1], L.ev_fps[2], L.ev_lvl[0], L.ev_lvl[1], L.ev_lvl[2],
-                             L.ev_nn, L.ev_knn, L.ev_gh, L.ev_feat, L.ev_cor, L.ev_prop, L.ev_aux, L.ev_done};
+                             L.ev_nn, L.ev_knn, L.ev_knn11, L.ev_sa3, L.ev_gh, L.ev_feat, L.ev_cor, L.ev_prop, L.ev_aux, L.ev_done};
         for (cudaEvent_t ev : evs)
             if (ev) cudaEventDestroy(ev);
     }
@@ -655,6 +690,28 @@ RT_API int rt_engine_set_profile_events(rt_engine *e, void *start, void *stop) {
 }
 
 RT_API long long rt_engine_launch_count(const rt_engine *e) { return e ? e->launches : -1; }
+
+// Stage profile of the NEXT forwards (lane 0's feature-path stream): on = 1 creates timing events and records one at every
+// stage boundary; rt_engine_stage_times synchronises and returns the milliseconds between consecutive marks of the last
+// forward (ms[i] = duration of stage names[i+1]).  Returns the number of intervals written.
+RT_API int rt_engine_stage_profile(rt_engine *e, int on) {
+    RT_REQUIRE(e, "engine_stage_profile: null engine");
+    if (on && !e->stage_ev[0])
+        for (cudaEvent_t &ev : e->stage_ev) cudaEventCreate(&ev);
+    e->stage_on = on != 0;
+    e->stage_n = 0;
+    return RT_OK;
+}
+RT_API int rt_engine_stage_times(rt_engine *e, float *ms, const char **names, int cap) {
+    if (!e || !ms || e->stage_n < 2) return 0;
+    cudaEventSynchronize(e->stage_ev[e->stage_n - 1]);
+    int n = 0;
+    for (int i = 1; i < e->stage_n && n < cap; ++i, ++n) {
+        cudaEventElapsedTime(&ms[n], e->stage_ev[i - 1], e->stage_ev[i]);
+        if (names) names[n] = kStageNames[i < 16 ? i : 15];
+    }
+    return n;
+}
 
 RT_API int rt_engine_set_flags(rt_engine *e, int flags) {
     RT_REQUIRE(e, "engine_set_flags: null engine");
@@ -698,6 +755,8 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_cm_to_rows(b, 2, n, ft2, w.ft0 + half2, 2, 0, st));
     e->launches += 4;
     // fork: geometry depends only on xyz, so it runs on its own stream and the feature path joins stage by stage
+    if (lane_idx == 0) e->stage_n = 0;
+    stage_mark(e, lane_idx, st);   // (the inputs->rows kernels precede this mark; "start" is recorded by the caller below)
     cudaEventRecord(L.ev_in, st);
     RT_TRY(run_geometry(e, L, w, b, n));
     // hidden half of the GRU (depends on h_in only): off the critical path, on the output stream
@@ -711,11 +770,12 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     e->last_status[lane_idx] = w.status;
     if (tc_mlp) {
         RtMlpSeg seg_ft{w.ft0, 2, 2, nullptr, nullptr, 0, 0};
-        RT_TRY(run_head_tc(e, L, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
+        RT_TRY(run_head_tc(e, L, lane_idx, e->w.pn, e->packs.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st, (e->flags & 256) != 0 && (e->flags & 2) != 0));
     } else {
         RtSeg seg_ft{w.ft0, 2, 2, e->w.pn.wf_ft, 2};
         RT_TRY(run_head(e, L, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     }
+    stage_mark(e, lane_idx, st);   // pn_head FP done
     RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
     // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95): off the critical path
     cudaStream_t aux = tc_mlp ? L.aux_stream : st;
@@ -753,7 +813,9 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         g.cloud_bias = w.cb_b; g.rows_per_cloud = n;
         RT_TRY(rt_launch_rowgemm(g, st));
     }
+    stage_mark(e, lane_idx, st);   // global max + P1/P2 done
     cudaStreamWaitEvent(st, L.ev_knn, 0);   // join: everything the geometry stream produced is now ordered before `st`
+    stage_mark(e, lane_idx, st);   // kNN joined
     if (e->flags & 1) {
         if (e->prof_start && lane_idx == 0) cudaEventRecord(e->prof_start, st);
         RT_TRY(rt_launch_costvol_tc(b * n, n, w.p1, w.p2, x1, x2, w.knn12, (e->flags & 64) ? w.perm1 : nullptr, cv.w1_x, cv.w23_pack, cv.wc1_pack, cv.b2, cv.b3,
@@ -777,11 +839,14 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         ws.v = w.xa; ws.out = w.cost1;
         ws.perm = (e->flags & 64) ? w.perm1 : nullptr;
         if (!(e->flags & 1)) RT_TRY(rt_launch_weighted_sum(ws, st));
+        stage_mark(e, lane_idx, st);   // cost volume done
+        cudaStreamWaitEvent(st, L.ev_knn11, 0);
         ws.gather_v = 1; ws.idx = w.knn11; ws.xyz_in = x1;
         ws.wa = cv.wn2.wa; ws.ba = cv.wn2.ba; ws.wb = cv.wn2.wb; ws.bb = cv.wn2.bb; ws.wc = cv.wn2.wc; ws.bc = cv.wn2.bc;
         ws.v = w.cost1; ws.out = w.cor;
         RT_TRY(rt_launch_weighted_sum(ws, st));
     }
+    stage_mark(e, lane_idx, st);   // patch-to-patch sum done
     if (aux != st) {
         cudaEventRecord(L.ev_cor, st);
         cudaStreamWaitEvent(aux, L.ev_cor, 0);
@@ -812,12 +877,13 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     if (tc_mlp) {
         RtMlpSeg segs[3] = {RtMlpSeg{w.ft0, 2, 2, nullptr, nullptr, 0, 0}, RtMlpSeg{w.feat, 128, 128, nullptr, nullptr, 0, 0},
                             RtMlpSeg{w.cor, 256, 256, nullptr, nullptr, 0, 0}};
-        RT_TRY(run_head_tc(e, L, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
+        RT_TRY(run_head_tc(e, L, lane_idx, mse, e->packs.mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     } else {
         RtSeg segs[3] = {RtSeg{w.ft0, 2, 2, mse.wf_ft, 2}, RtSeg{w.feat, 128, 128, mse.wf_loc, 128},
                          RtSeg{w.cor, 256, 256, mse.wf_cor, 256}};
         RT_TRY(run_head(e, L, mse, w, b, n, segs, 3, w.cb_a, w.prop, st));
     }
+    stage_mark(e, lane_idx, st);   // mse FP done
     if (aux != st) {
         cudaEventRecord(L.ev_prop, st);
         cudaStreamWaitEvent(aux, L.ev_prop, 0);
@@ -827,6 +893,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
     cudaStreamWaitEvent(st, L.ev_gh, 0);
     RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.bih, w.gru_gh, h_out, h_stride, st));
+    stage_mark(e, lane_idx, st);   // GRU done
     // FlowPredictor on cat(prop_features, broadcast GRU output)
     const FlowW &fp = e->w.fp;
     RT_TRY(rt_launch_cloud_matvec(b, 128, 128, fp.w1_g, 128, h_out + 4 * h_stride, 128, fp.b1, w.cb_b, st));
@@ -850,6 +917,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
     e->launches += 11;
     if (aux != st) cudaStreamWaitEvent(st, L.ev_aux, 0);   // join the output stream
+    stage_mark(e, lane_idx, st);   // flow head + joined outputs
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     return rt_check_launch("backbone_forward");

@@ -25,6 +25,7 @@
 namespace {
 
 int g_fps_exclusive = 0;
+int g_fps_pair = 0;
 constexpr size_t kFpsHogBytes = 226 * 1024;   // + static + the 1 KB per-CTA reserve = the SM's 228 KB: no other CTA fits beside it
 
 __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
@@ -38,33 +39,58 @@ __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
 // FUSED (engine-internal): the running min-distance starts at the reference's 1e10 in registers and is never stored
 // (no temp buffer, no fill kernel), and the coordinates of every selected point are written to new_xyz as it is picked
 // (no gather kernel) -- two dependent launches fewer per level on the latency-critical FPS chain.
-template <int T, int Q, int PH, bool FUSED>
-__global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all,
-                                                    float *__restrict__ temp_all, int *__restrict__ idx_all,
-                                                    float *__restrict__ new_xyz_all) {
+// CPB clouds per CTA (engine-internal, with the SM-exclusive mode): CPB independent groups of T threads, each with its own
+// named barrier, share one SM -- two latency-bound chains interleave almost for free, and the sampling of 2b clouds blocks
+// b SMs instead of 2b.
+template <int T, int Q, int PH, bool FUSED, int CPB>
+__global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int m, const float *__restrict__ xyz_all,
+                                                         float *__restrict__ temp_all, int *__restrict__ idx_all,
+                                                         float *__restrict__ new_xyz_all) {
     constexpr int PPT = Q * PH;
     constexpr int NW = (T + 31) / 32;
     constexpr int LOGT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;
     constexpr int LOGQ = (Q == 1) ? 0 : (Q == 2) ? 1 : (Q == 4) ? 2 : (Q == 8) ? 3 : (Q == 16) ? 4 : 5;
 
-    extern __shared__ __align__(16) float s_xyz[];  // n*3 floats
-    __shared__ uint2 s_red[2][NW];
-    __shared__ __align__(8) uint64_t s_bar;
+    extern __shared__ __align__(16) float s_xyz_all[];  // CPB x roundup4(n*3) floats
+    __shared__ uint2 s_red_all[CPB][2][NW];
+    __shared__ __align__(8) uint64_t s_bar_all[CPB];
 
-    const int cloud = blockIdx.x;
+    const int grp = (CPB == 1) ? 0 : (int)threadIdx.x / T;       // which cloud of the CTA this thread works on
+    const int cloud = blockIdx.x * CPB + grp;
+    if (cloud >= nclouds) return;                                // whole group leaves together (named barriers are per group)
+    float *s_xyz = s_xyz_all + (size_t)grp * ((n * 3 + 3) & ~3);
+    uint2(*s_red)[NW] = s_red_all[grp];
+    uint64_t &s_bar = s_bar_all[grp];
     const float *xyz = xyz_all + (size_t)cloud * n * 3;
     float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n;
     int *idx = idx_all + (size_t)cloud * m;
     float *new_xyz = FUSED ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
-    const int t = threadIdx.x;
+    const int t = (CPB == 1) ? (int)threadIdx.x : (int)threadIdx.x % T;   // thread within the group
     const int lane = t & 31, warp = t >> 5;
+    // group-wide barrier: id 1 + grp, T threads (bar.sync with an id lets the CPB groups of a CTA run independently)
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(T) : "memory"); };
 
     if (t == 0) {
         rt_mbar_init(&s_bar, 1);
         rt_fence_mbar_init();
     }
-    __syncthreads();
-    rt_stage_floats(s_xyz, xyz, n * 3, &s_bar, 0);
+    group_sync();
+    {   // stage the cloud's xyz: bulk copy (TMA engine) when 16-byte aligned, plain loads for the tail / unaligned clouds
+        const int nfl = n * 3;
+        const int bulk = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) ? (nfl & ~3) : 0;
+        if (t == 0) {
+            if (bulk > 0) {
+                rt_mbar_expect_tx(&s_bar, (uint32_t)bulk * 4u);
+                for (int off = 0; off < bulk; off += 16384)
+                    rt_bulk_g2s(s_xyz + off, xyz + off, (uint32_t)min(16384, bulk - off) * 4u, &s_bar);
+            } else {
+                rt_mbar_arrive(&s_bar);
+            }
+        }
+        for (int i = bulk + t; i < nfl; i += T) s_xyz[i] = xyz[i];
+        rt_mbar_wait(&s_bar, 0);
+        group_sync();
+    }
 
     const int r = (int)bitrev_bits((unsigned)t, LOGT);
     float px[PPT], py[PPT], pz[PPT], td[PPT];
@@ -122,7 +148,7 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(int n, int m, const float *_
         } else {
             const int buf = j & 1;
             if (lane == 0) s_red[buf][warp] = make_uint2(wmax, (uint32_t)wi);
-            __syncthreads();
+            group_sync();
             uint2 b = s_red[buf][0];
 #pragma unroll
             for (int w = 1; w < NW; ++w) {
@@ -196,20 +222,27 @@ __global__ void __launch_bounds__(256) fps_generic_kernel(int n, int m, int bs, 
     }
 }
 
-template <int T, int Q, int PH, bool FUSED>
-int launch_reg2(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
-    size_t smem = (size_t)n * 3 * sizeof(float);
+template <int T, int Q, int PH, bool FUSED, int CPB>
+int launch_reg3(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
+    size_t smem = (size_t)CPB * ((n * 3 + 3) & ~3) * sizeof(float);
     // SM-exclusive mode (rt_fps_set_exclusive): every round of this kernel is a dependent latency chain, and any CTA
     // sharing the SM stretches each round 2-3x (measured on B200).  Asking for (nearly) the whole shared memory of the
     // SM keeps every other CTA off it, so the chain runs at its stand-alone speed whatever else is in flight.
     if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
     static size_t attr_bytes = 0;
     if (smem > 40 * 1024 && smem > attr_bytes) {
-        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH, FUSED, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
         attr_bytes = kFpsHogBytes;
     }
-    fps_reg_kernel<T, Q, PH, FUSED><<<b, T, smem, st>>>(n, m, xyz, temp, idx, new_xyz);
+    fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n, m, xyz, temp, idx, new_xyz);
     return rt_check_launch("fps_reg_kernel");
+}
+template <int T, int Q, int PH, bool FUSED>
+int launch_reg2(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
+    // two clouds per CTA only where it pays: SM-exclusive mode (each CTA blocks a whole SM) and 256-thread groups
+    if (g_fps_exclusive && g_fps_pair && T == 256 && b >= 2 && (size_t)2 * ((n * 3 + 3) & ~3) * sizeof(float) <= kFpsHogBytes)
+        return launch_reg3<T, Q, PH, FUSED, (T == 256 ? 2 : 1)>(b, n, m, xyz, temp, idx, new_xyz, st);
+    return launch_reg3<T, Q, PH, FUSED, 1>(b, n, m, xyz, temp, idx, new_xyz, st);
 }
 template <int T, int Q, int PH>
 int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
@@ -220,7 +253,7 @@ int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, flo
 }  // namespace
 
 // engine-internal: 1 = FPS CTAs claim a whole SM each (see launch_reg)
-void rt_fps_set_exclusive(int on) { g_fps_exclusive = on; }
+void rt_fps_set_exclusive(int on) { g_fps_exclusive = on & 1; g_fps_pair = (on >> 1) & 1; }   // bit 1: two clouds per CTA
 
 // register-resident variants; returns 1 when one was launched, 0 when the shape needs the generic kernel, < 0 / > 0 on error
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st, int *launched) {

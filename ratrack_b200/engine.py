@@ -190,6 +190,17 @@ class FusedBackbone:
         if st.value:
             raise _cabi.RatrackError(f"fused backbone: device status {st.value} (cost-volume activation outside fp16 hi/lo range)")
 
+    def stage_profile(self, on=True):
+        """Record CUDA events at the stage boundaries of the next forwards (feature-path stream)."""
+        _cabi.call("rt_engine_stage_profile", self._handle, 1 if on else 0)
+
+    def stage_times(self):
+        """[(stage name, milliseconds)] of the last forward (blocking)."""
+        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 16)()
+        n = _cabi.lib().rt_engine_stage_times(self._handle, ms, names, 16)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def launch_count(self):
         return int(_cabi.lib().rt_engine_launch_count(self._handle))
 
