@@ -27,6 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL writes its banner / debug lines to stdout by default: keep stdout for the ONE JSON line of the contract
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "frames/sec on Bx1024-pt radar pairs (Track4D.backbone forward)"
 UNIT = "frames/s"
