@@ -149,6 +149,18 @@ int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const floa
                         float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
                         long long workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 3 -- association
+ * ------------------------------------------------------------------------------------------ */
+
+/* replaces log_optimal_transport + the matching of Track4D.sinkhorn_module
+ *   (reference: src/models/utils/track4d_utils.py:405-434, src/models/track4d.py:166-180)
+ * aff (b,m,n) affinities of m previous x n current objects -> scores (b,m+1,n+1) log-couplings after `iters` log-space
+ * Sinkhorn iterations with dustbin score `alpha` [optional, may be NULL], indices0 (b,m) [optional] and indices1 (b,n):
+ * the mutually-best partner of every object, -1 where there is none (int64, as torch returns them).  m, n <= 127. */
+int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha, int iters, float *scores, long long *indices0,
+                      long long *indices1, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
