@@ -22,18 +22,23 @@ __device__ __forceinline__ float sk_warp_sum(float v) {
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// log(sum_k exp(row[k] + add[k])), k < len  (torch.logsumexp: max-shifted; -inf rows stay -inf)
-__device__ __forceinline__ float sk_lse(const float *row, const float *add, int len, int lane) {
+// log(sum_k exp(row[k] + add[k])), k < len  (torch.logsumexp: max-shifted; -inf rows stay -inf), evaluated by the LPR
+// consecutive lanes that share the row (LPR = 8 for small matrices: four rows per warp step, 3-step shuffles)
+template <int LPR>
+__device__ __forceinline__ float sk_lse(const float *row, const float *add, int len, int sub) {
     float mx = -INFINITY;
-    for (int k = lane; k < len; k += 32) mx = fmaxf(mx, row[k] + add[k]);
-    mx = sk_warp_max(mx);
+    for (int k = sub; k < len; k += LPR) mx = fmaxf(mx, row[k] + add[k]);
+#pragma unroll
+    for (int o = LPR / 2; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float shift = (mx == -INFINITY || mx == INFINITY) ? 0.0f : mx;
     float sum = 0.0f;
-    for (int k = lane; k < len; k += 32) sum += expf(row[k] + add[k] - shift);
-    sum = sk_warp_sum(sum);
+    for (int k = sub; k < len; k += LPR) sum += expf(row[k] + add[k] - shift);
+#pragma unroll
+    for (int o = LPR / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     return logf(sum) + shift;
 }
 
+template <int LPR>
 __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n, const float *__restrict__ aff_all, float alpha,
                                                                      int iters, float *__restrict__ scores_all,
                                                                      long long *__restrict__ idx0_all, long long *__restrict__ idx1_all) {
@@ -69,15 +74,22 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
         log_nu[j] = j < n ? norm : logf((float)m) + norm;
     }
     __syncthreads();
+    constexpr int RPW = 32 / LPR;                       // rows per warp step
+    const int sub = lane % LPR, rsel = lane / LPR;
+    const int rows_per_step = nw * RPW;
     for (int it = 0; it < iters; ++it) {
-        for (int i = warp; i < M; i += nw) {
-            const float l = sk_lse(Z + i * ld, v, N, lane);
-            if (lane == 0) u[i] = log_mu[i] - l;
+        for (int i0 = 0; i0 < M; i0 += rows_per_step) {   // trip count is CTA-uniform: every lane reaches the shuffles
+            const int i = i0 + warp * RPW + rsel;
+            const int ic = i < M ? i : M - 1;
+            const float l = sk_lse<LPR>(Z + ic * ld, v, N, sub);
+            if (sub == 0 && i < M) u[i] = log_mu[i] - l;
         }
         __syncthreads();
-        for (int j = warp; j < N; j += nw) {
-            const float l = sk_lse(ZT + j * ldt, u, M, lane);
-            if (lane == 0) v[j] = log_nu[j] - l;
+        for (int j0 = 0; j0 < N; j0 += rows_per_step) {
+            const int j = j0 + warp * RPW + rsel;
+            const int jc = j < N ? j : N - 1;
+            const float l = sk_lse<LPR>(ZT + jc * ldt, u, M, sub);
+            if (sub == 0 && j < N) v[j] = log_nu[j] - l;
         }
         __syncthreads();
     }
@@ -151,9 +163,13 @@ RT_API int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha,
     const size_t smem = sizeof(float) * ((size_t)M * (N + 1) + (size_t)N * (M + 1) + 4 * (size_t)(M + N)) + sizeof(int) * (size_t)(M + N);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(sinkhorn_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(sinkhorn_match_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(sinkhorn_match_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr = true;
     }
-    sinkhorn_match_kernel<<<b, SK_THREADS, smem, (cudaStream_t)stream>>>(m, n, aff, alpha, iters, scores, indices0, indices1);
+    if (M <= 96 && N <= 96)
+        sinkhorn_match_kernel<8><<<b, SK_THREADS, smem, (cudaStream_t)stream>>>(m, n, aff, alpha, iters, scores, indices0, indices1);
+    else
+        sinkhorn_match_kernel<32><<<b, SK_THREADS, smem, (cudaStream_t)stream>>>(m, n, aff, alpha, iters, scores, indices0, indices1);
     return rt_check_launch("sinkhorn_match_kernel");
 }
