@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
     const int cloud = blockIdx.x * CPB + grp;
     if (cloud >= nclouds) return;                                // whole group leaves together (named barriers are per group)
     float *s_xyz = s_xyz_all + (size_t)grp * ((n * 3 + 3) & ~3);
-    uint2(*s_red)[NW] = s_red_all[grp];
+    // exchange slots, as plain pointers computed once (indexing the 3-D array inside the round loop made the compiler
+    // re-derive the address behind a branch every round: +75 cycles per round)
+    uint2 *const red_base = &s_red_all[grp][0][0];
     uint64_t &s_bar = s_bar_all[grp];
     const float *xyz = xyz_all + (size_t)cloud * n * 3;
     float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n;
@@ -67,8 +69,13 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
     float *new_xyz = FUSED ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
     const int t = (CPB == 1) ? (int)threadIdx.x : (int)threadIdx.x % T;   // thread within the group
     const int lane = t & 31, warp = t >> 5;
+    uint2 *const red_mine = red_base + warp;
     // group-wide barrier: id 1 + grp, T threads (bar.sync with an id lets the CPB groups of a CTA run independently)
-    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(T) : "memory"); };
+    // (CPB == 1 keeps the plain CTA barrier: a barrier named through a register costs ~75 cycles more per round)
+    auto group_sync = [&]() {
+        if (CPB == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(T) : "memory");
+    };
 
     if (t == 0) {
         rt_mbar_init(&s_bar, 1);
@@ -109,10 +116,11 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
 
     int old = 0;
     if (t == 0) idx[0] = 0;
-    if (FUSED && t < 3) new_xyz[t] = s_xyz[t];
 
     for (int j = 1; j < m; ++j) {
         const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+        // fused gather: the coordinates of the point picked in the previous round are in registers right now
+        if (FUSED && t < 3) new_xyz[(j - 1) * 3 + t] = t == 0 ? x1 : (t == 1 ? y1 : z1);
         // per-thread arg-max as a tournament over the priority-ordered slots (left wins ties == "first strict
         // maximum" of the reference's scan), so the dependent chain is log2(PPT) deep instead of PPT
         float cd[PPT];
@@ -146,27 +154,147 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
         if (NW == 1) {
             win = wi;
         } else {
-            const int buf = j & 1;
-            if (lane == 0) s_red[buf][warp] = make_uint2(wmax, (uint32_t)wi);
+            const int boff = (j & 1) * NW;
+            if (lane == 0) red_mine[boff] = make_uint2(wmax, (uint32_t)wi);
             group_sync();
-            uint2 b = s_red[buf][0];
+            const uint2 *rb = red_base + boff;
+            uint2 b = rb[0];
 #pragma unroll
             for (int w = 1; w < NW; ++w) {
-                const uint2 c = s_red[buf][w];
+                const uint2 c = rb[w];
                 if (c.x > b.x) b = c;
             }
             win = (int)b.y;
         }
         old = win;
         if (t == 0) idx[j] = old;
-        if (FUSED && t < 3) new_xyz[j * 3 + t] = s_xyz[old * 3 + t];
     }
+    if (FUSED && t < 3) new_xyz[(m - 1) * 3 + t] = s_xyz[old * 3 + t];
 
     if (!FUSED) {
 #pragma unroll
         for (int s = 0; s < PPT; ++s)
             if (pk[s] >= 0) temp[pk[s]] = td[s];
     }
+}
+
+// One WARP per cloud (32 <= n <= 1024): PPL = bs*PH/32 points per lane in registers, no block barrier and no shared-memory
+// exchange at all -- a round is the distance update, a per-lane tournament, redux.sync.max + ballot + one shuffle.  Lane l
+// owns the points of priority ranks [l*PPL, (l+1)*PPL) (rank = bitrev(k mod bs) * PH + k div bs, the reference's tie order),
+// so "first strict maximum inside the lane, lowest lane among equals" is again the reference's winner.  A CTA carries
+// FW_WARPS independent clouds, one per SM sub-partition: every warp has a scheduler to itself, and the sampling of 2b
+// clouds blocks 2b/4 SMs instead of 2b (SM-exclusive mode).
+constexpr int FW_WARPS = 4;
+
+template <int PPL, bool FUSED>
+__global__ void __launch_bounds__(32 * FW_WARPS) fps_warp_kernel(int nclouds, int n, int m, int logbs, int ph_shift,
+                                                                 const float *__restrict__ xyz_all, float *__restrict__ temp_all,
+                                                                 int *__restrict__ idx_all, float *__restrict__ new_xyz_all) {
+    extern __shared__ __align__(16) float s_xyz_all[];  // FW_WARPS x roundup4(n*3) floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.x * FW_WARPS + warp;
+    if (cloud >= nclouds) return;                       // warps are independent: no CTA-wide barrier anywhere
+    float *s_xyz = s_xyz_all + (size_t)warp * ((n * 3 + 3) & ~3);
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n;
+    int *idx = idx_all + (size_t)cloud * m;
+    float *new_xyz = FUSED ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
+    for (int i = lane; i < n * 3; i += 32) s_xyz[i] = __ldg(xyz + i);
+    __syncwarp();
+
+    const int bs = 1 << logbs, ph_mask = (1 << ph_shift) - 1;
+    auto point_of = [&](int rank) {                     // priority rank -> point index (may be >= n: padding)
+        const int a = rank >> ph_shift, ph = rank & ph_mask;
+        return (int)(__brev((unsigned)a) >> (32 - logbs)) + ph * bs;
+    };
+    float px[PPL], py[PPL], pz[PPL], td[PPL];
+#pragma unroll
+    for (int s = 0; s < PPL; ++s) {
+        const int k = point_of(lane * PPL + s);
+        const int kk = (k < n) ? k : 0;
+        px[s] = s_xyz[kk * 3 + 0];
+        py[s] = s_xyz[kk * 3 + 1];
+        pz[s] = s_xyz[kk * 3 + 2];
+        td[s] = (k < n) ? (FUSED ? 1e10f : temp[k]) : -2.0f;  // padding never beats the reference's initial best of -1
+    }
+    int old = 0;
+    if (lane == 0) idx[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+        if (FUSED && lane < 3) new_xyz[(j - 1) * 3 + lane] = lane == 0 ? x1 : (lane == 1 ? y1 : z1);
+        float cd[PPL];
+        int ci[PPL];
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            const float d2 = fminf(rt_sqdist(px[s], py[s], pz[s], x1, y1, z1), td[s]);
+            td[s] = d2;
+            cd[s] = (d2 > -1.0f) ? d2 : -2.0f;   // the reference's best starts at -1: NaN / padding never win
+            ci[s] = s;
+        }
+#pragma unroll
+        for (int stride = 1; stride < PPL; stride *= 2)
+#pragma unroll
+            for (int i = 0; i + stride < PPL; i += 2 * stride)
+                if (cd[i + stride] > cd[i]) {      // left wins ties: first strict maximum in priority order
+                    cd[i] = cd[i + stride];
+                    ci[i] = ci[i + stride];
+                }
+        const bool any = cd[0] > -1.0f;
+        const uint32_t key = rt_float_ordered(any ? cd[0] : -1.0f);
+        const uint32_t wmax = rt_redux_max_u32(key);
+        const uint32_t vote = __ballot_sync(0xffffffffu, key == wmax);
+        const int src = __ffs(vote) - 1;
+        const int wslot = __shfl_sync(0xffffffffu, any ? ci[0] : -1, src);
+        old = wslot >= 0 ? point_of(src * PPL + wslot) : 0;
+        if (lane == 0) idx[j] = old;
+    }
+    if (FUSED && lane < 3) new_xyz[(m - 1) * 3 + lane] = s_xyz[old * 3 + lane];
+    if (!FUSED) {
+#pragma unroll
+        for (int s = 0; s < PPL; ++s) {
+            const int k = point_of(lane * PPL + s);
+            if (k < n) temp[k] = td[s];
+        }
+    }
+}
+
+template <int PPL, bool FUSED>
+int launch_warp2(int b, int n, int m, int logbs, int ph_shift, const float *xyz, float *temp, int *idx, float *new_xyz,
+                 cudaStream_t st) {
+    size_t smem = (size_t)FW_WARPS * ((n * 3 + 3) & ~3) * sizeof(float);
+    if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
+    static size_t attr_bytes = 0;
+    if (smem > 40 * 1024 && smem > attr_bytes) {
+        cudaFuncSetAttribute(fps_warp_kernel<PPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        attr_bytes = kFpsHogBytes;
+    }
+    fps_warp_kernel<PPL, FUSED><<<(b + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(b, n, m, logbs, ph_shift, xyz, temp,
+                                                                                            idx, new_xyz);
+    return rt_check_launch("fps_warp_kernel");
+}
+// returns 1 if launched
+template <bool FUSED>
+int launch_warp(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st, int *launched) {
+    *launched = 0;
+    if (n < 32 || n > 1024) return RT_OK;
+    const int bs = rt_ref_block_size(n);
+    int logbs = 0;
+    while ((1 << logbs) < bs) ++logbs;
+    const int ph = (n + bs - 1) / bs;                 // 1 or 2 for n <= 1024
+    if (ph > 2) return RT_OK;
+    const int ppl = bs * ph / 32;
+    *launched = 1;
+    switch (ppl) {
+        case 1: return launch_warp2<1, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        case 2: return launch_warp2<2, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        case 4: return launch_warp2<4, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        case 8: return launch_warp2<8, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        case 16: return launch_warp2<16, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        case 32: return launch_warp2<32, FUSED>(b, n, m, logbs, ph - 1, xyz, temp, idx, new_xyz, st);
+        default: break;
+    }
+    *launched = 0;
+    return RT_OK;
 }
 
 // Generic kernel: any n >= 1, temp kept in global memory (L1/L2 resident), 256 threads.
@@ -257,6 +385,19 @@ void rt_fps_set_exclusive(int on) { g_fps_exclusive = on & 1; g_fps_pair = (on >
 
 // register-resident variants; returns 1 when one was launched, 0 when the shape needs the generic kernel, < 0 / > 0 on error
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st, int *launched) {
+    // warp-per-cloud kernel (n <= 1024) only with RT_FPS_WARP=1 (A/B timing): measured on B200 it frees 3/4 of the SMs the
+    // sampling blocks but its rounds are slower (245 vs 138 us at n=1024, 204 vs 118 us at n=512: one warp issues its 32
+    // point updates far below one instruction per cycle), and the longer chain costs the step 6 %
+    static int use_warp = -1;
+    if (use_warp < 0) {
+        const char *env = getenv("RT_FPS_WARP");
+        use_warp = (env && atoi(env) == 1) ? 1 : 0;
+    }
+    if (use_warp) {
+        const int rc = new_xyz ? launch_warp<true>(b, n, m, xyz, temp, idx, new_xyz, st, launched)
+                               : launch_warp<false>(b, n, m, xyz, temp, idx, nullptr, st, launched);
+        if (rc != RT_OK || *launched) return rc;
+    }
     const int bs = rt_ref_block_size(n);
     const int ph = (n + bs - 1) / bs;
     // T threads, Q = bs / T residues per thread, PH = ceil(n / bs) passes.  T = 256 halves the per-thread work of a round
