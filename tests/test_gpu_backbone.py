@@ -82,7 +82,7 @@ def knn_sets_equivalent(pc_q, pc_s, got, want, slack=8.0):
 
 
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("name,batch,n", [("backbone_n256_b1.npz", 1, 256), ("backbone_n1024_b2.npz", 2, 1024)])
+@pytest.mark.parametrize("name,batch,n", [("backbone_n256_b1.npz", 1, 256), ("backbone_n1024_b2.npz", 2, 1024), ("backbone_n3000_b1.npz", 1, 3000)])
 def test_backbone_vs_reference_golden(fused, name, batch, n):
     net, sd = _net(fused)
     if fused and not net.fused_available():

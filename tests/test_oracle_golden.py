@@ -30,7 +30,7 @@ def _oracle_backbone(batch, n):
     return backbone_oracle.backbone(sd, t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128))
 
 
-@pytest.mark.parametrize("name,batch,n", [("backbone_n256_b1.npz", 1, 256), ("backbone_n1024_b2.npz", 2, 1024)])
+@pytest.mark.parametrize("name,batch,n", [("backbone_n256_b1.npz", 1, 256), ("backbone_n1024_b2.npz", 2, 1024), ("backbone_n3000_b1.npz", 1, 3000)])
 def test_backbone_oracle_matches_reference_golden(name, batch, n):
     g = np.load(os.path.join(GOLDEN, name))
     out, h, cls, cor, f1, f2, prop = _oracle_backbone(batch, n)
