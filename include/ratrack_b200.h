@@ -161,6 +161,12 @@ int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const floa
 int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha, int iters, float *scores, long long *indices0,
                       long long *indices1, void *stream);
 
+/* replaces the host-side sklearn call of Track4D.clustering (reference: src/models/track4d.py:36,108-126)
+ * x (b,n,d) fp32 feature rows -> labels (b,n) int32: exactly sklearn.cluster.DBSCAN(eps, min_samples).fit_predict per set
+ * (cluster numbers in order of first core point, border points to the lowest-numbered adjacent cluster, noise = -1).
+ * n <= 1024, d <= 16. */
+int rt_dbscan(int b, int n, int d, const float *x, float eps, int min_samples, int *labels, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,3 +38,32 @@ def sinkhorn_module(aff, alpha=0.9, iters=500):
     valid0 = mutual0 & (mscores0 > 0)
     valid1 = mutual1 & valid0.gather(1, indices1)
     return torch.where(valid1, indices1, torch.full_like(indices1, -1)), scores
+
+
+def dbscan_labels(x, eps=1.5, min_samples=2):
+    """numpy restatement of sklearn.cluster.DBSCAN(eps, min_samples).fit_predict as the reference uses it
+    (src/models/track4d.py:36,118): core points, components in order of their first core point, border points to the
+    first cluster that reaches them, noise -1.  Pinned against sklearn itself in tests/test_association.py."""
+    import numpy as np
+
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    adj = d2 <= float(eps) ** 2
+    core = adj.sum(1) >= min_samples
+    labels = np.full(n, -1, dtype=np.int64)
+    cur = 0
+    for i in range(n):
+        if labels[i] != -1 or not core[i]:
+            continue
+        stack = [i]
+        while stack:
+            v = stack.pop()
+            if labels[v] == -1:
+                labels[v] = cur
+                if core[v]:
+                    stack.extend(int(j) for j in np.nonzero(adj[v] & (labels == -1))[0])
+        cur += 1
+    return labels

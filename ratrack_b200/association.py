@@ -34,3 +34,22 @@ def sinkhorn_module(aff_mat_tensor, indices1=None, alpha=0.9, iters=500):
     """aff_mat (1,m,n) -> indices1 (1,n): index of the mutually-best previous object of every current object, -1 = none.
     reference: Track4D.sinkhorn_module, track4d.py:166-180 (alpha 0.9, 500 iterations)."""
     return _run(aff_mat_tensor, alpha, iters, False)[2]
+
+
+def dbscan_labels(features, eps=1.5, min_samples=2):
+    """(n,d) or (b,n,d) fp32 CUDA features -> int64 labels of the same leading shape, identical to
+    sklearn.cluster.DBSCAN(eps, min_samples).fit_predict (the reference clusters on the host: Track4D.clustering,
+    src/models/track4d.py:108-126, `self.dbscan = DBSCAN(eps=1.5, min_samples=args.min_obj_points)`, :36)."""
+    if not features.is_cuda:
+        raise _cabi.RatrackError("dbscan: needs a CUDA tensor (no CPU / sklearn fallback)")
+    x = features.detach().contiguous().float()
+    single = x.dim() == 2
+    if single:
+        x = x.unsqueeze(0)
+    b, n, d = x.shape
+    labels = torch.empty(b, n, dtype=torch.int32, device=x.device)
+    with torch.cuda.device_of(x):
+        _cabi.call("rt_dbscan", b, n, d, x.data_ptr(), float(eps), int(min_samples), labels.data_ptr(),
+                   torch.cuda.current_stream(x.device).cuda_stream)
+    labels = labels.long()
+    return labels[0] if single else labels

@@ -49,3 +49,57 @@ def test_kernel_batched_and_limits():
         association.sinkhorn_module(torch.rand(1, 200, 3, device="cuda"), None)      # > 127 objects
     with pytest.raises(_cabi.RatrackError):
         association.sinkhorn_module(torch.rand(1, 0, 3, device="cuda"), None)        # empty: the reference skips association
+
+
+def _cluster_sets():
+    """(name, X (n,8) float32, min_samples): blobs + background, a long chain (large graph diameter), duplicates, tiny sets"""
+    rng = np.random.default_rng(7)
+    sets = []
+    for n, k, ms in ((300, 12, 2), (1024, 40, 2), (700, 25, 3), (512, 10, 5), (37, 3, 1)):
+        centres = rng.uniform(-40, 40, (k, 8))
+        pts = np.concatenate([centres[rng.integers(0, k, n // 2)] + rng.normal(0, 0.45, (n // 2, 8)),
+                              rng.uniform(-45, 45, (n - n // 2, 8))])
+        sets.append((f"blobs{n}", pts[rng.permutation(n)].astype(np.float32), ms))
+    chain = np.zeros((400, 8), np.float32)
+    chain[:, 0] = np.arange(400) * 1.4                       # every link within eps = 1.5: one component of diameter 399
+    sets.append(("chain", chain[rng.permutation(400)], 2))
+    dup = rng.normal(0, 3.0, (64, 8)).astype(np.float32)
+    dup[10:20] = dup[0]
+    sets.append(("duplicates", dup, 2))
+    sets.append(("single", np.zeros((1, 8), np.float32), 2))
+    sets.append(("pair", np.array([[0] * 8, [1] + [0] * 7], np.float32), 2))
+    return sets
+
+
+@pytest.mark.parametrize("name,x,ms", _cluster_sets(), ids=[s[0] for s in _cluster_sets()])
+def test_dbscan_oracle_matches_sklearn(name, x, ms):
+    from sklearn.cluster import DBSCAN   # the reference's own clustering call (track4d.py:36,118)
+
+    want = DBSCAN(eps=1.5, min_samples=ms).fit_predict(x)
+    assert np.array_equal(association_oracle.dbscan_labels(x, 1.5, ms), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,x,ms", _cluster_sets(), ids=[s[0] for s in _cluster_sets()])
+def test_dbscan_kernel_matches_sklearn(name, x, ms):
+    from sklearn.cluster import DBSCAN
+
+    from ratrack_b200 import association
+
+    want = DBSCAN(eps=1.5, min_samples=ms).fit_predict(x)
+    got = association.dbscan_labels(torch.from_numpy(x).cuda(), 1.5, ms)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+def test_dbscan_kernel_batched_and_limits():
+    from ratrack_b200 import _cabi, association
+
+    sets = [s for s in _cluster_sets() if s[0] == "blobs300"]
+    x = torch.from_numpy(np.stack([sets[0][1], sets[0][1][::-1].copy()])).cuda()
+    lab = association.dbscan_labels(x, 1.5, 2).cpu().numpy()
+    ref = [association_oracle.dbscan_labels(x[i].cpu().numpy(), 1.5, 2) for i in range(2)]
+    assert np.array_equal(lab[0], ref[0]) and np.array_equal(lab[1], ref[1])
+    with pytest.raises(_cabi.RatrackError):
+        association.dbscan_labels(torch.zeros(2000, 8, device="cuda"))
