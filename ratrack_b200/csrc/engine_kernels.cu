@@ -3,6 +3,8 @@
 // cost-volume MLP has its own tensor-core kernel (costvol_tc.cu).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "engine_kernels.cuh"
 
 namespace {
@@ -717,6 +719,72 @@ __global__ void __launch_bounds__(384) gru_chain_kernel(int bsz, const float *__
     }
 }
 
+// Cluster variant of the chain: 4 CTAs (one thread-block cluster) per batch element.  CTA r owns hidden units
+// [32r, 32r+32) = 96 of the 384 gate rows, 4 threads per row (a quarter of k each, all 32 weight loads in flight at once);
+// the 32 new hidden values of a CTA are written into the next-layer input buffer of ALL four CTAs through distributed
+// shared memory, one cluster barrier per layer.  The chain is bound by streaming W_ih from L2 (196 KB per layer): four SMs
+// pull it in parallel, and every load of a layer is in flight together -- 43 -> ~10 us for the five layers.
+__device__ __forceinline__ uint32_t gru_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gru_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void gru_st_remote(float *local_addr, uint32_t rank, float v) {
+    uint32_t la = rt_smem_u32(local_addr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(384) gru_chain_cluster_kernel(
+    int bsz, const float *__restrict__ x, const float *__restrict__ h_in, const float *__restrict__ wih_t,
+    const float *__restrict__ bih, const float *__restrict__ gh, float *__restrict__ h_out, size_t h_stride) {
+    __shared__ float s_x[2][128], s_part[4][96];
+    const int t = threadIdx.x;
+    const uint32_t rank = gru_cluster_rank();
+    const int b = blockIdx.x / 4;
+    const int rl = t % 96, kq = t / 96;                     // local row (gate-major: 32 rows per gate), k quarter
+    const int row = (rl / 32) * 128 + 32 * (int)rank + (rl % 32);
+    if (t < 128) s_x[0][t] = x[(size_t)b * 128 + t];
+    gru_cluster_sync();                                     // every CTA's buffers exist before anybody writes remotely
+    int cur = 0;
+    for (int l = 0; l < 5; ++l) {
+        const float *w = wih_t + (size_t)l * 128 * 384 + (size_t)(kq * 32) * 384 + row;
+        float wv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wv[i] = __ldg(w + (size_t)i * 384);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            a0 = fmaf(wv[i + 0], s_x[cur][kq * 32 + i + 0], a0);
+            a1 = fmaf(wv[i + 1], s_x[cur][kq * 32 + i + 1], a1);
+            a2 = fmaf(wv[i + 2], s_x[cur][kq * 32 + i + 2], a2);
+            a3 = fmaf(wv[i + 3], s_x[cur][kq * 32 + i + 3], a3);
+        }
+        s_part[kq][rl] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (t < 32) {
+            const int u = 32 * (int)rank + t;               // hidden unit
+            float gi[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+                gi[g] = ((s_part[0][g * 32 + t] + s_part[1][g * 32 + t]) + (s_part[2][g * 32 + t] + s_part[3][g * 32 + t])) +
+                        __ldg(bih + l * 384 + g * 128 + u);
+            const float *g_h = gh + ((size_t)l * bsz + b) * 384;
+            const float r = 1.0f / (1.0f + expf(-(gi[0] + g_h[u])));
+            const float z = 1.0f / (1.0f + expf(-(gi[1] + g_h[128 + u])));
+            const float nn = tanhf(gi[2] + r * g_h[256 + u]);
+            const float h = (1.0f - z) * nn + z * h_in[(size_t)l * h_stride + (size_t)b * 128 + u];
+            h_out[(size_t)l * h_stride + (size_t)b * 128 + u] = h;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; ++c) gru_st_remote(&s_x[cur ^ 1][u], c, h);   // next layer's input, in all four CTAs
+        }
+        gru_cluster_sync();                                 // remote stores visible; s_part / s_x[cur] free again
+        cur ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(256) cls_tail_kernel(long long rows, const float *__restrict__ h3, const float *__restrict__ w4,
                                                        const float *__restrict__ lin_w, const float *__restrict__ lin_b,
                                                        float *__restrict__ cls) {
@@ -926,6 +994,15 @@ int rt_launch_gru_hh(int b, const float *h_in, const float *whh, const float *bh
 int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, const float *bih, const float *gh, float *h_out,
                   size_t h_stride, cudaStream_t st) {
     if (b <= 0) return RT_OK;
+    static int use_cluster = -1;
+    if (use_cluster < 0) {
+        const char *env = getenv("RT_GRU_CLUSTER");
+        use_cluster = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    if (use_cluster) {
+        gru_chain_cluster_kernel<<<4 * b, 384, 0, st>>>(b, x, h_in, wih, bih, gh, h_out, h_stride);
+        return rt_check_launch("gru_chain_cluster_kernel");
+    }
     gru_chain_kernel<<<b, 384, 0, st>>>(b, x, h_in, wih, bih, gh, h_out, h_stride);
     return rt_check_launch("gru_chain_kernel");
 }
