@@ -119,6 +119,13 @@ __device__ __forceinline__ void rt_ldg256(const float *p, float4 &lo, float4 &hi
                  : "l"(p));
 }
 
+// 256-bit global store (SASS STG.E.ENL2.256), the store-side counterpart of rt_ldg256; `p` must be 32-byte aligned
+__device__ __forceinline__ void rt_stg256(float *p, float4 lo, float4 hi) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x),
+                 "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
+
 // packed fp32 pairs (SASS FFMA2 / FMUL2 / FADD2): every half is an ordinary round-to-nearest IEEE operation, so results are
 // bit-identical to the scalar forms; one issue slot instead of two
 __device__ __forceinline__ float2 rt_ffma2(float2 a, float2 b, float2 c) {

@@ -142,7 +142,7 @@ __device__ __forceinline__ void mt_gather_issue(const RtMlpTc &a, long long tile
 }
 
 template <int LOAD_MODE>
-__global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
+__global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_a, bar_d, bar_w;
     __shared__ uint32_t tmem_slot;
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
         const int row_in_tile = 32 * q + lane;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         uint32_t d_phase = 0;
+        const bool out_al32 = (reinterpret_cast<uintptr_t>(a.out) & 31) == 0;
         __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         MtGatherRow pre;
         if (LOAD_MODE == RT_MLP_LOAD_GATHER && (long long)blockIdx.x < ntiles) mt_gather_issue(a, blockIdx.x, row_in_tile, pre);
@@ -371,7 +372,11 @@ __global__ void __launch_bounds__(MT_THREADS) mlp_tc_kernel(RtMlpTc a) {
                     } else if (a.out_mode == RT_MLP_OUT_ROWS) {
                         if (valid) {
                             float *o = a.out + row * a.ldo + a.ooff + c0;
-                            if (c0 + 16 <= a.n_out && (a.ldo & 3) == 0 && (a.ooff & 3) == 0) {
+                            if (c0 + 16 <= a.n_out && (a.ldo & 7) == 0 && (a.ooff & 7) == 0 && out_al32) {
+                                // thread-per-row stores pay one L1 wavefront per lane per instruction: 256-bit stores
+                                rt_stg256(o, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+                                rt_stg256(o + 8, make_float4(v[8], v[9], v[10], v[11]), make_float4(v[12], v[13], v[14], v[15]));
+                            } else if (c0 + 16 <= a.n_out && (a.ldo & 3) == 0 && (a.ooff & 3) == 0) {
 #pragma unroll
                                 for (int g = 0; g < 4; ++g)
                                     reinterpret_cast<float4 *>(o)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
