@@ -1,0 +1,146 @@
+"""`Track4D` with the reference's constructor, forward signature, return tuple and state_dict keys
+(reference: src/models/track4d.py:13-245), every device-side step served by this package:
+
+    backbone            -> the fused engine / modular path (model_utils.Track4DBackbone)
+    clustering          -> rt_dbscan on the device (the reference: device->host copy + scikit-learn, :108-126)
+    affinity_module     -> ONE batched evaluation of the Affinity MLP over all m x n object pairs, object embeddings by
+                           segment reductions (the reference: a Python double loop, ~15 torch launches per pair, :182-223)
+    sinkhorn_module     -> rt_sinkhorn_match (500 log-space iterations + mutual matching in one kernel, :166-180)
+
+What stays on the host is what the reference's API makes host-side by construction: the dicts / lists of per-object
+tensors it returns and the track-id bookkeeping (one small device->host read of labels and matches per frame).
+Batch 1 per call, like the reference (`squeeze(0)` at :56).  SURVEY.md section 8(f) rows 1-2.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import association
+from .model_utils import Track4DBackbone
+
+
+class Affinity(nn.Module):
+    """MLP emb -> 4 emb -> 2 emb -> emb/2 -> emb/4 -> 1 + sigmoid on the DIFFERENCE of two object embeddings.  reference :226-245"""
+
+    def __init__(self, emb_dims=137):
+        super().__init__()
+        self.emb_dims = emb_dims
+        self.affinity = nn.Sequential(nn.Linear(emb_dims, emb_dims * 4), nn.ReLU(),
+                                      nn.Linear(emb_dims * 4, emb_dims * 2), nn.ReLU(),
+                                      nn.Linear(emb_dims * 2, emb_dims // 2), nn.ReLU(),
+                                      nn.Linear(emb_dims // 2, emb_dims // 4), nn.ReLU(),
+                                      nn.Linear(emb_dims // 4, 1), nn.Sigmoid())
+
+    def forward(self, *input):
+        return self.affinity((input[0] - input[1])[0])
+
+
+def object_embeddings(points, seg, nseg):
+    """points (139, P) feature columns of all objects side by side, seg (P,) object index of every column ->
+    (nseg, 141) embeddings [centre(3), position variance(3), max feature(128), mean flow(3), mean rrv(2), rrv variance(2)]
+    exactly as the reference assembles them per object (track4d.py:202-216; variances are population variances,
+    computed two-pass like torch.var)."""
+    cnt = torch.zeros(nseg, device=points.device).index_add_(0, seg, torch.ones_like(seg, dtype=torch.float32))
+
+    def seg_mean(x):                       # (C,P) -> (nseg,C)
+        return torch.zeros(nseg, x.shape[0], device=x.device).index_add_(0, seg, x.t()) / cnt[:, None]
+
+    def seg_var(x, mean):
+        d = x.t() - mean[seg]
+        return torch.zeros(nseg, x.shape[0], device=x.device).index_add_(0, seg, d * d) / cnt[:, None]
+
+    pos, flow, rrv, feat = points[3:6], points[6:9], points[9:11], points[11:139]
+    pos_m, rrv_m = seg_mean(pos), seg_mean(rrv)
+    fmax = torch.full((nseg, feat.shape[0]), float("-inf"), device=points.device)
+    fmax = fmax.scatter_reduce(0, seg[:, None].expand(-1, feat.shape[0]), feat.t(), reduce="amax", include_self=True)
+    return torch.cat([pos_m, seg_var(pos, pos_m), fmax, seg_mean(flow), rrv_m, seg_var(rrv, rrv_m)], dim=1)
+
+
+class Track4D(Track4DBackbone):
+    """reference: src/models/track4d.py:13-223.  `args` needs npoints (FPS samples) and min_obj_points (DBSCAN min_samples)."""
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.min_samples = int(getattr(args, "min_obj_points", 2))
+        self.eps = 1.5                                     # reference :36
+        self.affinity = Affinity(141)
+        self.register_parameter("bin_score", nn.Parameter(torch.tensor(1.0)))
+        self.max_id = 0
+
+    # -- reference-shaped methods ----------------------------------------------------------------------------------
+    def forward(self, pc1, pc2, feature1, feature2, h, objects_prev):
+        out = self.backbone(pc1, pc2, feature1, feature2, h)
+        return self.track(pc1, feature1, out, objects_prev)
+
+    def track(self, pc1, feature1, backbone_out, objects_prev):
+        """Everything of `forward` after the backbone (reference :52-65), given the backbone's 7-tuple."""
+        output, h, cls, _, _, _, prop_features = backbone_out
+        pc1_warp = pc1 + output
+        pc1_features_warp = torch.cat((pc1_warp, pc1, output, feature1, prop_features), dim=1)
+        mov_mask = (cls > 0.5).squeeze(0)
+        objects_curr = self.clustering(pc1_features_warp[:, :, mov_mask])
+        objects = dict()
+        aff_list, aff_mat, indices1, confs = self.association_module(objects, objects_curr, objects_prev)
+        return h, pc1_warp, cls, aff_list, aff_mat, indices1, confs, objects, dict(), objects_curr
+
+    def clustering(self, pc1_features):
+        """(1,139,Nm) features of the moving points -> list of (1,139,n_k) tensors, one per DBSCAN cluster, in the order
+        the clusters first appear along the point index (the reference's defaultdict insertion order, :120-126)."""
+        if pc1_features.shape[2] == 0:
+            return []
+        f = torch.cat((pc1_features[0, 3:9, :], pc1_features[0, 10:12, :]), dim=0).t().contiguous()
+        labels = association.dbscan_labels(f.detach(), self.eps, self.min_samples).cpu().numpy()
+        order, seen = [], set()
+        for lab in labels.tolist():
+            if lab != -1 and lab not in seen:
+                seen.add(lab)
+                order.append(lab)
+        dev = pc1_features.device
+        return [pc1_features[:, :, torch.from_numpy(np.nonzero(labels == lab)[0]).to(dev)] for lab in order]
+
+    def affinity_module(self, objects_curr, objects_prev):
+        """-> (aff_list (m*n,), aff_mat (1,m,n), m, n); empty inputs give ([], (1,0)) as the reference does (:218-222)."""
+        m, n = len(objects_prev), len(objects_curr)
+        dev = next(self.parameters()).device
+        if m == 0 or n == 0:
+            return [], torch.zeros(1, 0, device=dev), m, n
+
+        def embed(objs):
+            pts = torch.cat([o[0] for o in objs], dim=1)
+            seg = torch.cat([torch.full((o.shape[2],), i, dtype=torch.long, device=pts.device) for i, o in enumerate(objs)])
+            return object_embeddings(pts, seg, len(objs))
+
+        e_curr, e_prev = embed(objects_curr), embed(list(objects_prev.values()))
+        diff = (e_curr[None, :, :] - e_prev[:, None, :]).reshape(m * n, -1)      # row-major (prev, curr), as the reference loops
+        aff_list = self.affinity.affinity(diff).reshape(m * n)
+        return aff_list, aff_list.reshape(m, n).unsqueeze(0), m, n
+
+    def sinkhorn_module(self, aff_mat_tensor, indices1=None):
+        return association.sinkhorn_module(aff_mat_tensor, indices1)
+
+    def association_module(self, objects, objects_curr, objects_prev):
+        """reference :135-164: matched objects keep the previous id, the others get fresh ids from self.max_id."""
+        aff_list, aff_mat, m, n = self.affinity_module(objects_curr, objects_prev)
+        indices1 = None
+        confs = []
+        if m > 0 and n > 0:
+            indices1 = self.sinkhorn_module(aff_mat, indices1)
+            idx = indices1[0]
+            conf_all = aff_mat[0, idx.clamp(min=0), torch.arange(n, device=aff_mat.device)]
+            idx_h, conf_h = idx.cpu().tolist(), conf_all.detach().cpu().tolist()      # the frame's one device->host read
+            # (an unmatched object has index -1: the reference then reads aff_mat[0, -1, i]; only the sign of the test matters)
+            prev_keys = list(objects_prev.keys())
+            for i in range(n):
+                if idx_h[i] == -1 or idx_h[i] >= m or conf_h[i] < 0.01:
+                    objects[self.max_id] = objects_curr[i]
+                    self.max_id += 1
+                    confs.append(0)
+                else:
+                    objects[prev_keys[idx_h[i]]] = objects_curr[i]
+                    confs.append(conf_all[i])
+        else:
+            for obj in objects_curr:
+                objects[self.max_id] = obj
+                self.max_id += 1
+                confs.append(0)
+        return aff_list, aff_mat, indices1, confs
