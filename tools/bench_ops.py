@@ -59,13 +59,15 @@ def main():
 
     rows = []
 
-    def report(name, kernel, bytes_, fn_ours, fn_ref, note=""):
+    def report(name, kernel, bytes_, fn_ours, fn_ref, note="", evals=None):
         t_o = timed(fn_ours)
         t_r = timed(fn_ref) if (ref is not None and fn_ref is not None and not ONCE) else None
         gbs = bytes_ / (t_o * 1e-3) / 1e9
         rows.append({"op": name, "kernel": kernel, "algorithmic_bytes": bytes_, "ours_us": t_o * 1e3,
                      "ref_kernel_us": None if t_r is None else t_r * 1e3, "achieved_gbs": gbs,
                      "frac_of_hbm_peak": gbs / peaks(), "speedup_vs_ref_kernel": None if t_r is None else t_r / t_o,
+                     # search ops are bound by point-pair distance evaluations, not HBM: algorithmic pair evaluations / time
+                     "pair_distance_evals": evals, "gevals_per_s": None if evals is None else evals / (t_o * 1e-3) / 1e9,
                      "note": note})
 
     # ---- FPS (SA1: N -> S; SA2/3: S -> S) ----------------------------------------------------------------
@@ -78,7 +80,7 @@ def main():
             temp.fill_(1e10)
             mod.furthest_point_sampling_wrapper(B, n_in, S, x, temp, idx)
         report(f"furthest_point_sample n={n_in} m={S}", "fps_reg_kernel", B * (12 * n_in + 4 * S),
-               lambda: f(ours), lambda: f(ref), "latency-bound: m-1 dependent rounds; includes the temp fill")
+               lambda: f(ours), lambda: f(ref), "latency-bound: m-1 dependent rounds; includes the temp fill", evals=B * (S - 1) * n_in)
     fps_idx = idx.clone()
     new_xyz = torch.gather(xyz[:, :S], 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()   # (B,S,3)
 
@@ -89,7 +91,7 @@ def main():
         idx = torch.zeros(B, S, ns, dtype=torch.int32, device=dev)
         report(f"ball_query n={n_in} r={r} ns={ns}", "ball_query_kernel", B * (12 * n_in + 12 * S + 4 * S * ns),
                lambda: ours.ball_query_wrapper(B, n_in, S, r, ns, q, x, idx),
-               lambda: ref.ball_query_wrapper(B, n_in, S, r, ns, q, x, idx))
+               lambda: ref.ball_query_wrapper(B, n_in, S, r, ns, q, x, idx), evals=B * S * n_in)
     bq_idx = idx.clone()   # (B,S,32) over S points
 
     # ---- group_points ----------------------------------------------------------------------------------
@@ -126,7 +128,7 @@ def main():
         ni = torch.empty(B, n_u, 3, dtype=torch.int32, device=dev)
         report(f"three_nn n={n_u} m={m_k}", "three_nn_kernel", B * (12 * n_u + 12 * m_k + 24 * n_u),
                lambda: ours.three_nn_wrapper(B, n_u, m_k, unk, kn, d2, ni),
-               lambda: ref.three_nn_wrapper(B, n_u, m_k, unk, kn, d2, ni))
+               lambda: ref.three_nn_wrapper(B, n_u, m_k, unk, kn, d2, ni), evals=B * n_u * m_k)
     w = torch.softmax(rnd(B, N, 3), -1).contiguous()
     for c, n_u in ((64, S), (128, N)):
         pts = rnd(B, c, S)
@@ -150,7 +152,7 @@ def main():
     d2 = torch.empty(B, N, 16, device=dev)
     ki = torch.empty(B, N, 16, dtype=torch.int32, device=dev)
     report(f"knn k=16 n={N} m={N}", "knn_kernel", B * (12 * N + 12 * N + 8 * N * 16),
-           lambda: ours.knn_wrapper(B, N, N, 16, xyz, xyz, d2, ki), lambda: ref.knn_wrapper(B, N, N, 16, xyz, xyz, d2, ki))
+           lambda: ours.knn_wrapper(B, N, N, 16, xyz, xyz, d2, ki), lambda: ref.knn_wrapper(B, N, N, 16, xyz, xyz, d2, ki), evals=B * N * N)
     st = torch.cuda.current_stream().cuda_stream
 
     def torch_knn():
@@ -160,17 +162,18 @@ def main():
         torch.topk(torch.clamp_min(dist, 0.0), 16, dim=-1, largest=False, sorted=False)
     report(f"knn_point (cost volume) k=16 n={N} m={N}", "knn_expanded_warp_kernel", B * (12 * N + 12 * N + 4 * N * 16),
            lambda: _cabi.call("rt_knn_expanded", B, N, N, 16, xyz.data_ptr(), xyz.data_ptr(), ki.data_ptr(), st),
-           None if ONCE else torch_knn, "reference column = torch matmul + topk (model_utils.py:85-99), materialises (B,N,N)")
+           None if ONCE else torch_knn, "reference column = torch matmul + topk (model_utils.py:85-99), materialises (B,N,N)", evals=B * N * N)
 
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     if not ONCE:
         json.dump({"geometry": {"clouds": B, "N": N, "S": S}, "hbm_peak_gbs": peaks(), "l2": "flushed before every launch",
                    "reps": REPS, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "ops_roofline.json"), "w"), indent=1)
-    print(f"{'op':52s} {'ours us':>9s} {'ref us':>9s} {'x':>6s} {'GB/s':>8s} {'frac':>6s}")
+    print(f"{'op':52s} {'ours us':>9s} {'ref us':>9s} {'x':>6s} {'GB/s':>8s} {'frac':>6s} {'Gevals/s':>9s}")
     for r in rows:
         ru = f"{r['ref_kernel_us']:9.1f}" if r["ref_kernel_us"] else "        -"
         sp = f"{r['speedup_vs_ref_kernel']:6.1f}" if r["speedup_vs_ref_kernel"] else "     -"
-        print(f"{r['op']:52s} {r['ours_us']:9.1f} {ru} {sp} {r['achieved_gbs']:8.1f} {r['frac_of_hbm_peak']:6.3f}")
+        ge = f"{r['gevals_per_s']:9.1f}" if r["gevals_per_s"] else "        -"
+        print(f"{r['op']:52s} {r['ours_us']:9.1f} {ru} {sp} {r['achieved_gbs']:8.1f} {r['frac_of_hbm_peak']:6.3f} {ge}")
 
 
 if __name__ == "__main__":
