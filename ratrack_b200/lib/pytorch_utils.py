@@ -9,7 +9,34 @@ The fused engine reads these parameters directly and folds BN in eval mode.
 """
 from typing import List
 
+import torch
 import torch.nn as nn
+
+
+class PointwiseConv2d(nn.Conv2d):
+    """nn.Conv2d whose 1x1 / stride-1 case is evaluated as what it is: ONE GEMM over the channel axis, rows = all
+    B*H*W positions (same parameters, same state_dict keys, same fp32 result up to summation order).  With TF32 off --
+    which parity with the fp32 reference needs -- cuDNN serves 1x1 convolutions with its generic SIMT convolution
+    engines; torch.profiler on the training step showed 53 % of the device time in those forward / wgrad / dgrad
+    kernels.  Here the activation is kept channels-innermost (torch.channels_last; the cost volume's concatenated
+    tensor already is), so forward, dX and dW are each a single large cuBLAS sgemm and BatchNorm / ReLU / max-pool run
+    their NHWC kernels on the result without a layout copy."""
+
+    def forward(self, x):
+        if (self.kernel_size != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0) or self.groups != 1 or
+                self.dilation != (1, 1) or x.dim() != 4):
+            return super().forward(x)
+        dims = [0, 2, 3]
+        if x.stride(1) == 1:
+            dims.sort(key=lambda d: -x.stride(d))                       # memory order of the non-channel axes
+        rows = x.permute(*dims, 1)
+        if not rows.is_contiguous():                                   # e.g. NCHW from a gather kernel: one copy, then
+            x = x.contiguous(memory_format=torch.channels_last)        # every later layer stays channels-innermost
+            dims = [0, 2, 3]
+            rows = x.permute(0, 2, 3, 1)
+        y = nn.functional.linear(rows, self.weight.view(self.out_channels, self.in_channels), self.bias)
+        src = dims + [1]                                               # y's axes in terms of (B,C,H,W) axes
+        return y.permute(*[src.index(d) for d in range(4)])            # (B,Cout,H,W) view, channels still innermost
 
 
 class BatchNorm2d(nn.Sequential):
@@ -26,7 +53,7 @@ class Conv2d(nn.Sequential):
                  bias: bool = True, preact: bool = False, name: str = "", instance_norm: bool = False):
         super().__init__()
         bias = bias and (not bn)
-        conv = nn.Conv2d(in_size, out_size, kernel_size=kernel_size, stride=stride, padding=padding, bias=bias)
+        conv = PointwiseConv2d(in_size, out_size, kernel_size=kernel_size, stride=stride, padding=padding, bias=bias)
         init(conv.weight)
         if bias:
             nn.init.constant_(conv.bias, 0)

@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .lib.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+from .lib.pytorch_utils import PointwiseConv2d
 
 
 def square_distance(src, dst):
@@ -68,7 +69,7 @@ class WeightNet(nn.Module):
         self.mlp_bns = nn.ModuleList()
         widths = [in_channel] + list(hidden_unit or []) + [out_channel]
         for cin, cout in zip(widths[:-1], widths[1:]):
-            self.mlp_convs.append(nn.Conv2d(cin, cout, 1))
+            self.mlp_convs.append(PointwiseConv2d(cin, cout, 1))
             self.mlp_bns.append(nn.BatchNorm2d(cout))
 
     def forward(self, localized_xyz):
@@ -95,7 +96,7 @@ class FeatureCorrelator(nn.Module):
             self.mlp_bns2 = nn.ModuleList()
         last_channel = in_channel
         for out_channel in mlp:
-            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            self.mlp_convs.append(PointwiseConv2d(last_channel, out_channel, 1))
             if bn:
                 self.mlp_bns.append(nn.BatchNorm2d(out_channel))
             last_channel = out_channel
@@ -142,10 +143,10 @@ class FlowPredictor(nn.Module):
         self.sf_mlp = nn.ModuleList()
         last_channel = in_channel
         for out_channel in mlp:
-            self.sf_mlp.append(nn.Sequential(nn.Conv2d(last_channel, out_channel, 1, bias=False),
+            self.sf_mlp.append(nn.Sequential(PointwiseConv2d(last_channel, out_channel, 1, bias=False),
                                              nn.BatchNorm2d(out_channel), nn.ReLU(inplace=False)))
             last_channel = out_channel
-        self.conv2 = nn.Conv2d(mlp[-1], 3, 1, bias=False)
+        self.conv2 = PointwiseConv2d(mlp[-1], 3, 1, bias=False)
 
     def forward(self, feat):
         feat = feat.unsqueeze(3)
@@ -162,10 +163,10 @@ class ClsPredictor(nn.Module):
         self.sf_mlp = nn.ModuleList()
         last_channel = in_channel
         for out_channel in mlp:
-            self.sf_mlp.append(nn.Sequential(nn.Conv2d(last_channel, out_channel, 1, bias=False),
+            self.sf_mlp.append(nn.Sequential(PointwiseConv2d(last_channel, out_channel, 1, bias=False),
                                              nn.BatchNorm2d(out_channel), nn.ReLU(inplace=False)))
             last_channel = out_channel
-        self.conv2 = nn.Conv2d(mlp[-1], 3, 1, bias=False)
+        self.conv2 = PointwiseConv2d(mlp[-1], 3, 1, bias=False)
         self.linear = nn.Linear(3, 1)
         self.sig = nn.Sigmoid()
 
