@@ -39,7 +39,7 @@ class _PointnetSAModuleBase(nn.Module):
                 x = F.avg_pool2d(x, kernel_size=[1, x.size(3)])
             else:
                 raise NotImplementedError
-            pooled.append(x.squeeze(-1))
+            pooled.append(x.squeeze(-1).contiguous())   # leave the channels-innermost layout of the conv stack
         return new_xyz, torch.cat(pooled, dim=1)
 
 
@@ -85,4 +85,4 @@ class PointnetFPModule(nn.Module):
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
         x = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
-        return self.mlp(x.unsqueeze(-1)).squeeze(-1)
+        return self.mlp(x.unsqueeze(-1)).squeeze(-1).contiguous()   # (B,C,n) as the reference's ops expect it

@@ -132,7 +132,7 @@ class FeatureCorrelator(nn.Module):
         direction_xyz = index_points(pc1, knn_idx) - pc1.reshape(B, N1, 1, C)
         weights = self.weightnet2(direction_xyz.permute(0, 3, 2, 1))
         x = index_points(x.permute(0, 2, 1), knn_idx)
-        return torch.sum(weights * x.permute(0, 3, 2, 1), dim=2)
+        return torch.sum(weights * x.permute(0, 3, 2, 1), dim=2).contiguous()
 
 
 class FlowPredictor(nn.Module):
@@ -152,7 +152,7 @@ class FlowPredictor(nn.Module):
         feat = feat.unsqueeze(3)
         for block in self.sf_mlp:
             feat = block(feat)
-        return self.conv2(feat).squeeze(3)
+        return self.conv2(feat).squeeze(3).contiguous()
 
 
 class ClsPredictor(nn.Module):
