@@ -385,8 +385,11 @@ def ref_gpu_rate(net, t, h0, steps, B):
     ref = ref_gpu.load()
     if ref is None:
         return {"unavailable": "oracle/_ref/pointnet2_cuda.so not built"}
+    from ratrack_b200.lib.pytorch_utils import PointwiseConv2d
+
     ours, fused = U.pointnet2, net.use_fused
     U.pointnet2, net.use_fused = ref, False
+    PointwiseConv2d.use_gemm = False      # 1x1 convolutions through nn.Conv2d / cuDNN, as the reference's modules run them
     try:
         with torch.no_grad():
             for _ in range(3):
@@ -402,6 +405,7 @@ def ref_gpu_rate(net, t, h0, steps, B):
                 "what": "reference CUDA kernels (oracle/_ref) + torch fp32 modules, same B200, same batch"}
     finally:
         U.pointnet2, net.use_fused = ours, fused
+        PointwiseConv2d.use_gemm = True
 
 
 if __name__ == "__main__":

@@ -22,8 +22,10 @@ class PointwiseConv2d(nn.Conv2d):
     tensor already is), so forward, dX and dW are each a single large cuBLAS sgemm and BatchNorm / ReLU / max-pool run
     their NHWC kernels on the result without a layout copy."""
 
+    use_gemm = True   # class-wide switch: False = plain nn.Conv2d (cuDNN), what the reference's own modules do
+
     def forward(self, x):
-        if (self.kernel_size != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0) or self.groups != 1 or
+        if (not PointwiseConv2d.use_gemm or self.kernel_size != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0) or self.groups != 1 or
                 self.dilation != (1, 1) or x.dim() != 4):
             return super().forward(x)
         dims = [0, 2, 3]
