@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
         log_nu[j] = j < n ? norm : logf((float)m) + norm;
     }
     __syncthreads();
+    // (a single-warp variant for <= 32 objects -- rows in registers, u / v by shuffles, no CTA barrier -- was measured slower:
+    //  1.7 vs 0.68 ms at 20 x 20; the serial exp/log chain of one warp costs more than the two barriers it removes)
+    {
     constexpr int RPW = 32 / LPR;                       // rows per warp step
     const int sub = lane % LPR, rsel = lane / LPR;
     const int rows_per_step = nw * RPW;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
             if (sub == 0 && j < N) v[j] = log_nu[j] - l;
         }
         __syncthreads();
+    }
     }
     // Z + u + v - norm
     for (int e = t; e < M * N; e += SK_THREADS) {
