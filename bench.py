@@ -27,8 +27,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# NCCL writes its banner / debug lines to stdout by default: keep stdout for the ONE JSON line of the contract
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def init_dist(dev):
+    """NCCL process group for the N-GPU launch.  NCCL prints its version banner (and NCCL_DEBUG output) on the process's
+    stdout while the communicator is created; stdout is reserved for the ONE JSON line of the contract, so file
+    descriptor 1 points at stderr until the first collective has run."""
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        import torch
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 METRIC = "frames/sec on Bx1024-pt radar pairs (Track4D.backbone forward)"
 UNIT = "frames/s"
@@ -159,7 +177,7 @@ def run_train(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_dist(dev)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     B = a.batch if a.batch != 32 else 256
@@ -251,7 +269,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_dist(dev)
     torch.backends.cudnn.allow_tf32 = False          # fp32 math everywhere (SURVEY.md hard part 3)
     torch.backends.cuda.matmul.allow_tf32 = False
 
