@@ -123,7 +123,7 @@ __device__ __forceinline__ int ct_group_at(int i) { return (i >> 1) + 4 * (i & 1
 // F16 x F16 -> F32, A and B K-major, M = 128, N = 256
 constexpr uint32_t CT_IDESC = (1u << 4) | ((uint32_t)(CT_C >> 3) << 17) | ((uint32_t)(CT_ROWS >> 4) << 24);
 
-__device__ __forceinline__ float leaky01(float v) { return fmaxf(v, 0.1f * v); }   // LeakyReLU(0.1): two instructions, no select
+// LeakyReLU(0.1) on a packed pair: max(v, 0.1 v) -- two instructions per pair, no select
 __device__ __forceinline__ float2 leaky01x2(float2 v) {
     const float2 m = rt_fmul2(v, make_float2(0.1f, 0.1f));
     return make_float2(fmaxf(v.x, m.x), fmaxf(v.y, m.y));

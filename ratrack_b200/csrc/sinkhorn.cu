@@ -12,16 +12,6 @@ namespace {
 constexpr int SK_THREADS = 256;
 constexpr int SK_MAX = 128;   // (m+1), (n+1) <= SK_MAX
 
-__device__ __forceinline__ float sk_warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float sk_warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 // log(sum_k exp(row[k] + add[k])), k < len  (torch.logsumexp: max-shifted; -inf rows stay -inf), evaluated by the LPR
 // consecutive lanes that share the row (LPR = 8 for small matrices: four rows per warp step, 3-step shuffles)
 template <int LPR>
