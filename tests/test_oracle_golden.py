@@ -168,3 +168,22 @@ print("OK")
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name,batch,n", [("train_step_n256_b1.npz", 1, 256), ("train_step_n512_b2.npz", 2, 512)])
+def test_backbone_oracle_train_mode_matches_reference_train_forward(name, batch, n):
+    """training=True (BatchNorm on batch statistics) against the forward outputs of the reference's own training step
+    (tests/golden/train_step_*.npz, oracle/gen_golden_train.py)."""
+    from ratrack_b200.model_utils import Track4DBackbone
+
+    class A:
+        npoints = 512
+
+    g = np.load(os.path.join(GOLDEN, name))
+    sd = synthetic.make_state_dict(Track4DBackbone(A()), seed=1234)
+    d = synthetic.make_batch(batch, n, seed=1234)
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    out = backbone_oracle.backbone(sd, t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128), training=True,
+                                   knn_override=(torch.from_numpy(g["knn12"]).long(), torch.from_numpy(g["knn11"]).long()))
+    assert np.abs(out[0].numpy() - g["flow"]).max() <= 2e-5 * max(1.0, np.abs(g["flow"]).max())
+    assert np.abs(out[2].numpy() - g["cls"]).max() <= 2e-5
