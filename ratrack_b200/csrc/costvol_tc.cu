@@ -25,7 +25,7 @@ namespace {
 
 constexpr int CT_ROWS = 128, CT_PTS = 8, CT_NS = 16, CT_C = 256;
 constexpr int CT_KC = 32;                          // K per streamed weight chunk
-constexpr int CT_CHUNKS = 2 * (CT_C / CT_KC);      // 8 chunks per layer, 2 layers
+
 constexpr int CT_STAGES = 4;
 constexpr int CT_GROUPS = CT_C / CT_KC;            // K groups per layer: the unit of the A-operand hand-off (8)
 constexpr int CT_PLANE_BYTES = CT_C * CT_KC * 2;   // one fp16 plane of a chunk: 16 KB
@@ -233,14 +233,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int c = 0; c < CT_CHUNKS; ++c) {
-                    ct_mbar_wait(&bar_empty[stage], phase ^ 1);
-                    rt_mbar_expect_tx(&bar_full[stage], CT_STAGE_BYTES);
-                    const int chunk = (c / CT_GROUPS) * CT_GROUPS + ct_group_at(c % CT_GROUPS);   // layer-major, MMA order
-                    rt_bulk_g2s(s_stage + stage * CT_STAGE_BYTES,
-                                reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)chunk * CT_STAGE_BYTES, CT_STAGE_BYTES,
-                                &bar_full[stage]);
-                    if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                const uint8_t *wp = reinterpret_cast<const uint8_t *>(a.wpack);
+                for (int layer = 0; layer < 2; ++layer) {
+                    // correction pass: [hi, lo] planes of one K chunk per stage, in the order the A groups arrive
+                    for (int c = 0; c < CT_GROUPS; ++c) {
+                        ct_mbar_wait(&bar_empty[stage], phase ^ 1);
+                        rt_mbar_expect_tx(&bar_full[stage], CT_STAGE_BYTES);
+                        const int chunk = layer * CT_GROUPS + ct_group_at(c);
+                        rt_bulk_g2s(s_stage + stage * CT_STAGE_BYTES, wp + (size_t)chunk * CT_STAGE_BYTES, CT_STAGE_BYTES, &bar_full[stage]);
+                        if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    // main pass: the hi planes of two consecutive K chunks per stage
+                    for (int c = 0; c < CT_GROUPS / 2; ++c) {
+                        ct_mbar_wait(&bar_empty[stage], phase ^ 1);
+                        rt_mbar_expect_tx(&bar_full[stage], CT_STAGE_BYTES);
+                        for (int pl = 0; pl < 2; ++pl) {
+                            const int chunk = layer * CT_GROUPS + 2 * c + pl;
+                            rt_bulk_g2s(s_stage + stage * CT_STAGE_BYTES + pl * CT_PLANE_BYTES, wp + (size_t)chunk * CT_STAGE_BYTES,
+                                        CT_PLANE_BYTES, &bar_full[stage]);
+                        }
+                        if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -261,25 +274,39 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         ct_mbar_wait(&bar_full[stage], phase);
                         ct_fence_after();
                         const uint32_t base = rt_smem_u32(s_stage + stage * CT_STAGE_BYTES);
+                        // Correction products first (lo*hi + hi*lo over all of K), main products (hi*hi) last: the tensor
+                        // core truncates the fp32 accumulator after every k-step, so the number of accumulation steps taken
+                        // at full magnitude sets the error (tools/tc_precision.cu: 3x smaller rms than interleaving).
 #pragma unroll
                         for (int j = 0; j < CT_KC / 16; ++j) {
                             const int kk = g * (CT_KC / 16) + j;
                             // chunk plane = [kc = K/8][row group = 32][8 rows][8 halfs]: kc stride 4096 B, row group 128 B
                             const uint64_t bhi = ct_desc(base + j * 8192, 4096, 128);
                             const uint64_t blo = ct_desc(base + CT_PLANE_BYTES + j * 8192, 4096, 128);
-                            ct_mma_ts(tD, tAhi + 8 * kk, bhi, CT_IDESC, (c | j) > 0);
-                            ct_mma_ts(tD, tAlo + 8 * kk, bhi, CT_IDESC, 1);
+                            ct_mma_ts(tD, tAlo + 8 * kk, bhi, CT_IDESC, (c | j) > 0);
                             ct_mma_ts(tD, tAhi + 8 * kk, blo, CT_IDESC, 1);
                         }
                         ct_commit(&bar_empty[stage]);  // frees the ring slot when these MMAs have read it
                         if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
                     }
+                    for (int c = 0; c < CT_GROUPS / 2; ++c) {
+                        ct_mbar_wait(&bar_full[stage], phase);
+                        ct_fence_after();
+                        const uint32_t base = rt_smem_u32(s_stage + stage * CT_STAGE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < 2 * (CT_KC / 16); ++j) {
+                            const int kk = 2 * c * (CT_KC / 16) + j;   // the stage holds the hi planes of K chunks 2c, 2c+1 back to back
+                            ct_mma_ts(tD, tAhi + 8 * kk, ct_desc(base + j * 8192, 4096, 128), CT_IDESC, 1);
+                        }
+                        ct_commit(&bar_empty[stage]);
+                        if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                    }
                     if (layer == 1) {
                         // WeightNet last layer: [128 x 16] . [256 x 16]^T -> columns [256,512) (the A planes are dead now;
                         // tcgen05.mma executes in issue order)
-                        ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 0);
-                        ct_mma_ss(tW, ct_desc(aw_lo, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 1);
+                        ct_mma_ss(tW, ct_desc(aw_lo, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 0);
                         ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_lo, 4096, 128), CT_IDESC, 1);
+                        ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 1);
                     }
                     ct_commit(bar_d);
                     a_phase ^= 1;

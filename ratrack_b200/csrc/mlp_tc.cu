@@ -203,13 +203,16 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                     const uint32_t lbo = (uint32_t)(n / 8) * 128;
                     const uint32_t hi_base = rt_smem_u32(smem + w_off[l]), lo_base = hi_base + 2 * k * n;
                     const uint32_t idesc = mt_idesc(n);
+                    // Issue order matters for accuracy: the tensor core TRUNCATES the fp32 accumulator after every
+                    // k-step (measured, tools/tc_precision.cu: error grows with the number of accumulation steps taken
+                    // at full magnitude and is biased toward zero).  The small correction products go first, while the
+                    // accumulator is ~2^-11 of its final size, the k/16 main products last.
                     for (int kk = 0; kk < k / 16; ++kk) {
-                        const uint64_t bhi = mt_desc(hi_base + kk * 2 * lbo, lbo, 128);
-                        const uint64_t blo = mt_desc(lo_base + kk * 2 * lbo, lbo, 128);
-                        mt_mma_ts(tD, tAhi + 8 * kk, bhi, idesc, kk > 0);
-                        mt_mma_ts(tD, tAlo + 8 * kk, bhi, idesc, 1);
-                        mt_mma_ts(tD, tAhi + 8 * kk, blo, idesc, 1);
+                        mt_mma_ts(tD, tAlo + 8 * kk, mt_desc(hi_base + kk * 2 * lbo, lbo, 128), idesc, kk > 0);
+                        mt_mma_ts(tD, tAhi + 8 * kk, mt_desc(lo_base + kk * 2 * lbo, lbo, 128), idesc, 1);
                     }
+                    for (int kk = 0; kk < k / 16; ++kk)
+                        mt_mma_ts(tD, tAhi + 8 * kk, mt_desc(hi_base + kk * 2 * lbo, lbo, 128), idesc, 1);
                     mt_commit(&bar_d);
                 }
             }

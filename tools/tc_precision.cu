@@ -1,0 +1,243 @@
+// Precision probe for the split-fp16 tcgen05 products (development tool, not part of the product library).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/tc_precision tools/tc_precision.cu && ./tools/tc_precision
+// Question: where does the error of  x*y ~ hi*hi + lo*hi + hi*lo  (fp16 planes, fp32 accumulation in TMEM) come from,
+// and which issue order / accumulator layout brings it to the level of an fp32 FMA chain?
+//   S0  interleaved per k-step into one accumulator (round-1 kernels)
+//   S1  correction products first (all k), then the main products, one accumulator
+//   S2  main -> D0, corrections -> D1, summed in fp32 (RN) in the epilogue
+//   S3  S2 with the main product split into two K halves (two accumulators)
+//   S4  S2 + lo*lo
+//   S5  S2 with the main product in four K quarters
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity, int *err) {
+    for (int it = 0; it < (1 << 22); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    *err = 1;
+    return false;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t of warp w <-> lane 32*(w%4)+t
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // version = 1 (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: F16 x F16 -> F32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
+constexpr int M = 128, N = 64, K = 256;
+__host__ __device__ inline int core_off(int r, int k, int R) { return ((k / 8) * (R / 8) + r / 8) * 64 + (r % 8) * 8 + (k % 8); }
+
+__global__ void __launch_bounds__(192) prec_kernel(int strat, const float *A, const float *B, float *D, int *err) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __half *sAh = reinterpret_cast<__half *>(smem);
+    __half *sAl = sAh + M * K;
+    __half *sBh = sAl + M * K;
+    __half *sBl = sBh + N * K;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+        const float x = A[i];
+        const __half h = __float2half_rn(x);
+        sAh[core_off(i / K, i % K, M)] = h;
+        sAl[core_off(i / K, i % K, M)] = __float2half_rn(x - __half2float(h));
+    }
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+        const float x = B[i] * 1024.0f;
+        const __half h = __float2half_rn(x);
+        sBh[core_off(i / K, i % K, N)] = h;
+        sBl[core_off(i / K, i % K, N)] = __float2half_rn(x - __half2float(h));
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 4) tmem_alloc(&tmem_slot, 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = tmem_slot;
+    if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(M, N);
+            const uint32_t kA = (M / 8) * 128, kB = (N / 8) * 128;
+            auto dA = [&](const __half *p, int k) { return make_desc(smem_u32(p) + k * 2 * kA, kA, 128); };
+            auto dB = [&](const __half *p, int k) { return make_desc(smem_u32(p) + k * 2 * kB, kB, 128); };
+            const int KS = K / 16;
+            if (strat == 0) {
+                for (int k = 0; k < KS; ++k) {
+                    mma_ss(tm, dA(sAh, k), dB(sBh, k), idesc, k > 0);
+                    mma_ss(tm, dA(sAl, k), dB(sBh, k), idesc, 1);
+                    mma_ss(tm, dA(sAh, k), dB(sBl, k), idesc, 1);
+                }
+            } else if (strat == 1) {
+                for (int k = 0; k < KS; ++k) {
+                    mma_ss(tm, dA(sAl, k), dB(sBh, k), idesc, k > 0);
+                    mma_ss(tm, dA(sAh, k), dB(sBl, k), idesc, 1);
+                }
+                for (int k = 0; k < KS; ++k) mma_ss(tm, dA(sAh, k), dB(sBh, k), idesc, 1);
+            } else {
+                const int parts = strat == 3 ? 2 : (strat == 5 ? 4 : 1);
+                for (int k = 0; k < KS; ++k) {
+                    mma_ss(tm + 64, dA(sAl, k), dB(sBh, k), idesc, k > 0);
+                    mma_ss(tm + 64, dA(sAh, k), dB(sBl, k), idesc, 1);
+                    if (strat == 4) mma_ss(tm + 64, dA(sAl, k), dB(sBl, k), idesc, 1);
+                }
+                for (int p = 0; p < parts; ++p) {
+                    const uint32_t d = p == 0 ? tm : tm + 64 + 64 * p;
+                    for (int k = p * KS / parts; k < (p + 1) * KS / parts; ++k) mma_ss(d, dA(sAh, k), dB(sBh, k), idesc, k > p * KS / parts);
+                }
+            }
+            umma_commit(&bar);
+        }
+        __syncwarp();
+    }
+    if (warp < 4) {
+        if (mbar_wait_bounded(&bar, 0, err)) {
+            fence_after();
+            const int row = warp * 32 + lane;
+            const uint32_t lb = (uint32_t)(warp * 32) << 16;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t r[32], c[32];
+                tmem_ld32(tm + lb + c0, r);
+                float v[32];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (strat >= 2) {
+                    const int parts = strat == 3 ? 2 : (strat == 5 ? 4 : 1);
+                    for (int p = 1; p < parts; ++p) {
+                        tmem_ld32(tm + lb + 64 + 64 * p + c0, c);
+                        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(c[j]);
+                    }
+                    tmem_ld32(tm + lb + 64 + c0, c);
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(c[j]);
+                }
+                for (int j = 0; j < 32; ++j) D[row * N + c0 + j] = v[j] * (1.0f / 1024.0f);
+            }
+        }
+        fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tm, 512);
+}
+
+static double gauss() {
+    double u = (rand() + 1.0) / (RAND_MAX + 2.0), v = (rand() + 1.0) / (RAND_MAX + 2.0);
+    return sqrt(-2 * log(u)) * cos(6.283185307179586 * v);
+}
+
+int main() {
+    float *hA = (float *)malloc(M * K * 4), *hB = (float *)malloc(N * K * 4), *out = (float *)malloc(M * N * 4);
+    double *ref = (double *)malloc(M * N * 8);
+    float *simt = (float *)malloc(M * N * 4);
+    float *dA, *dB, *dD;
+    int *dErr;
+    CK(cudaMalloc(&dA, M * K * 4)); CK(cudaMalloc(&dB, N * K * 4)); CK(cudaMalloc(&dD, M * N * 4)); CK(cudaMalloc(&dErr, 4));
+    CK(cudaFuncSetAttribute(prec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608));
+    for (int data = 0; data < 3; ++data) {
+        srand(7 + data);
+        // data 0: post-ReLU activations (half zeros, |x|~1) x signed weights;  1: all-positive both (bias detector);  2: small activations (|x|~0.02)
+        for (int i = 0; i < M * K; ++i) {
+            double g = gauss();
+            hA[i] = data == 0 ? (float)fmax(g, 0.0) : data == 1 ? (float)fabs(g) : (float)(0.02 * fmax(g, 0.0));
+        }
+        for (int i = 0; i < N * K; ++i) hB[i] = data == 1 ? (float)(0.06 * fabs(gauss())) : (float)(0.06 * gauss());
+        double scale = 0;
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n) {
+                double s = 0;
+                float f = 0;
+                for (int k = 0; k < K; ++k) {
+                    s += (double)hA[m * K + k] * (double)hB[n * K + k];
+                    f = fmaf(hA[m * K + k], hB[n * K + k], f);
+                }
+                ref[m * N + n] = s;
+                simt[m * N + n] = f;
+                scale += s * s;
+            }
+        scale = sqrt(scale / (M * N));
+        auto report = [&](const char *name, const float *o) {
+            double mx = 0, rms = 0, mean = 0;
+            for (int i = 0; i < M * N; ++i) {
+                double d = (double)o[i] - ref[i];
+                mx = fmax(mx, fabs(d)); rms += d * d; mean += d * (ref[i] >= 0 ? 1 : -1);
+            }
+            printf("data %d %-28s max %.3e  rms %.3e  mean(toward-zero<0) %+.3e   (of rms|ref| = %.3f)\n", data, name, mx / scale,
+                   sqrt(rms / (M * N)) / scale, mean / (M * N) / scale, scale);
+        };
+        report("fp32 fmaf chain (host)", simt);
+        CK(cudaMemcpy(dA, hA, M * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB, N * K * 4, cudaMemcpyHostToDevice));
+        const char *names[6] = {"S0 interleaved", "S1 corrections first", "S2 separate corr acc", "S3 S2 + main in 2 halves", "S4 S2 + lo*lo", "S5 S2 + main in 4 quarters"};
+        for (int s = 0; s < 6; ++s) {
+            CK(cudaMemset(dD, 0xff, M * N * 4)); CK(cudaMemset(dErr, 0, 4));
+            prec_kernel<<<1, 192, 196608>>>(s, dA, dB, dD, dErr);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("strategy %d: CUDA error %s\n", s, cudaGetErrorString(e)); return 1; }
+            int err; CK(cudaMemcpy(&err, dErr, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out, dD, M * N * 4, cudaMemcpyDeviceToHost));
+            if (err) printf("  (timeout)\n");
+            report(names[s], out);
+        }
+    }
+    return 0;
+}
