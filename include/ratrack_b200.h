@@ -130,6 +130,11 @@ int rt_engine_num_lanes(const rt_engine *e, int b);
  * MLP left the fp16 hi/lo range (|x| >= 65000): that call's outputs are invalid */
 int rt_engine_last_status(rt_engine *e, int *status_out);
 
+/* non-blocking form: enqueues on `stream` the copy of the status words (one per lane) into host_status[0..1], which must be
+ * pinned host memory; read them after synchronising with `stream`.  Independently of either call, a forward whose guard fired
+ * overwrites its flow / cls / h outputs with NaN on the device, so the failure is loud even when the status is never read. */
+int rt_engine_status_async(rt_engine *e, int *host_status, void *stream);
+
 /* kernels launched by this engine since creation */
 long long rt_engine_launch_count(const rt_engine *e);
 
@@ -157,14 +162,15 @@ int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const floa
  *   (reference: src/models/utils/track4d_utils.py:405-434, src/models/track4d.py:166-180)
  * aff (b,m,n) affinities of m previous x n current objects -> scores (b,m+1,n+1) log-couplings after `iters` log-space
  * Sinkhorn iterations with dustbin score `alpha` [optional, may be NULL], indices0 (b,m) [optional] and indices1 (b,n):
- * the mutually-best partner of every object, -1 where there is none (int64, as torch returns them).  m, n <= 127. */
+ * the mutually-best partner of every object, -1 where there is none (int64, as torch returns them).  Up to 127 objects on a
+ * side the coupling matrix lives in shared memory; up to 2047 it moves to a stream-ordered scratch (cudaMallocAsync). */
 int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha, int iters, float *scores, long long *indices0,
                       long long *indices1, void *stream);
 
 /* replaces the host-side sklearn call of Track4D.clustering (reference: src/models/track4d.py:36,108-126)
  * x (b,n,d) fp32 feature rows -> labels (b,n) int32: exactly sklearn.cluster.DBSCAN(eps, min_samples).fit_predict per set
  * (cluster numbers in order of first core point, border points to the lowest-numbered adjacent cluster, noise = -1).
- * n <= 1024, d <= 16. */
+ * d <= 16; n <= 1024 keeps the adjacency in shared memory, n <= 16384 uses a stream-ordered scratch (cudaMallocAsync). */
 int rt_dbscan(int b, int n, int d, const float *x, float eps, int min_samples, int *labels, void *stream);
 
 #ifdef __cplusplus

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rt_engine_set_flags": [_P, _I],
     "rt_engine_stage_profile": [_P, _I],
     "rt_engine_last_status": [_P, ctypes.POINTER(ctypes.c_int)],
+    "rt_engine_status_async": [_P, _P, _P],
     "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
 }
 # entries whose return value is not an error code

@@ -26,6 +26,24 @@ int rt_check_launch(const char *what);  // cudaGetLastError() -> code (+ message
 
 static inline int rt_divup(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: a process that drives several
+// GPUs (nn.DataParallel threads, one engine per device) must opt in on each of them.  One bit per device ordinal,
+// thread-safe; a device is marked only after the caller's attribute calls succeeded.
+struct RtPerDevice {
+    unsigned long long mask[4] = {0, 0, 0, 0};   // device ordinals 0..255
+    bool done(int dev) const {
+        return dev >= 0 && dev < 256 && (__atomic_load_n(&mask[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull;
+    }
+    void mark(int dev) {
+        if (dev >= 0 && dev < 256) __atomic_fetch_or(&mask[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+    }
+};
+static inline int rt_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
 // largest power of two <= n, capped at 1024: the CTA size the reference picks for FPS
 // (reference: src/lib/src/cuda_utils.h:10-14); it fixes the arg-max tie-break order.
 static inline int rt_ref_block_size(int n) {

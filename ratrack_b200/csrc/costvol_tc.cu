@@ -501,14 +501,14 @@ int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2,
                          const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
                          float *out, int *status, cudaStream_t st) {
     if (total_pts <= 0) return RT_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static RtPerDevice attr_set;
+    if (!attr_set.done(rt_current_device())) {
         cudaError_t e = cudaFuncSetAttribute(costvol_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e != cudaSuccess) {
             rt_set_error("costvol_tc: cannot reserve %d bytes of shared memory: %s", SM_TOTAL, cudaGetErrorString(e));
             return (int)e;
         }
-        attr_set = true;
+        attr_set.mark(rt_current_device());
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

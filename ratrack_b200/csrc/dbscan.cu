@@ -7,23 +7,26 @@
 //               it opens the next);
 //   border    = a non-core point within eps of core points joins the lowest-numbered of their clusters (the first one to
 //               reach it in sklearn's traversal);  noise = -1.
-// One CTA per set; the n x n adjacency lives in shared memory as bit rows (n <= 1024: 128 KB), components come from
-// min-label propagation with pointer jumping.  Distances are accumulated in fp64 from the fp32 inputs, like sklearn's trees.
+// One CTA per set; the n x n adjacency lives in shared memory as bit rows (n <= 1024: 128 KB) -- or, for larger sets (the
+// reference has no limit; config-5 frames of ~3000 points can have more than 1024 moving points), in a stream-ordered global
+// scratch with the points read through L1 -- components come from min-label propagation with pointer jumping.  Distances are accumulated in fp64 from the fp32 inputs, like sklearn's trees.
 #include "common.cuh"
 
 namespace {
 
 constexpr int DB_THREADS = 1024;
-constexpr int DB_MAX_N = 1024;
+constexpr int DB_MAX_N_SMEM = 1024;
+constexpr int DB_MAX_N = 16384;
 constexpr int DB_MAX_D = 16;
 
 __global__ void __launch_bounds__(DB_THREADS) dbscan_kernel(int n, int d, const float *__restrict__ x_all, double eps2, int min_samples,
-                                                            int *__restrict__ labels_all) {
+                                                            int *__restrict__ labels_all, uint32_t *__restrict__ adj_scratch) {
     extern __shared__ __align__(16) unsigned char db_smem[];
     const int words = (n + 31) >> 5;
-    uint32_t *adj = reinterpret_cast<uint32_t *>(db_smem);          // n x words
-    float *xs = reinterpret_cast<float *>(adj + (size_t)n * words);  // n x d
-    int *label = reinterpret_cast<int *>(xs + (size_t)n * d);        // n: smallest core index of the component (cores only)
+    const bool big = adj_scratch != nullptr;
+    uint32_t *adj = big ? adj_scratch + (size_t)blockIdx.x * n * words : reinterpret_cast<uint32_t *>(db_smem);   // n x words
+    float *xs_s = reinterpret_cast<float *>(db_smem + (big ? 0 : sizeof(uint32_t) * (size_t)n * words));           // n x d (small sets)
+    int *label = reinterpret_cast<int *>(xs_s + (big ? 0 : (size_t)n * d));   // n: smallest core index of the component (cores only)
     int *cid = label + n;                                            // n: cluster number of a core point
     uint32_t *corem = reinterpret_cast<uint32_t *>(cid + n);         // words: core bit mask
     uint32_t *rootm = corem + words;                                 // words: component-root bit mask
@@ -32,7 +35,9 @@ __global__ void __launch_bounds__(DB_THREADS) dbscan_kernel(int n, int d, const 
     const float *x = x_all + (size_t)blockIdx.x * n * d;
     int *labels = labels_all + (size_t)blockIdx.x * n;
 
-    for (int i = t; i < n * d; i += DB_THREADS) xs[i] = x[i];
+    const float *xs = big ? x : xs_s;
+    if (!big)
+        for (int i = t; i < n * d; i += DB_THREADS) xs_s[i] = x[i];
     for (int i = t; i < words; i += DB_THREADS) { corem[i] = 0u; rootm[i] = 0u; }
     __syncthreads();
     // adjacency rows + neighbour counts: one row per thread, so every candidate read is a shared-memory broadcast
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(DB_THREADS) dbscan_kernel(int n, int d, const 
     }
     __syncthreads();
     // connected components of the core graph: label = smallest core index reachable
-    for (int iter = 0; iter < 4 * DB_MAX_N; ++iter) {
+    for (int iter = 0; iter < 4 * n + 8; ++iter) {
         if (t == 0) s_changed = 0;
         __syncthreads();
         for (int i = t; i < n; i += DB_THREADS) {
@@ -132,13 +137,31 @@ RT_API int rt_dbscan(int b, int n, int d, const float *x, float eps, int min_sam
     RT_REQUIRE(n <= DB_MAX_N && d <= DB_MAX_D, "dbscan: at most %d points of %d dimensions per set", DB_MAX_N, DB_MAX_D);
     if (b == 0 || n == 0) return RT_OK;
     const int words = (n + 31) >> 5;
-    const size_t smem = sizeof(uint32_t) * ((size_t)n * words + 2 * (size_t)words) + sizeof(float) * (size_t)n * d + sizeof(int) * 2 * (size_t)n;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(dbscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr = true;
+    const bool big = n > DB_MAX_N_SMEM;
+    const size_t adj_bytes = sizeof(uint32_t) * (size_t)n * words;
+    const size_t smem = (big ? 0 : adj_bytes + sizeof(float) * (size_t)n * d) + sizeof(uint32_t) * 2 * (size_t)words + sizeof(int) * 2 * (size_t)n;
+    static RtPerDevice attr;
+    const int dev = rt_current_device();
+    if (!attr.done(dev)) {
+        const cudaError_t e = cudaFuncSetAttribute(dbscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) {
+            rt_set_error("dbscan: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr.mark(dev);
     }
     RT_REQUIRE(smem <= 220 * 1024, "dbscan: %zu bytes of shared memory", smem);
-    dbscan_kernel<<<b, DB_THREADS, smem, (cudaStream_t)stream>>>(n, d, x, (double)eps * (double)eps, min_samples, labels);
-    return rt_check_launch("dbscan_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *scratch = nullptr;
+    if (big) {
+        const cudaError_t e = cudaMallocAsync(&scratch, adj_bytes * (size_t)b, st);
+        if (e != cudaSuccess) {
+            rt_set_error("dbscan: cudaMallocAsync(%zu): %s", adj_bytes * (size_t)b, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    dbscan_kernel<<<b, DB_THREADS, smem, st>>>(n, d, x, (double)eps * (double)eps, min_samples, labels, scratch);
+    const int rc = rt_check_launch("dbscan_kernel");
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
 }

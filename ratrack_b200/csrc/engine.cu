@@ -737,6 +737,22 @@ RT_API int rt_engine_last_status(rt_engine *e, int *status_out) {
     return RT_OK;
 }
 
+// non-blocking companion of rt_engine_last_status: enqueues, on `stream`, the copy of the status words of the last forward into
+// host_status[0..1] (pinned host memory; unused lanes are written as 0).  The caller reads them after an event / sync of its own.
+RT_API int rt_engine_status_async(rt_engine *e, int *host_status, void *stream) {
+    RT_REQUIRE(e && host_status, "engine_status_async: null argument");
+    for (int l = 0; l < 2; ++l) {
+        host_status[l] = 0;
+        if (!e->last_status[l]) continue;
+        const cudaError_t err = cudaMemcpyAsync(host_status + l, e->last_status[l], sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (err != cudaSuccess) {
+            rt_set_error("engine_status_async: %s", cudaGetErrorString(err));
+            return (int)err;
+        }
+    }
+    return RT_OK;
+}
+
 // One lane: b pairs of a call of b_total pairs.  All tensor pointers are already offset to the lane's first pair;
 // h_in / h_out are (5, b_total, 128), so their layer stride is h_stride = b_total * 128.
 static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_stride, int n, const float *pc1, const float *pc2,
@@ -917,6 +933,11 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
     e->launches += 11;
     if (aux != st) cudaStreamWaitEvent(st, L.ev_aux, 0);   // join the output stream
+    // fp16-range guard fired anywhere in this lane's step -> its results become NaN (never silently saturated values)
+    if (e->flags & 3) {
+        RT_TRY(rt_launch_poison_on_status(w.status, flow, (long long)b * 3 * n, cls, (long long)b * n, h_out, b, h_stride, st));
+        e->launches += 1;
+    }
     stage_mark(e, lane_idx, st);   // flow head + joined outputs
     if (knn12) cudaMemcpyAsync(knn12, w.knn12, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);
     if (knn11) cudaMemcpyAsync(knn11, w.knn11, sizeof(int) * (size_t)b * n * kKnn, cudaMemcpyDeviceToDevice, st);

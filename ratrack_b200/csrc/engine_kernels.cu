@@ -1025,6 +1025,23 @@ int rt_launch_morton_perm(int clouds, int n, const float *xyz, int *perm, cudaSt
     morton_perm_kernel<<<clouds, 256, npad * sizeof(unsigned long long), st>>>(n, npad, xyz, perm);
     return rt_check_launch("morton_perm_kernel");
 }
+// Loud failure instead of silent garbage: when the fp16-range guard of the tensor-core kernels fired (status != 0), the
+// step's results are overwritten with NaN on the device, so a caller that never reads the status word cannot consume
+// saturated values.  No host synchronisation; when the status is clean the kernel reads one word and exits.
+__global__ void __launch_bounds__(256) poison_on_status_kernel(const int *status, float *flow, long long nflow, float *cls,
+                                                               long long ncls, float *h_out, int b, size_t h_stride) {
+    if (*status == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t0; i < nflow; i += stride) flow[i] = nan;
+    for (long long i = t0; i < ncls; i += stride) cls[i] = nan;
+    for (long long i = t0; i < (long long)5 * b * 128; i += stride) h_out[(i / (b * 128)) * h_stride + i % (b * 128)] = nan;
+}
+int rt_launch_poison_on_status(const int *status, float *flow, long long nflow, float *cls, long long ncls, float *h_out, int b,
+                               size_t h_stride, cudaStream_t st) {
+    poison_on_status_kernel<<<64, 256, 0, st>>>(status, flow, nflow, cls, ncls, h_out, b, h_stride);
+    return rt_check_launch("poison_on_status_kernel");
+}
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return RT_OK;
     fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);

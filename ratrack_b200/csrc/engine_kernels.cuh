@@ -94,6 +94,9 @@ int rt_launch_gru(int b, const float *x, const float *h_in, const float *wih, co
 int rt_launch_cls_tail(long long rows, const float *h3, const float *w4, const float *lin_w, const float *lin_b,
                        float *cls, cudaStream_t st);
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st);
+// if *status != 0: flow, cls and h_out (5 x b x 128, layer stride h_stride) become NaN (fp16-range guard fired)
+int rt_launch_poison_on_status(const int *status, float *flow, long long nflow, float *cls, long long ncls, float *h_out, int b,
+                               size_t h_stride, cudaStream_t st);
 // Spatial processing order: perm[cloud*n + j] = cloud*n + (index of the j-th point of the cloud along a 30-bit Morton curve).
 // Kernels that gather neighbour rows walk their points in this order so that the points of a tile share neighbours (L1 / L2
 // hits instead of repeated 1 KB row fetches); every point is still computed independently and written to its own row, so the

@@ -263,10 +263,14 @@ int launch_warp2(int b, int n, int m, int logbs, int ph_shift, const float *xyz,
                  cudaStream_t st) {
     size_t smem = (size_t)FW_WARPS * ((n * 3 + 3) & ~3) * sizeof(float);
     if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
-    static size_t attr_bytes = 0;
-    if (smem > 40 * 1024 && smem > attr_bytes) {
-        cudaFuncSetAttribute(fps_warp_kernel<PPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
-        attr_bytes = kFpsHogBytes;
+    static RtPerDevice attr;   // per kernel instantiation, per device
+    if (smem > 40 * 1024 && !attr.done(rt_current_device())) {
+        const cudaError_t e = cudaFuncSetAttribute(fps_warp_kernel<PPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        if (e != cudaSuccess) {
+            rt_set_error("fps: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr.mark(rt_current_device());
     }
     fps_warp_kernel<PPL, FUSED><<<(b + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, smem, st>>>(b, n, m, logbs, ph_shift, xyz, temp,
                                                                                             idx, new_xyz);
@@ -357,10 +361,14 @@ int launch_reg3(int b, int n, int m, const float *xyz, float *temp, int *idx, fl
     // sharing the SM stretches each round 2-3x (measured on B200).  Asking for (nearly) the whole shared memory of the
     // SM keeps every other CTA off it, so the chain runs at its stand-alone speed whatever else is in flight.
     if (g_fps_exclusive && smem < kFpsHogBytes) smem = kFpsHogBytes;
-    static size_t attr_bytes = 0;
-    if (smem > 40 * 1024 && smem > attr_bytes) {
-        cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH, FUSED, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
-        attr_bytes = kFpsHogBytes;
+    static RtPerDevice attr;   // per kernel instantiation, per device
+    if (smem > 40 * 1024 && !attr.done(rt_current_device())) {
+        const cudaError_t e = cudaFuncSetAttribute(fps_reg_kernel<T, Q, PH, FUSED, CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFpsHogBytes);
+        if (e != cudaSuccess) {
+            rt_set_error("fps: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr.mark(rt_current_device());
     }
     fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n, m, xyz, temp, idx, new_xyz);
     return rt_check_launch("fps_reg_kernel");

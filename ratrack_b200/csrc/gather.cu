@@ -179,12 +179,12 @@ inline int smem_slab(int c, int n) {
 }
 template <typename K>
 inline bool smem_opt_in(K kernel) {
-    static bool done = false, ok = false;
-    if (!done) {
-        ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_MAX) == cudaSuccess;
-        done = true;
-    }
-    return ok;
+    static RtPerDevice done;   // one instance per kernel (template instantiation); per device, thread-safe
+    const int dev = rt_current_device();
+    if (done.done(dev)) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_MAX) != cudaSuccess) return false;
+    done.mark(dev);
+    return true;
 }
 
 int launch_gather(int b, int c, int n, long long e_total, const float *points, const int *idx, float *out,

@@ -475,8 +475,8 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     a.d_cols = dmax;
     a.a_cols = kmax / 2;
     RT_REQUIRE(wbytes <= 200 * 1024, "mlp_tc: %d bytes of weights do not fit in shared memory", wbytes);
-    static bool smem_set = false;
-    if (!smem_set) {
+    static RtPerDevice smem_set;
+    if (!smem_set.done(rt_current_device())) {
         cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
@@ -484,7 +484,7 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
             rt_set_error("mlp_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        smem_set = true;
+        smem_set.mark(rt_current_device());
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -10,7 +10,8 @@
 namespace {
 
 constexpr int SK_THREADS = 256;
-constexpr int SK_MAX = 128;   // (m+1), (n+1) <= SK_MAX
+constexpr int SK_MAX_SMEM = 128;   // (m+1), (n+1) <= SK_MAX_SMEM: coupling matrix and its transpose live in shared memory
+constexpr int SK_MAX = 2048;       // beyond that, up to SK_MAX, they live in a stream-ordered global scratch (L1/L2-resident)
 
 // log(sum_k exp(row[k] + add[k])), k < len  (torch.logsumexp: max-shifted; -inf rows stay -inf), evaluated by the LPR
 // consecutive lanes that share the row (LPR = 8 for small matrices: four rows per warp step, 3-step shuffles)
@@ -31,12 +32,14 @@ __device__ __forceinline__ float sk_lse(const float *row, const float *add, int 
 template <int LPR>
 __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n, const float *__restrict__ aff_all, float alpha,
                                                                      int iters, float *__restrict__ scores_all,
-                                                                     long long *__restrict__ idx0_all, long long *__restrict__ idx1_all) {
+                                                                     long long *__restrict__ idx0_all, long long *__restrict__ idx1_all,
+                                                                     float *__restrict__ zscratch) {
     extern __shared__ float sm[];
     const int M = m + 1, N = n + 1, ld = N + 1, ldt = M + 1;   // +1: rows start on different banks
-    float *Z = sm;                    // M x ld
-    float *ZT = Z + M * ld;           // N x ldt (transposed copy)
-    float *u = ZT + N * ldt;          // M
+    const size_t zfloats = (size_t)M * ld + (size_t)N * ldt;
+    float *Z = zscratch ? zscratch + blockIdx.x * zfloats : sm;   // M x ld
+    float *ZT = Z + (size_t)M * ld;                               // N x ldt (transposed copy)
+    float *u = zscratch ? sm : ZT + (size_t)N * ldt;              // M
     float *v = u + M;                 // N
     float *log_mu = v + N;            // M
     float *log_nu = log_mu + M;       // N
@@ -154,16 +157,35 @@ RT_API int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha,
     RT_REQUIRE(m + 1 <= SK_MAX && n + 1 <= SK_MAX, "sinkhorn_match: at most %d x %d objects", SK_MAX - 1, SK_MAX - 1);
     if (b == 0) return RT_OK;
     const int M = m + 1, N = n + 1;
-    const size_t smem = sizeof(float) * ((size_t)M * (N + 1) + (size_t)N * (M + 1) + 4 * (size_t)(M + N)) + sizeof(int) * (size_t)(M + N);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(sinkhorn_match_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(sinkhorn_match_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr = true;
+    const bool in_smem = M <= SK_MAX_SMEM && N <= SK_MAX_SMEM;
+    const size_t zbytes = sizeof(float) * ((size_t)M * (N + 1) + (size_t)N * (M + 1));
+    const size_t vbytes = sizeof(float) * 4 * (size_t)(M + N) + sizeof(int) * (size_t)(M + N);
+    const size_t smem = vbytes + (in_smem ? zbytes : 0);
+    static RtPerDevice attr;
+    const int dev = rt_current_device();
+    if (!attr.done(dev)) {
+        cudaError_t e = cudaFuncSetAttribute(sinkhorn_match_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sinkhorn_match_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) {
+            rt_set_error("sinkhorn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr.mark(dev);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float *zscratch = nullptr;
+    if (!in_smem) {   // more than 127 objects on a side: the reference has no limit (track4d.py:166-180), so neither has this entry
+        const cudaError_t e = cudaMallocAsync(&zscratch, zbytes * (size_t)b, st);
+        if (e != cudaSuccess) {
+            rt_set_error("sinkhorn_match: cudaMallocAsync(%zu): %s", zbytes * (size_t)b, cudaGetErrorString(e));
+            return (int)e;
+        }
     }
     if (M <= 96 && N <= 96)
-        sinkhorn_match_kernel<8><<<b, SK_THREADS, smem, (cudaStream_t)stream>>>(m, n, aff, alpha, iters, scores, indices0, indices1);
+        sinkhorn_match_kernel<8><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
     else
-        sinkhorn_match_kernel<32><<<b, SK_THREADS, smem, (cudaStream_t)stream>>>(m, n, aff, alpha, iters, scores, indices0, indices1);
-    return rt_check_launch("sinkhorn_match_kernel");
+        sinkhorn_match_kernel<32><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
+    const int rc = rt_check_launch("sinkhorn_match_kernel");
+    if (zscratch) cudaFreeAsync(zscratch, st);
+    return rc;
 }

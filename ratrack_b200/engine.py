@@ -157,6 +157,17 @@ class FusedBackbone:
         self._ws_key = None
         self.last_knn = None
         self._prof = None
+        # fp16-range guard of the tensor-core kernels (costvol_tc.cu / mlp_tc.cu): weights enter as 2^10 * W, activations
+        # as fp16 hi/lo planes.  Out-of-range WEIGHTS are known now: such a model runs on the fp32 SIMT kernels.
+        # Out-of-range ACTIVATIONS are caught per forward: the device overwrites that step's outputs with NaN, the status
+        # word comes back without a host synchronisation and the next forward (and everything after it) uses the fp32
+        # SIMT kernels -- see _poll_status / run_checked.
+        self.tensor_cores = True
+        self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._status_event = None
+        wmax = max(float(t.abs().max()) for t in self._weights if t is not None and t.dtype == torch.float32 and t.dim() >= 2)   # matrices: what gets packed
+        if not wmax * W_SCALE < 65000.0:
+            self._to_simt(f"a folded weight has magnitude {wmax:.3g}: 2^10 * W leaves the fp16 range")
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -180,11 +191,44 @@ class FusedBackbone:
                    (16 if knn_early else 0) | (32 if own_stream else 0) | (64 if morton else 0))
         self._ws_key = None   # the workspace layout depends on the lane split
 
+    def _to_simt(self, why):
+        import warnings
+
+        warnings.warn(f"ratrack_b200: {why}; this engine now runs its dense layers on the fp32 SIMT kernels "
+                      "(same dataflow, ~3x slower)", RuntimeWarning, stacklevel=3)
+        self.tensor_cores = False
+        self.set_flags(costvol_tc=False, mlp_tc=False)
+
+    def _poll_status(self, block=False):
+        """Status of the previous forward, if it has arrived (block=True waits for it).  True = its guard fired (its
+        outputs are NaN on the device) and the engine has switched to the fp32 SIMT kernels."""
+        ev = self._status_event
+        if ev is None or not (block or ev.query()):
+            return False
+        if block:
+            ev.synchronize()
+        self._status_event = None
+        if int(self._status_host[0]) | int(self._status_host[1]):
+            if self.tensor_cores:
+                self._to_simt("an activation left the fp16 hi/lo range of the tensor-core kernels (that forward's outputs were "
+                              "overwritten with NaN)")
+            return True
+        return False
+
+    def run_checked(self, *args, **kw):
+        """Forward + blocking status check; a forward whose fp16-range guard fired is repeated on the fp32 SIMT kernels."""
+        out = self(*args, **kw)
+        if self._poll_status(block=True):
+            out = self(*args, **kw)
+            if self._poll_status(block=True):
+                raise _cabi.RatrackError("fused backbone: device status set on the fp32 SIMT path")
+        return out
+
     def num_lanes(self, batch):
         return int(_cabi.lib().rt_engine_num_lanes(self._handle, int(batch)))
 
     def check_status(self):
-        """Blocking.  Raises if the last forward flagged an fp16-range overflow in the tensor-core cost volume."""
+        """Blocking.  Raises if the last forward flagged an fp16-range overflow in the tensor-core kernels."""
         st = ctypes.c_int(0)
         _cabi.call("rt_engine_last_status", self._handle, ctypes.byref(st))
         if st.value:
@@ -227,6 +271,7 @@ class FusedBackbone:
         return (base + 255) // 256 * 256, self._workspace.numel() - 256
 
     def __call__(self, pc1, pc2, feature1, feature2, h=None, want_knn=False):
+        self._poll_status()
         b, _, n = pc1.shape
         f32 = dict(dtype=torch.float32, device=self.device)
         args = [t.to(**f32).contiguous() for t in (pc1, pc2, feature1, feature2)]
@@ -249,6 +294,11 @@ class FusedBackbone:
                        cls.data_ptr(), cor.data_ptr(), f1.data_ptr(), f2.data_ptr(), prop.data_ptr(),
                        knn[0].data_ptr() if want_knn else None, knn[1].data_ptr() if want_knn else None,
                        ws_ptr, ws_bytes, torch.cuda.current_stream(self.device).cuda_stream)
+            if self.tensor_cores and self._status_event is None:
+                _cabi.call("rt_engine_status_async", self._handle, self._status_host.data_ptr(),
+                           torch.cuda.current_stream(self.device).cuda_stream)
+                self._status_event = torch.cuda.Event()
+                self._status_event.record()
         if want_knn:
             self.last_knn = knn
         return flow, h_out, cls, cor, f1, f2, prop

@@ -95,30 +95,68 @@ def all_gather_entries(x, group=None):
     return _AllGatherEntries.apply(x.reshape(-1), group)
 
 
-def sharded_affinity_loss(aff_list, aff_gt_list, group=None, grad_average=True):
+class _AllGatherFixed(torch.autograd.Function):
+    """all_gather of a (rows, width) block of the same shape on every rank -> (world * rows... ) stacked as (world, rows, width).
+    No size exchange, hence no device -> host synchronisation.  Backward returns the rank's own slice."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        world = dist.get_world_size(group)
+        ctx.rank = dist.get_rank(group)
+        out = torch.empty((world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
+        dist.all_gather(list(out.unbind(0)), x.detach().contiguous(), group=group)   # views of `out`: gathered in place
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank].clone(), None
+
+
+def sharded_affinity_loss(aff_list, aff_gt_list, group=None, grad_average=True, max_entries=None):
     """Affinity BCE as ONE mean over the entries of all ranks (what the single-process reference computes over its
     whole batch).  Every rank returns the same value.  With `grad_average` the local gradient is scaled by the world
-    size, so that the usual gradient all-reduce *average* yields exactly the gradient of the global mean."""
+    size, so that the usual gradient all-reduce *average* yields exactly the gradient of the global mean.
+
+    `max_entries` (an upper bound on one rank's entry count, e.g. 20 x 20 objects per frame x frames per shard) selects
+    the synchronisation-free form: every rank contributes one fixed-width block [prediction | target | validity] to a
+    single all_gather and the mean is a masked sum -- no counts travel to the host.  Without it the ragged vectors are
+    gathered after one exchange of their lengths (a host synchronisation per step)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     if world == 1:
         return affinity_loss(aff_list, aff_gt_list)
-    pred = all_gather_entries(aff_list.float(), group)
-    gt = all_gather_entries(aff_gt_list.float().detach(), group)
-    loss = affinity_loss(pred, gt)
+    if max_entries is None:
+        pred = all_gather_entries(aff_list.float(), group)
+        gt = all_gather_entries(aff_gt_list.float().detach(), group)
+        loss = affinity_loss(pred, gt)
+    else:
+        n = aff_list.numel()                       # a shape: known on the host without touching the device
+        if n > max_entries:
+            raise ValueError(f"sharded_affinity_loss: {n} entries on this rank exceed max_entries={max_entries}")
+        block = torch.zeros(3, max_entries, device=aff_list.device, dtype=torch.float32)
+        block[0] = 0.5                             # padding predictions: any value inside (0,1); masked out below
+        if n:
+            block = torch.cat([torch.cat([aff_list.float().reshape(-1), block[0, n:]])[None],
+                               torch.cat([aff_gt_list.float().detach().reshape(-1), block[1, n:]])[None],
+                               torch.cat([torch.ones(n, device=block.device), block[2, n:]])[None]])
+        allb = _AllGatherFixed.apply(block, group)                     # (world, 3, max_entries)
+        pred, gt, mask = allb[:, 0], allb[:, 1].detach(), allb[:, 2].detach()
+        bce = F.binary_cross_entropy(pred, gt, reduction="none")
+        cnt = mask.sum()
+        loss = torch.where(cnt > 0, (bce * mask).sum() / cnt.clamp_min(1.0), torch.zeros((), device=block.device))
     if grad_average:
         loss = loss.detach() + (loss - loss.detach()) * world
     return loss
 
 
 def track_4d_loss(pc1_wrap, cls, gt_flow, gt_cls, aff_list=None, aff_gt_list=None, pretrain=False, group=None,
-                  flow_reduction="mean"):
+                  flow_reduction="mean", max_entries=None):
     """total = 0.5 * flow + 0.5 * affinity + 1.0 * segmentation (segmentation only while `pretrain`); NaN terms are
     replaced by 0 as in the reference.  reference :8-31.  Returns (total, items)."""
     sf = flow_loss(pc1_wrap, gt_flow, reduction=flow_reduction)
     if aff_list is None:
         trk = torch.zeros((), device=pc1_wrap.device)
     else:
-        trk = sharded_affinity_loss(aff_list, aff_gt_list, group)
+        trk = sharded_affinity_loss(aff_list, aff_gt_list, group, max_entries=max_entries)
     seg = motion_seg_loss(cls, gt_cls, nan_to_zero=True)
     zero = torch.zeros((), device=pc1_wrap.device)
     sf = torch.where(torch.isnan(sf), zero, sf)

@@ -269,6 +269,7 @@ class Track4DBackbone(nn.Module):
         self.fd_layer = FlowDecoder(fc_inch=fc_inch, args=args)
         self.use_fused = True   # eval + no_grad -> fused engine (ratrack_b200/engine.py)
         self.capture_knn = False  # fused path: also return the cost volume's neighbour sets (tie-aware parity checks)
+        self.checked_forward = False   # True: synchronise after every fused forward and re-run it on the fp32 SIMT kernels if the fp16-range guard fired
         self._engine = None
 
     # -- reference-shaped methods ------------------------------------------------------------
@@ -297,11 +298,34 @@ class Track4DBackbone(nn.Module):
         """pc (B,3,N), feature (B,2,N), h (5,B,128)|None ->
         (output (B,3,N), h, cls (B,N), cor_features (B,256,N), pc1_features, pc2_features (B,256,N), prop_features (B,128,N))"""
         if self.use_fused and not self.training and not torch.is_grad_enabled():
-            from .engine import FusedBackbone
-            if self._engine is None:
-                self._engine = FusedBackbone(self)
-            return self._engine(pc1, pc2, feature1, feature2, h, want_knn=self.capture_knn)
+            # fp16-range guard of the tensor-core kernels: a forward that trips it returns NaN in flow / cls / h (the device
+            # overwrites them), reports through a status word polled without synchronisation at the next call, and the
+            # engine then stays on its fp32 SIMT kernels.  `checked_forward = True` trades one stream synchronisation per
+            # call for an immediate re-run of such a forward (what infer_host does).
+            eng = self._fused_engine()
+            run = eng.run_checked if self.checked_forward else eng
+            return run(pc1, pc2, feature1, feature2, h, want_knn=self.capture_knn)
         return self.backbone_modular(pc1, pc2, feature1, feature2, h)
+
+    def _fused_engine(self):
+        if self._engine is None:
+            from .engine import FusedBackbone
+            self._engine = FusedBackbone(self)
+        return self._engine
+
+    # The engine snapshots BatchNorm-folded copies of the parameters: anything that can change a parameter or move the
+    # module drops the snapshot (train()/eval(), load_state_dict, .to()/.cuda()/.half()...).  In-place edits of
+    # parameters that bypass these (optimizer steps happen in train mode; manual `p.data.copy_`, EMA) need refresh_engine().
+    def refresh_engine(self):
+        self._engine = None
+
+    def _apply(self, fn, *args, **kw):
+        self._engine = None
+        return super()._apply(fn, *args, **kw)
+
+    def load_state_dict(self, *args, **kw):
+        self._engine = None
+        return super().load_state_dict(*args, **kw)
 
     def forward(self, pc1, pc2, feature1, feature2, h=None):
         return self.backbone(pc1, pc2, feature1, feature2, h)
@@ -309,12 +333,15 @@ class Track4DBackbone(nn.Module):
     @torch.no_grad()
     def infer_host(self, pc1, pc2, feature1, feature2, h=None):
         """Host-buffer entry: (B,3,N)/(B,2,N) fp32 host tensors (pinned for async copies) -> (flow (B,3,N),
-        cls (B,N)) as host tensors.  H2D copies, the backbone and the D2H result reads all happen here."""
+        cls (B,N)) as host tensors.  H2D copies, the backbone and the D2H result reads all happen here; one call is
+        serial by construction -- `infer_host_stream` overlaps the copies of neighbouring batches with the compute."""
         dev = next(self.parameters()).device
         args = [x.to(dev, non_blocking=True) for x in (pc1, pc2, feature1, feature2)]
         if h is None:
             h = torch.zeros(5, pc1.size(0), 128, device=dev)
-        out = self.backbone(args[0], args[1], args[2], args[3], h)
+        fused = self.use_fused and not self.training
+        out = (self._fused_engine().run_checked(args[0], args[1], args[2], args[3], h, want_knn=self.capture_knn) if fused
+               else self.backbone(args[0], args[1], args[2], args[3], h))
         key = (tuple(out[0].shape), dev)
         if getattr(self, "_host_out_key", None) != key:
             self._host_out = (torch.empty(out[0].shape, dtype=torch.float32).pin_memory(),
@@ -323,9 +350,67 @@ class Track4DBackbone(nn.Module):
         self._host_out[0].copy_(out[0], non_blocking=True)
         self._host_out[1].copy_(out[2], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        if self._engine is not None and self.use_fused and not self.training:
-            self._engine.check_status()
         return self._host_out
+
+    @torch.no_grad()
+    def infer_host_stream(self, batches, depth=2):
+        """Pipelined host-buffer entry for throughput: `batches` yields (pc1, pc2, feature1, feature2) pinned host tensors
+        of one shape; this generator yields (flow (B,3,N), cls (B,N)) pinned host tensors in order, each valid until the
+        second-next result is requested.  The H2D copy of batch i+1 (copy stream), the backbone of batch i
+        (current stream) and the D2H read of batch i-1 (second copy stream) overlap; every batch still pays its own copies.
+        No recurrent state is carried (h = 0 per batch, as in the reference's per-sequence reset, main_utils.py:94-98)."""
+        from collections import deque
+
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        slots, pending, h = [], deque(), None
+        fused = self.use_fused and not self.training
+
+        def take(item):
+            ev, slot, batch = item
+            ev.synchronize()
+            flow, cls = slot["host"]
+            if fused and bool(torch.isnan(flow.view(-1)[0])):      # the fp16-range guard fired: that step was poisoned on the device
+                out = self._fused_engine().run_checked(*[x.to(dev) for x in batch], h)
+                flow.copy_(out[0])
+                cls.copy_(out[2])
+            return flow, cls
+
+        for i, batch in enumerate(batches):
+            if len(slots) < depth + 2:
+                slots.append({"dev": [torch.empty(x.shape, dtype=torch.float32, device=dev) for x in batch], "host": None,
+                              "free": None})
+            slot = slots[i % (depth + 2)]
+            if h is None:
+                h = torch.zeros(5, batch[0].size(0), 128, device=dev)
+            with torch.cuda.stream(s_in):
+                if slot["free"] is not None:
+                    s_in.wait_event(slot["free"])               # the forward that last read these device buffers is done
+                for d, x in zip(slot["dev"], batch):
+                    d.copy_(x, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            main.wait_event(ev_in)
+            out = self.backbone(*slot["dev"], h)
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record(main)
+            if slot["host"] is None:
+                slot["host"] = (torch.empty(out[0].shape, dtype=torch.float32).pin_memory(),
+                                torch.empty(out[2].shape, dtype=torch.float32).pin_memory())
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(slot["free"])
+                slot["host"][0].copy_(out[0], non_blocking=True)
+                slot["host"][1].copy_(out[2], non_blocking=True)
+                out[0].record_stream(s_out)
+                out[2].record_stream(s_out)
+                ev_out = torch.cuda.Event()
+                ev_out.record(s_out)
+            pending.append((ev_out, slot, batch))
+            if len(pending) > depth:
+                yield take(pending.popleft())
+        while pending:
+            yield take(pending.popleft())
 
     @staticmethod
     def fused_available():

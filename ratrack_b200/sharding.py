@@ -64,3 +64,75 @@ def allreduce_gradients(params, average: bool = True, group=None):
             p.grad.copy_(g)
         off += n
     return off
+
+
+class GradBuckets:
+    """Gradient reduction that starts before backward has finished.  The parameters are split into flat fp32 buckets in
+    the order their gradients become final during backward (the decoder / cost-volume parameters first, pn_head -- the
+    first module of the forward pass -- last); a post-accumulate-grad hook counts arrivals and issues the bucket's
+    all_reduce (async) the moment its last gradient lands, so the decoder bucket travels while pn_head is still being
+    differentiated.  `finish()` issues what is left, waits, averages and writes the reduced values back to `.grad`.
+    Same result as `allreduce_gradients` (one bucket after backward); replaces the reference's nn.DataParallel gather
+    (reference: src/models/model.py:38-40)."""
+
+    def __init__(self, module, late_prefixes=("pn_head.",), group=None, average=True):
+        self.group, self.average = group, average
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        late = [p for n, p in named if n.startswith(tuple(late_prefixes))]
+        early = [p for n, p in named if not n.startswith(tuple(late_prefixes))]
+        self.buckets = [b for b in (early, late) if b]
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._owner = {}
+        self._hooks = []
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._owner[p] = bi
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._arrived))
+        self.reset()
+
+    def reset(self):
+        self._seen = [0] * len(self.buckets)
+        self._flat = [None] * len(self.buckets)
+        self._work = [None] * len(self.buckets)
+
+    def _launch(self, bi):
+        bucket = self.buckets[bi]
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        self._flat[bi] = flat
+        if self.world > 1:
+            self._work[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _arrived(self, p):
+        bi = self._owner[p]
+        self._seen[bi] += 1
+        if self._seen[bi] == len(self.buckets[bi]) and self._flat[bi] is None:
+            self._launch(bi)
+
+    def finish(self):
+        """-> number of gradient elements reduced."""
+        total = 0
+        for bi, bucket in enumerate(self.buckets):
+            if self._flat[bi] is None:        # some parameter of the bucket got no gradient this step
+                self._launch(bi)
+            if self._work[bi] is not None:
+                self._work[bi].wait()
+            flat = self._flat[bi]
+            if self.average and self.world > 1:
+                flat /= self.world
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                g = flat[off: off + n].view_as(p).to(p.dtype)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
+            total += off
+        self.reset()
+        return total
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import association
+from . import _cabi, association
 from .model_utils import Track4DBackbone
 
 
@@ -124,7 +124,15 @@ class Track4D(Track4DBackbone):
         indices1 = None
         confs = []
         if m > 0 and n > 0:
-            indices1 = self.sinkhorn_module(aff_mat, indices1)
+            try:
+                indices1 = self.sinkhorn_module(aff_mat, indices1)
+            except _cabi.RatrackError:
+                # the reference wraps the association in try/except and hands out fresh ids on any failure (:143-160)
+                for obj in objects_curr:
+                    objects[self.max_id] = obj
+                    self.max_id += 1
+                    confs.append(0)
+                return aff_list, aff_mat, None, confs
             idx = indices1[0]
             conf_all = aff_mat[0, idx.clamp(min=0), torch.arange(n, device=aff_mat.device)]
             idx_h, conf_h = idx.cpu().tolist(), conf_all.detach().cpu().tolist()      # the frame's one device->host read

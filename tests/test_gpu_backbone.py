@@ -19,18 +19,16 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
 # Tolerances, as a fraction of the tensor's scale: |d| <= TOL * max(1, max|ref|)   (DESIGN.md "Parity").
-# north_star asks 1e-5 abs on the fp32 scene flow.  Measured on B200 (profiles/r1_parity_report.txt):
-#   * the reference's OWN fp32 layers run by torch on the GPU (the modular path: cuDNN/cuBLAS fp32, TF32 off)
-#     differ from the same layers run by torch on the CPU by 0.7-1.8e-4 abs on the flow (|flow| <= 11, i.e.
-#     1.0-1.6e-5 of scale) and by 2-6e-5 on h: the GRU / global-max-pool / BatchNorm chain amplifies 1e-6-level
-#     feature differences, so 1e-5 abs is below the reference's own cross-device noise;
-#   * the fused engine with fp32 SIMT dense layers sits at the same level (flow 1.1-1.7e-5 of scale);
-#   * the default engine evaluates every dense layer on the tensor cores as split-fp16 products (22-bit
-#     operands, fp32 accumulation): per-point features stay within 1e-5 of scale, the amplified outputs land at
-#     4-5e-5 of scale for the flow and 0.9-1.6e-4 abs for h.
-# The per-point feature tensors, which are not amplified, are held to 1e-5 of scale in every mode.
-TOL_FP32 = {"f1": 1e-5, "f2": 1e-5, "cor": 1e-5, "prop": 1.5e-5, "flow": 3e-5, "h": 1.5e-4, "cls": 3e-5}   # modular + SIMT engine
-TOL_TC = {"f1": 1e-5, "f2": 1e-5, "cor": 1e-5, "prop": 3.5e-5, "flow": 8e-5, "h": 2.5e-4, "cls": 5e-5}     # tcgen05 engine
+# north_star asks 1e-5 abs on the fp32 scene flow.  Measured on B200 (tests/test_gpu_parity_floor.py measures it on
+# every run; one run is committed as profiles/r2_parity_floor.txt):
+#   * the reference's OWN GPU arithmetic (its unmodified CUDA kernels + torch fp32 cuDNN/cuBLAS layers, TF32 off)
+#     differs from the same layers on the CPU by 0.8-1.7e-4 abs on the flow (|flow| <= 11), 2-4e-5 on h and
+#     1.1e-5 abs on the per-point features: the GRU / global-max-pool / BatchNorm chain amplifies 1e-6-level
+#     differences, so 1e-5 abs on the flow is below the reference's own cross-device noise;
+#   * every mode of the product -- modular, fp32 SIMT engine and the default tcgen05 engine (split-fp16 products with
+#     the correction terms accumulated first, tools/tc_precision.cu) -- is held to ONE table, set from that floor.
+TOL_FP32 = {"f1": 1e-5, "f2": 1e-5, "cor": 1e-5, "prop": 1.5e-5, "flow": 3e-5, "h": 1.5e-4, "cls": 3e-5}
+TOL_TC = TOL_FP32      # no separate, looser table for the tensor-core engine
 TOL = TOL_TC
 
 
@@ -194,3 +192,68 @@ def test_two_lanes_equal_one_lane():
         eng.check_status()
     for a, b in zip(outs[False], outs[True]):
         assert torch.equal(a, b)
+
+
+def test_fp16_range_guard_is_loud_and_falls_back():
+    """an activation beyond the fp16 hi/lo range must never yield silently saturated outputs on the DEFAULT
+    path.  The step's outputs become NaN on the device, the status arrives without a host sync, and the engine continues
+    on its fp32 SIMT kernels; checked_forward=True re-runs the step at once."""
+    import warnings
+
+    d = synthetic.make_batch(2, 256, seed=3)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    for checked in (False, True):
+        net, _ = _net(True)
+        with torch.no_grad():
+            net.fc_layer.mlp_convs[1].bias.add_(1.0e5)      # cost-volume layer-2 activations ~1e5 > 65504
+        net.refresh_engine()
+        net.checked_forward = checked
+        with torch.no_grad(), warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            first = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)
+            torch.cuda.synchronize()
+            second = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)
+            torch.cuda.synchronize()
+            net.use_fused = False
+            want = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)
+        if checked:
+            assert torch.isfinite(first[0]).all() and torch.isfinite(first[2]).all()
+        else:
+            assert torch.isnan(first[0]).all() and torch.isnan(first[2]).all() and torch.isnan(first[1]).all()
+        assert not net._engine.tensor_cores and any("fp16" in str(x.message) for x in w)
+        assert torch.isfinite(second[0]).all()
+        assert float((second[0] - want[0]).abs().max()) <= 1e-4 * max(1.0, float(want[0].abs().max()))
+
+
+def test_out_of_range_weights_select_the_simt_kernels():
+    import warnings
+
+    net, _ = _net(True)
+    with torch.no_grad():
+        net.fd_layer.cp.sf_mlp[0][0].weight[0, 0] = 1.0e6      # folded: 2^10 * W far beyond 65504
+    net.refresh_engine()
+    d = synthetic.make_batch(1, 256, seed=4)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    with torch.no_grad(), warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        a = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)
+        net.use_fused = False
+        b = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)
+    assert not net._engine.tensor_cores and any("fp16" in str(x.message) for x in w)
+    assert torch.isfinite(a[2]).all() and float((a[2] - b[2]).abs().max()) <= 1e-4
+
+
+def test_engine_snapshot_follows_the_parameters():
+    """load_state_dict / .to() after an eval forward must not leave the folded-weight snapshot behind."""
+    net, sd = _net(True)
+    d = synthetic.make_batch(1, 256, seed=5)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    with torch.no_grad():
+        a = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)[0].clone()
+        sd2 = {k: (v * 1.25 if k.endswith("pn_head.linear3.weight") else v) for k, v in net.state_dict().items()}
+        net.load_state_dict(sd2)
+        b = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)[0].clone()
+        net.use_fused = False
+        want = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)[0]
+    assert float((a - b).abs().max()) > 1e-3
+    assert float((b - want).abs().max()) <= TOL["flow"] * max(1.0, float(want.abs().max()))

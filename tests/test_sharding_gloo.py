@@ -93,6 +93,22 @@ def _train_worker(rank, world, port, q):
     got = [p.grad.clone() for p in lin.parameters()]
     trk_val = float(trk)
 
+    # the same step with the synchronisation-free affinity all_gather (fixed-width blocks) and the bucketed gradient
+    # reduction that starts inside backward: must give the same loss value and the same gradients
+    lin.zero_grad()
+    holder = torch.nn.Module()
+    holder.pn_head = lin                                # "late" bucket
+    holder.extra = torch.nn.Linear(2, 2)               # "early" bucket, one parameter of which never gets a gradient
+    buckets = sharding.GradBuckets(holder)
+    total2, trk2 = terms(x[start:start + count], gt_flow[start:start + count], gt_cls[start:start + count],
+                         aff_in[a0:a0 + n_aff[rank]], aff_gt[a0:a0 + n_aff[rank]],
+                         lambda a, g: losses.sharded_affinity_loss(a, g, max_entries=8))
+    (total2 + 0.0 * holder.extra.weight.sum()).backward()
+    n2 = buckets.finish()
+    buckets.remove()
+    same = abs(float(trk2) - trk_val) < 1e-6 and n2 == n + 6 and all(
+        bool(torch.allclose(g, p.grad, rtol=1e-6, atol=1e-7)) for g, p in zip(got, lin.parameters()))
+
     lin.zero_grad()
     ref_total = 0.0
     for r in range(world):
@@ -102,7 +118,7 @@ def _train_worker(rank, world, port, q):
                                  losses.motion_seg_loss(torch.sigmoid(y[..., 3]), gt_cls[s:s + c])) / world
     ref_trk = losses.affinity_loss(torch.sigmoid(lin(aff_in)[:, 0]), aff_gt)   # ONE mean over all entries
     (ref_total + 0.5 * ref_trk).backward()
-    ok = n == sum(p.numel() for p in lin.parameters()) and abs(trk_val - float(ref_trk)) < 1e-6
+    ok = same and n == sum(p.numel() for p in lin.parameters()) and abs(trk_val - float(ref_trk)) < 1e-6
     for g, p in zip(got, lin.parameters()):
         ok = ok and bool(torch.allclose(g, p.grad, rtol=1e-5, atol=1e-6))
     dist.barrier()

@@ -8,6 +8,9 @@
 //   S3  S2 with the main product split into two K halves (two accumulators)
 //   S4  S2 + lo*lo
 //   S5  S2 with the main product in four K quarters
+//   S6  lo planes stored as 2^11 * lo (never subnormal in fp16), corrections first, then the FIRST main MMA rescales the
+//       accumulator with the instruction's scale-input-d operand: D = A*B + D * 2^-11 -- one accumulator, no extra MMAs
+//   S7  S6 with the main product in two K halves (second accumulator)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -85,6 +88,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 
 constexpr int M = 128, N = 64, K = 256;
+__device__ __forceinline__ void mma_ss_scale11(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
 __host__ __device__ inline int core_off(int r, int k, int R) { return ((k / 8) * (R / 8) + r / 8) * 64 + (r % 8) * 8 + (k % 8); }
 
 __global__ void __launch_bounds__(192) prec_kernel(int strat, const float *A, const float *B, float *D, int *err) {
@@ -100,13 +107,13 @@ __global__ void __launch_bounds__(192) prec_kernel(int strat, const float *A, co
         const float x = A[i];
         const __half h = __float2half_rn(x);
         sAh[core_off(i / K, i % K, M)] = h;
-        sAl[core_off(i / K, i % K, M)] = __float2half_rn(x - __half2float(h));
+        sAl[core_off(i / K, i % K, M)] = __float2half_rn((x - __half2float(h)) * (strat >= 6 ? 2048.0f : 1.0f));
     }
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
         const float x = B[i] * 1024.0f;
         const __half h = __float2half_rn(x);
         sBh[core_off(i / K, i % K, N)] = h;
-        sBl[core_off(i / K, i % K, N)] = __float2half_rn(x - __half2float(h));
+        sBl[core_off(i / K, i % K, N)] = __float2half_rn((x - __half2float(h)) * (strat >= 6 ? 2048.0f : 1.0f));
     }
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -137,6 +144,15 @@ __global__ void __launch_bounds__(192) prec_kernel(int strat, const float *A, co
                     mma_ss(tm, dA(sAh, k), dB(sBl, k), idesc, 1);
                 }
                 for (int k = 0; k < KS; ++k) mma_ss(tm, dA(sAh, k), dB(sBh, k), idesc, 1);
+            } else if (strat >= 6) {
+                for (int k = 0; k < KS; ++k) {
+                    mma_ss(tm, dA(sAl, k), dB(sBh, k), idesc, k > 0);
+                    mma_ss(tm, dA(sAh, k), dB(sBl, k), idesc, 1);
+                }
+                mma_ss_scale11(tm, dA(sAh, 0), dB(sBh, 0), idesc);
+                const int kend = strat == 7 ? KS / 2 : KS;
+                for (int k = 1; k < kend; ++k) mma_ss(tm, dA(sAh, k), dB(sBh, k), idesc, 1);
+                for (int k = kend; k < KS; ++k) mma_ss(tm + 128, dA(sAh, k), dB(sBh, k), idesc, k > kend);
             } else {
                 const int parts = strat == 3 ? 2 : (strat == 5 ? 4 : 1);
                 for (int k = 0; k < KS; ++k) {
@@ -163,7 +179,10 @@ __global__ void __launch_bounds__(192) prec_kernel(int strat, const float *A, co
                 tmem_ld32(tm + lb + c0, r);
                 float v[32];
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (strat >= 2) {
+                if (strat == 7) {
+                    tmem_ld32(tm + lb + 128 + c0, c);
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(c[j]);
+                } else if (strat >= 2 && strat < 6) {
                     const int parts = strat == 3 ? 2 : (strat == 5 ? 4 : 1);
                     for (int p = 1; p < parts; ++p) {
                         tmem_ld32(tm + lb + 64 + 64 * p + c0, c);
@@ -227,8 +246,8 @@ int main() {
         };
         report("fp32 fmaf chain (host)", simt);
         CK(cudaMemcpy(dA, hA, M * K * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB, N * K * 4, cudaMemcpyHostToDevice));
-        const char *names[6] = {"S0 interleaved", "S1 corrections first", "S2 separate corr acc", "S3 S2 + main in 2 halves", "S4 S2 + lo*lo", "S5 S2 + main in 4 quarters"};
-        for (int s = 0; s < 6; ++s) {
+        const char *names[8] = {"S0 interleaved", "S1 corrections first", "S2 separate corr acc", "S3 S2 + main in 2 halves", "S4 S2 + lo*lo", "S5 S2 + main in 4 quarters", "S6 scaled lo + scale-input-d", "S7 S6 + main in 2 halves"};
+        for (int s = 0; s < 8; ++s) {
             CK(cudaMemset(dD, 0xff, M * N * 4)); CK(cudaMemset(dErr, 0, 4));
             prec_kernel<<<1, 192, 196608>>>(s, dA, dB, dD, dErr);
             cudaError_t e = cudaDeviceSynchronize();
