@@ -10,9 +10,9 @@
 //   layer 2/3 = tcgen05.mma kind::f16, M128 N256 K16, accumulator in TMEM columns [0,256); A operand read from
 //               TMEM columns [256,512); B operand (weights) streamed by the bulk-copy engine (UBLKCP) through a
 //               4-stage shared-memory ring in the canonical K-major core-matrix layout (pre-packed on the host);
-//   precision = every fp32 operand x is split x = hi + lo (two fp16 planes, weights pre-scaled by 2^10) and each
-//               product is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation: ~2^-22 relative per product,
-//               i.e. fp32-class results (north_star tolerance) at 1/3 of the fp16 tensor rate;
+//   precision = every fp32 operand x is split x = hi + 2^-11 lo' (two fp16 planes, weights pre-scaled by 2^10) and each
+//               product is evaluated as (lo'*hi + hi*lo') * 2^-11 + hi*hi with fp32 accumulation, corrections first
+//               (tools/tc_precision.cu: the rms error of an fp32 FMA chain x 1.7) at 1/3 of the fp16 tensor rate;
 //   WeightNet = its last layer (8 -> 256) is a K=16 MMA whose accumulator lands on the dead A columns;
 //   epilogue  = bias + LeakyReLU, weight, and a 16-lane butterfly that leaves the neighbour sum in registers.
 // TMEM (512 columns) is exactly full: 256 accumulator + 128 A_hi + 128 A_lo, so a tile's MMA and epilogue phases
@@ -91,6 +91,15 @@ __device__ __forceinline__ void ct_mma_ts(uint32_t d, uint32_t a, uint64_t b, ui
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// D = A*B + D * 2^-11 (scale-input-d): folds the 2^11 of the scaled lo planes back when the main products start
+__device__ __forceinline__ void ct_mma_ts_rescale(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void ct_mma_ss_rescale(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void ct_ld32(uint32_t taddr, uint32_t *r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -129,12 +138,12 @@ __device__ __forceinline__ float2 leaky01x2(float2 v) {
     return make_float2(fmaxf(v.x, m.x), fmaxf(v.y, m.y));
 }
 
-// x = hi + lo with two fp16 (x0 in the low half: K even)
+// x = hi + 2^-11 * lo' with two fp16 (x0 in the low half: K even)
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo, float &amax) {
     amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);   // lo plane stored as 2^11 * lo: normal whenever hi is
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -274,9 +283,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         ct_mbar_wait(&bar_full[stage], phase);
                         ct_fence_after();
                         const uint32_t base = rt_smem_u32(s_stage + stage * CT_STAGE_BYTES);
-                        // Correction products first (lo*hi + hi*lo over all of K), main products (hi*hi) last: the tensor
-                        // core truncates the fp32 accumulator after every k-step, so the number of accumulation steps taken
-                        // at full magnitude sets the error (tools/tc_precision.cu: 3x smaller rms than interleaving).
+                        // Correction products first (lo*hi + hi*lo over all of K, carrying the 2^11 of the scaled lo planes),
+                        // main products (hi*hi) last, the first of them rescaling the partial sum by 2^-11: the tensor core
+                        // truncates the fp32 accumulator after every k-step, so the number of accumulation steps taken at
+                        // full magnitude sets the error (tools/tc_precision.cu: 3x smaller rms than interleaving).
 #pragma unroll
                         for (int j = 0; j < CT_KC / 16; ++j) {
                             const int kk = g * (CT_KC / 16) + j;
@@ -296,7 +306,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
 #pragma unroll
                         for (int j = 0; j < 2 * (CT_KC / 16); ++j) {
                             const int kk = 2 * c * (CT_KC / 16) + j;   // the stage holds the hi planes of K chunks 2c, 2c+1 back to back
-                            ct_mma_ts(tD, tAhi + 8 * kk, ct_desc(base + j * 8192, 4096, 128), CT_IDESC, 1);
+                            if (kk == 0) ct_mma_ts_rescale(tD, tAhi, ct_desc(base, 4096, 128), CT_IDESC);   // D = A*B + D * 2^-11
+                            else ct_mma_ts(tD, tAhi + 8 * kk, ct_desc(base + j * 8192, 4096, 128), CT_IDESC, 1);
                         }
                         ct_commit(&bar_empty[stage]);
                         if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         // tcgen05.mma executes in issue order)
                         ct_mma_ss(tW, ct_desc(aw_lo, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 0);
                         ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_lo, 4096, 128), CT_IDESC, 1);
-                        ct_mma_ss(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC, 1);
+                        ct_mma_ss_rescale(tW, ct_desc(aw_hi, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC);
                     }
                     ct_commit(bar_d);
                     a_phase ^= 1;

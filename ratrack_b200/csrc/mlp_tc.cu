@@ -22,6 +22,9 @@ namespace {
 constexpr int MT_WORKER_WARPS = 8;   // two per TMEM lane quarter: they split the 16-column chunks of a row between them
 constexpr int MT_THREADS = 32 * (MT_WORKER_WARPS + 1);
 constexpr float MT_WINV = 1.0f / 1024.0f;
+// x = hi + lo with two fp16 planes; the lo plane is stored as 2^11 * lo so that it is a NORMAL fp16 number whenever hi is
+// (an unscaled lo of an activation below 0.25 is subnormal and loses up to 10 bits: tools/tc_precision.cu, data set 2)
+constexpr float MT_LO_SCALE = 2048.0f;
 
 __device__ __forceinline__ void mt_mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = rt_smem_u32(bar);
@@ -48,6 +51,11 @@ __device__ __forceinline__ void mt_commit(uint64_t *bar) {
 __device__ __forceinline__ void mt_mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// D = A*B + D * 2^-11 (the instruction's scale-input-d operand): folds the 2^11 scaling of the correction products back
+__device__ __forceinline__ void mt_mma_ts_rescale(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void mt_ld16(uint32_t taddr, uint32_t *r) {
     asm volatile(
@@ -78,7 +86,7 @@ __device__ __forceinline__ void mt_split2(float x0, float x1, uint32_t &hi, uint
     const __half2 h = __floats2half2_rn(x0, x1);
     amax = __hmax2(amax, __habs2(h));
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    const __half2 l = __floats2half2_rn((x0 - hf.x) * MT_LO_SCALE, (x1 - hf.y) * MT_LO_SCALE);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
     __syncthreads();
     mt_fence_after();
     const uint32_t tm = tmem_slot;
-    const uint32_t tD = tm, tAhi = tm + a.d_cols, tAlo = tAhi + a.a_cols;
+    const uint32_t tD = tm, tAhi = tm + a.nsplit * a.d_cols, tAlo = tAhi + a.a_cols;
 
     if (warp == MT_WORKER_WARPS) {
         // ===== MMA issuer =====
@@ -204,15 +212,23 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                     const uint32_t hi_base = rt_smem_u32(smem + w_off[l]), lo_base = hi_base + 2 * k * n;
                     const uint32_t idesc = mt_idesc(n);
                     // Issue order matters for accuracy: the tensor core TRUNCATES the fp32 accumulator after every
-                    // k-step (measured, tools/tc_precision.cu: error grows with the number of accumulation steps taken
-                    // at full magnitude and is biased toward zero).  The small correction products go first, while the
-                    // accumulator is ~2^-11 of its final size, the k/16 main products last.
-                    for (int kk = 0; kk < k / 16; ++kk) {
+                    // k-step (measured, tools/tc_precision.cu: the error grows with the number of accumulation steps taken
+                    // at full magnitude and is biased toward zero).  So: (1) the correction products lo*hi + hi*lo first,
+                    // both carrying the 2^11 of the scaled lo planes; (2) the first main product rescales that partial sum
+                    // with scale-input-d (D = A*B + D * 2^-11); (3) the remaining k/16 - 1 main products.  With a second
+                    // accumulator (a.nsplit == 2) the second half of K accumulates separately and the epilogue adds the two
+                    // in fp32 round-to-nearest: half as many truncations at full magnitude.
+                    const int ksteps = k / 16;
+                    const int khalf = (a.nsplit == 2 && ksteps >= 4) ? ksteps / 2 : ksteps;
+                    for (int kk = 0; kk < ksteps; ++kk) {
                         mt_mma_ts(tD, tAlo + 8 * kk, mt_desc(hi_base + kk * 2 * lbo, lbo, 128), idesc, kk > 0);
                         mt_mma_ts(tD, tAhi + 8 * kk, mt_desc(lo_base + kk * 2 * lbo, lbo, 128), idesc, 1);
                     }
-                    for (int kk = 0; kk < k / 16; ++kk)
+                    mt_mma_ts_rescale(tD, tAhi, mt_desc(hi_base, lbo, 128), idesc);
+                    for (int kk = 1; kk < khalf; ++kk)
                         mt_mma_ts(tD, tAhi + 8 * kk, mt_desc(hi_base + kk * 2 * lbo, lbo, 128), idesc, 1);
+                    for (int kk = khalf; kk < ksteps; ++kk)
+                        mt_mma_ts(tD + a.d_cols, tAhi + 8 * kk, mt_desc(hi_base + kk * 2 * lbo, lbo, 128), idesc, kk > khalf);
                     mt_commit(&bar_d);
                 }
             }
@@ -346,6 +362,12 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                 for (int c0 = 16 * hlf; c0 < n; c0 += 32) {
                     uint32_t r[16];
                     mt_ld16(tD + lane_base + c0, r);
+                    if (a.nsplit == 2 && a.layer[l].k >= 64) {   // second K half accumulated separately (see the issuer)
+                        uint32_t r2[16];
+                        mt_ld16(tD + a.d_cols + lane_base + c0, r2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                    }
                     float v[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -471,6 +493,10 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     RT_REQUIRE(need <= 512, "mlp_tc: %d TMEM columns needed", need);
     int cols = 32;
     while (cols < need) cols *= 2;
+    // a second accumulator for the second half of K (accuracy, see the issuer) where it is free: the power-of-two TMEM
+    // allocation already has the room.  The choice depends on the layer shapes only, never on the row count: a pair's
+    // results must not depend on the batch it travels in.
+    a.nsplit = (kmax >= 64 && 2 * dmax + kmax <= cols) ? 2 : 1;
     a.tmem_cols = cols;
     a.d_cols = dmax;
     a.a_cols = kmax / 2;
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(256) pack_umma_kernel(PackArgs a) {
         }
         w *= 1024.0f;
         const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
+        const __half lo = __float2half_rn((w - __half2float(hi)) * MT_LO_SCALE);   // scaled like the activations' lo plane
         // [plane][kc = k/8][rg = n/8][n%8][k%8]
         const size_t off = ((size_t)(k / 8) * (a.n_pad / 8) + n / 8) * 64 + (n % 8) * 8 + (k % 8);
         a.dst[off] = hi;

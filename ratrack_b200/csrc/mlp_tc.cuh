@@ -44,7 +44,7 @@ struct RtMlpTc {
     float *mid_out;            // optional: the (activated) output of layer `mid_layer` (not the last) is also written as fp32 rows,
     int mid_ldo, mid_layer;    //           mid_out[row * mid_ldo + c], c < layer[mid_layer].n -- two chained GEMMs, both results kept
     int *status;               // optional device status word (bit 1: fp16 range exceeded)
-    int tmem_cols, d_cols, a_cols, ns_shift;  // filled by the launcher
+    int tmem_cols, d_cols, a_cols, ns_shift, nsplit;  // filled by the launcher (nsplit: accumulators per layer, 1 or 2)
 };
 int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st);
 

@@ -79,6 +79,7 @@ def _predictor(p):
     return out, p.conv2.weight.detach().flatten(1)
 
 
+LO_SCALE = 2048.0
 W_SCALE = 1024.0  # costvol_tc.cu: weights enter the tensor core as 2^10 * W (keeps the fp16 `lo` plane normal)
 
 
@@ -89,7 +90,7 @@ def _umma_planes(w, k_chunk):
     assert n % 8 == 0 and k % k_chunk == 0 and k_chunk % 8 == 0
     w = w.float() * W_SCALE
     hi = w.half()
-    lo = (w - hi.float()).half()
+    lo = ((w - hi.float()) * LO_SCALE).half()     # lo plane stored as 2^11 * lo (costvol_tc.cu / mlp_tc.cu: scale-input-d)
 
     def lay(x):
         return x.reshape(n // 8, 8, k // k_chunk, k_chunk // 8, 8).permute(2, 3, 0, 1, 4)

@@ -48,7 +48,7 @@ def test_umma_planes_hold_the_weights_to_22_bits_in_core_matrix_order():
     assert p.shape == (1, 2, 4, 2, 8, 8) and p.dtype == torch.float16
     hi, lo = p[0, 0].float(), p[0, 1].float()
     for n, k in ((0, 0), (3, 9), (15, 31), (8, 16)):
-        v = hi[k // 8, n // 8, n % 8, k % 8] + lo[k // 8, n // 8, n % 8, k % 8]
+        v = hi[k // 8, n // 8, n % 8, k % 8] + lo[k // 8, n // 8, n % 8, k % 8] / engine.LO_SCALE   # lo plane is stored x 2^11
         assert abs(float(v) - float(w[n, k]) * engine.W_SCALE) <= abs(float(w[n, k])) * engine.W_SCALE * 2 ** -20
     wc = engine.pack_weightnet_last(torch.randn(256, 8))
     assert wc.shape == (2, 2, 32, 8, 8)                                # K padded 8 -> 16
