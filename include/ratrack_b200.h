@@ -115,12 +115,13 @@ long long rt_engine_workspace_bytes(const rt_engine *e, int b, int n);
  * cost-volume MLP) of every forward; pass NULL, NULL to disable */
 int rt_engine_set_profile_events(rt_engine *e, void *start_event, void *stop_event);
 
-/* flags (default 59 = bits 0,1,3,4,5): bit 0 = cost volume on the tcgen05 tensor-core kernel, bit 1 = every other dense layer on the
+/* flags (default 571 = bits 0,1,3,4,5,9): bit 0 = cost volume on the tcgen05 tensor-core kernel, bit 1 = every other dense layer on the
  * tcgen05 MLP kernel; cleared bits select the fp32 SIMT kernels of the same dataflow (A/B parity of the split-fp16
  * arithmetic).  Scheduling bits, all bit-identical in their results: bit 2 = split batches of >= 8 pairs over two concurrent lanes
  * (stream sets); bit 3 = every FPS CTA claims a whole SM; bit 4 = the cost-volume kNN starts beside the FPS chain; bit 5 = the
  * feature path runs on an engine-owned stream of middle priority; bit 6 = Morton-ordered cost-volume tiles; bit 7 = two clouds per
- * FPS CTA; bit 8 = self-kNN deferred behind the SA levels.  RT_ENGINE_FLAGS in the environment overrides the default at creation. */
+ * FPS CTA; bit 8 = self-kNN deferred behind the SA levels; bit 9 = FPS levels 2/3 by the parallel identity check where it
+ * proves the serial sampler's result.  RT_ENGINE_FLAGS in the environment overrides the default at creation. */
 int rt_engine_set_flags(rt_engine *e, int flags);
 
 /* how many lanes rt_backbone_forward will use for a batch of b pairs (1 or 2); lane 0 gets ceil(b/2) pairs */

@@ -53,14 +53,14 @@ def opt_n_threads(n: int) -> int:
     return lib().orc_opt_n_threads(int(n))
 
 
-def furthest_point_sample(xyz, npoint):
-    """xyz (B,N,3) -> idx (B,npoint) int32.  pointnet2_utils.py:10-36"""
+def furthest_point_sample(xyz, npoint, return_temp=False):
+    """xyz (B,N,3) -> idx (B,npoint) int32 [, temp (B,N): the running minimum the kernel leaves behind].  pointnet2_utils.py:10-36"""
     xyz, px = _f(xyz)
     B, N, _ = xyz.shape
     temp, pt = _f(np.full((B, N), 1e10, dtype=np.float32))
     idx = np.zeros((B, npoint), dtype=np.int32)  # the reference leaves it uninitialised; kernel writes all
     lib().orc_furthest_point_sampling(B, N, int(npoint), px, pt, idx.ctypes.data_as(_I))
-    return idx
+    return (idx, temp) if return_temp else idx
 
 
 def gather_operation(features, idx):

@@ -19,6 +19,9 @@
 #include "mlp_tc.cuh"
 
 void rt_fps_set_exclusive(int on);  // fps.cu
+void rt_fps_set_skip(const int *flags);
+int rt_launch_fps_identity(int b, int n, const float *xyz, float *temp, int *ok, int *idx_a, float *xyz_a, int *idx_b, float *xyz_b,
+                           cudaStream_t st);
 int rt_launch_costvol_mlp(int rows, const float *x1, const float *w2, const float *b2, const float *w3, const float *b3,
                           float *xa, float *xb, cudaStream_t st);  // engine-internal, below
 // costvol_tc.cu: gather + 3-layer MLP + WeightNet-weighted neighbour sum on tcgen05
@@ -87,7 +90,7 @@ struct Carver {
 
 struct Ws {
     float *xyz0, *ft0, *xyz[3], *temp;
-    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11, *perm1;
+    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11, *perm1, *fps_ok;
     float *nn_w[3];
     float *proj, *xa, *xb, *pooled, *l1, *l2, *l3, *l2p, *l1p, *interp, *feat, *prop;
     float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h, *gru_gh;
@@ -101,6 +104,7 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     for (int l = 0; l < 3; ++l) w.xyz[l] = c.take<float>(B2 * S * 3);
     w.temp = c.take<float>(3 * B2 * (size_t)max(n, S));   // one FPS scratch per level
     for (int l = 0; l < 3; ++l) w.fps[l] = c.take<int>(B2 * S);
+    w.fps_ok = c.take<int>(B2);
     for (int l = 0; l < 3; ++l)
         for (int s = 0; s < 2; ++s) w.bq[l][s] = c.take<int>(B2 * S * kLevels[l].ns[s]);
     // three_nn of FP3 (xyz2 <- xyz3), FP2 (xyz1 <- xyz2), FP1 (xyz0 <- xyz1)
@@ -193,13 +197,14 @@ struct rt_engine {
     long long launches = 0;
     Lane lanes[2];
     cudaEvent_t ev_fork = nullptr;
-    int flags = 59;                // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
+    int flags = 571;               // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
                                    // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow;
                                    // bit 2 (off by default: measured 4 % slower at 32 pairs, neutral at 128): split batches of >= 8 pairs over two lanes
                                    // bit 3: FPS CTAs claim a whole SM each (fps.cu launch_reg) so co-running kernels cannot stretch the chain
                                    // bit 4: cost-volume kNN starts with the FPS chain instead of behind it (pair with bit 3)
                                    // bit 7: with bit 3, two clouds share one FPS CTA (2b clouds block b SMs instead of 2b)
                                    // bit 6: the cost-volume kernels walk pc1 in Morton order (tiles of spatial neighbours share gathered rows)
+                                   // bit 9: FPS levels 2 / 3 take the identity shortcut where fps_identity_kernel proves it (fps.cu)
                                    // bit 5: the feature path runs on an engine-owned stream of middle priority (geometry above it, kNN
                                    //        and API-layout outputs below it) forked from / joined to the caller's stream
     const int *last_status[2] = {nullptr, nullptr};
@@ -251,9 +256,19 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
         e->launches += 2;
     }
     rt_fps_set_exclusive(((e->flags & 8) ? 1 : 0) | ((e->flags & 128) ? 2 : 0));
+    // Levels 2 and 3 sample S of the S points level 1 selected: the identity permutation unless a round ties, which
+    // fps_identity_kernel checks exactly (fps.cu).  Clouds that pass are skipped by the serial sampler of both levels:
+    // the dependent FPS chain shrinks from 3 x 511 rounds to 511 rounds + one parallel check.
+    const bool identity = (e->flags & 512) != 0 && S >= 128 && S <= 1024;
     for (int l = 0; l < 3; ++l) {
+        if (l == 1 && identity) {
+            RT_TRY(rt_launch_fps_identity(B2, S, w.xyz[0], nullptr, w.fps_ok, w.fps[1], w.xyz[1], w.fps[2], w.xyz[2], s_fps));
+            e->launches += 1;
+        }
+        rt_fps_set_skip(l >= 1 && identity ? w.fps_ok : nullptr);
         // one launch per level on the dependent chain: min-distance init, sampling and the gather of new_xyz are fused
         int rc = rt_launch_fps_fused(B2, lvl_n[l], S, lvl_in[l], w.fps[l], w.xyz[l], s_fps);
+        rt_fps_set_skip(nullptr);
         if (rc == RT_ERR_UNSUPPORTED) {   // cloud too large for the register-resident kernel
             RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
             RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));

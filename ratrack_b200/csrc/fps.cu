@@ -26,6 +26,7 @@ namespace {
 
 int g_fps_exclusive = 0;
 int g_fps_pair = 0;
+const int *g_fps_skip = nullptr;   // per-cloud flags: clouds already served by fps_identity_kernel (their CTAs exit at once)
 constexpr size_t kFpsHogBytes = 226 * 1024;   // + static + the 1 KB per-CTA reserve = the SM's 228 KB: no other CTA fits beside it
 
 __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
@@ -45,7 +46,7 @@ __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
 template <int T, int Q, int PH, bool FUSED, int CPB>
 __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int m, const float *__restrict__ xyz_all,
                                                          float *__restrict__ temp_all, int *__restrict__ idx_all,
-                                                         float *__restrict__ new_xyz_all) {
+                                                         float *__restrict__ new_xyz_all, const int *__restrict__ skip) {
     constexpr int PPT = Q * PH;
     constexpr int NW = (T + 31) / 32;
     constexpr int LOGT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
 
     const int grp = (CPB == 1) ? 0 : (int)threadIdx.x / T;       // which cloud of the CTA this thread works on
     const int cloud = blockIdx.x * CPB + grp;
-    if (cloud >= nclouds) return;                                // whole group leaves together (named barriers are per group)
+    if (cloud >= nclouds || (skip && skip[cloud])) return;       // whole group leaves together (named barriers are per group)
     float *s_xyz = s_xyz_all + (size_t)grp * ((n * 3 + 3) & ~3);
     // exchange slots, as plain pointers computed once (indexing the 3-D array inside the round loop made the compiler
     // re-derive the address behind a branch every round: +75 cycles per round)
@@ -370,7 +371,7 @@ int launch_reg3(int b, int n, int m, const float *xyz, float *temp, int *idx, fl
         }
         attr.mark(rt_current_device());
     }
-    fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n, m, xyz, temp, idx, new_xyz);
+    fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n, m, xyz, temp, idx, new_xyz, g_fps_skip);
     return rt_check_launch("fps_reg_kernel");
 }
 template <int T, int Q, int PH, bool FUSED>
@@ -386,10 +387,95 @@ int launch_reg(int b, int n, int m, const float *xyz, float *temp, int *idx, flo
                    : launch_reg2<T, Q, PH, false>(b, n, m, xyz, temp, idx, nullptr, st);
 }
 
+
+// ---- FPS of a cloud that already IS in FPS order ------------------------------------------------------------------------
+// Levels 2 and 3 of PNHead sample npoint = 512 points out of the 512 points level 1 has just selected, starting again at
+// point 0 (reference: src/utils/model_utils/model_utils.py:397-399, lib/pointnet2_modules.py:30-35).  Let Q_0..Q_{n-1} be a
+// cloud in FPS order and M_j[k] = min(init_k, min_{i<j} d(Q_k, Q_i)) the running distance before round j.  The sampler picks
+// idx[j] = argmax_k M_j[k].  Because Q is in FPS order, Q_j attained that maximum over a SUPERSET of Q when it was selected,
+// with bit-identical distance arithmetic -- so the result is the identity permutation unless another Q_k ties with Q_j at
+// round j and wins the reference's tie-break (lowest (bitrev(k mod bs), k div bs)).  This kernel CHECKS exactly that
+// condition, round by round but for all rounds in parallel (every (k, j) test is independent given the prefix minima):
+//   pass 1   D[k] = M_k[k]                       (what candidate k holds at the round it must win)
+//   pass 2   for j < k: M_j[k] < D[j], or M_j[k] == D[j] and k loses the tie-break to j     (k not yet selected)
+//            for j > k: M_j[k] = 0 <= D[j]; conservatively D[j] > 0 is required (no exhausted / duplicate rounds)
+// A cloud that passes gets idx = 0..n-1 (and new_xyz = xyz, twice when the next level repeats the same question) and its
+// flag set, so the serial sampler (511 dependent rounds, ~146 us) skips it; a cloud that fails is left to the serial kernel.
+// Not a heuristic: where the flag is set the serial kernel would have produced the same indices bit for bit.
+__global__ void __launch_bounds__(1024) fps_identity_kernel(int n, int bs, int logbs, const float *__restrict__ xyz_all,
+                                                            float *__restrict__ temp_all, int *__restrict__ ok_all,
+                                                            int *__restrict__ idx_a, float *__restrict__ xyz_a,
+                                                            int *__restrict__ idx_b, float *__restrict__ xyz_b) {
+    extern __shared__ __align__(16) float s_id[];   // n x 3 coordinates, n diagonal values
+    float *q = s_id, *dg = s_id + 3 * n;
+    __shared__ int s_fail;
+    const int cloud = blockIdx.x, k = threadIdx.x;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    if (k == 0) s_fail = 0;
+    for (int i = k; i < 3 * n; i += blockDim.x) q[i] = xyz[i];
+    __syncthreads();
+    const bool live = k < n;
+    const float px = live ? q[3 * k] : 0.0f, py = live ? q[3 * k + 1] : 0.0f, pz = live ? q[3 * k + 2] : 0.0f;
+    const float init = (temp_all && live) ? temp_all[(size_t)cloud * n + k] : 1e10f;
+    bool fail = false;
+    float m = init;
+    if (live) {
+        for (int i = 0; i < k; ++i) m = fminf(m, rt_sqdist(px, py, pz, q[3 * i], q[3 * i + 1], q[3 * i + 2]));
+        dg[k] = m;
+        // NaN / infinite coordinates, exhausted rounds (duplicates) and a non-standard initial state go to the serial kernel
+        fail = !(fabsf(px) < 1e18f && fabsf(py) < 1e18f && fabsf(pz) < 1e18f) || !(init >= 0.0f) || (k >= 1 && !(m > 0.0f));
+    }
+    __syncthreads();
+    if (live && !fail) {
+        const unsigned pk = (__brev((unsigned)(k & (bs - 1))) >> (32 - logbs)) * 4096u + (unsigned)(k >> logbs);
+        m = init;
+        for (int j = 1; j < k; ++j) {
+            m = fminf(m, rt_sqdist(px, py, pz, q[3 * j - 3], q[3 * j - 2], q[3 * j - 1]));   // M_j[k]
+            const float d = dg[j];
+            if (m >= d) {
+                const unsigned pj = (__brev((unsigned)(j & (bs - 1))) >> (32 - logbs)) * 4096u + (unsigned)(j >> logbs);
+                fail = fail || m > d || pk < pj;
+            }
+        }
+    }
+    if (fail) s_fail = 1;
+    __syncthreads();
+    const bool ok = s_fail == 0;
+    if (k == 0) ok_all[cloud] = ok ? 1 : 0;
+    if (!ok) return;
+    for (int i = k; i < n; i += blockDim.x) {
+        idx_a[(size_t)cloud * n + i] = i;
+        if (idx_b) idx_b[(size_t)cloud * n + i] = i;
+    }
+    for (int i = k; i < 3 * n; i += blockDim.x) {
+        if (xyz_a) xyz_a[(size_t)cloud * n * 3 + i] = q[i];
+        if (xyz_b) xyz_b[(size_t)cloud * n * 3 + i] = q[i];
+    }
+    // what the serial kernel leaves in `temp`: the running minimum after the last round (every point but the last has met itself)
+    if (temp_all && live) temp_all[(size_t)cloud * n + k] = k < n - 1 ? fminf(init, 0.0f) : dg[k];
+}
+
 }  // namespace
 
 // engine-internal: 1 = FPS CTAs claim a whole SM each (see launch_reg)
 void rt_fps_set_exclusive(int on) { g_fps_exclusive = on & 1; g_fps_pair = (on >> 1) & 1; }   // bit 1: two clouds per CTA
+// engine-internal: clouds whose flag is set are skipped by the next register-resident FPS launches (nullptr = none)
+void rt_fps_set_skip(const int *flags) { g_fps_skip = flags; }
+
+// engine-internal: identity test of FPS(n points -> n samples) for clouds already in FPS order (see fps_identity_kernel).
+// ok (b) flags; idx_a / xyz_a (and optionally idx_b / xyz_b for a second identical level) are written for the clouds that pass.
+// temp: the caller's running-minimum buffer (C ABI) or nullptr for the reference's initial 1e10.
+int rt_launch_fps_identity(int b, int n, const float *xyz, float *temp, int *ok, int *idx_a, float *xyz_a, int *idx_b, float *xyz_b,
+                           cudaStream_t st) {
+    if (b == 0) return RT_OK;
+    RT_REQUIRE(n >= 32 && n <= 1024, "fps_identity: n=%d", n);
+    const int bs = rt_ref_block_size(n);
+    int logbs = 0;
+    while ((1 << logbs) < bs) ++logbs;
+    const int threads = (n + 31) / 32 * 32;
+    fps_identity_kernel<<<b, threads, (size_t)4 * n * sizeof(float), st>>>(n, bs, logbs, xyz, temp, ok, idx_a, xyz_a, idx_b, xyz_b);
+    return rt_check_launch("fps_identity_kernel");
+}
 
 // register-resident variants; returns 1 when one was launched, 0 when the shape needs the generic kernel, < 0 / > 0 on error
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st, int *launched) {
@@ -401,7 +487,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         const char *env = getenv("RT_FPS_WARP");
         use_warp = (env && atoi(env) == 1) ? 1 : 0;
     }
-    if (use_warp) {
+    if (use_warp && !g_fps_skip) {
         const int rc = new_xyz ? launch_warp<true>(b, n, m, xyz, temp, idx, new_xyz, st, launched)
                                : launch_warp<false>(b, n, m, xyz, temp, idx, nullptr, st, launched);
         if (rc != RT_OK || *launched) return rc;
@@ -454,8 +540,28 @@ RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, flo
     if (m <= 0 || b == 0) return RT_OK;  // reference kernel returns early on m <= 0
     cudaStream_t st = (cudaStream_t)stream;
     int launched = 0;
+    // sampling ALL points of a cloud (the second and third set-abstraction levels: 512 of 512) is the identity whenever the
+    // cloud is already in FPS order and no round ties -- checked exactly by fps_identity_kernel; clouds that fail the check
+    // (and every other shape) take the serial kernel
+    int *ok = nullptr;
+    if (m == n && n >= 128 && n <= 1024 && b <= 65535) {
+        if (cudaMallocAsync(&ok, sizeof(int) * (size_t)b, st) == cudaSuccess) {
+            const int rc0 = rt_launch_fps_identity(b, n, xyz, temp, ok, idx, nullptr, nullptr, nullptr, st);
+            if (rc0 != RT_OK) {
+                cudaFreeAsync(ok, st);
+                return rc0;
+            }
+        } else {
+            ok = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
+    g_fps_skip = ok;
     const int rc = fps_dispatch(b, n, m, xyz, temp, idx, nullptr, st, &launched);
+    g_fps_skip = nullptr;
+    if (ok) cudaFreeAsync(ok, st);
     if (rc != RT_OK || launched) return rc;
+    RT_REQUIRE(!ok, "furthest_point_sampling: internal (identity shortcut without a register-resident kernel)");
     const int bs = rt_ref_block_size(n);
     int logbs = 0;
     while ((1 << logbs) < bs) ++logbs;

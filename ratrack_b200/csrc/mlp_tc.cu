@@ -13,6 +13,7 @@
 //   output    = MT_OUT_ROWS: fp32 rows, or MT_OUT_MAXPOOL: max over the ns consecutive rows of a centre
 //               (reference: F.max_pool2d over nsample, src/lib/pointnet2_modules.py:42-44) by warp shuffles.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "engine_kernels.cuh"
 #include "mlp_tc.cuh"
@@ -26,6 +27,9 @@ constexpr float MT_WINV = 1.0f / 1024.0f;
 // (an unscaled lo of an activation below 0.25 is subnormal and loses up to 10 bits: tools/tc_precision.cu, data set 2)
 constexpr float MT_LO_SCALE = 2048.0f;
 
+// A failed probe backs off with nanosleep: a spinning warp otherwise burns issue slots of the SM sub-partition it shares
+// with the warps (of this and the co-resident CTAs) that have work -- ncu counted a third of this kernel's issued
+// instructions in these loops (profiles/r1_ncu_mlp_tc_sa3.txt: ISETP + BRA + SYNCS + YIELD).
 __device__ __forceinline__ void mt_mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = rt_smem_u32(bar);
     for (uint32_t it = 0;; ++it) {
@@ -33,7 +37,8 @@ __device__ __forceinline__ void mt_mbar_wait(uint64_t *bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
-        if (it > (1u << 24)) __trap();
+        __nanosleep(it < 4 ? 32 : 96);
+        if (it > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void mt_tmem_alloc(uint32_t *slot, uint32_t ncols) {
@@ -86,7 +91,9 @@ __device__ __forceinline__ void mt_split2(float x0, float x1, uint32_t &hi, uint
     const __half2 h = __floats2half2_rn(x0, x1);
     amax = __hmax2(amax, __habs2(h));
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn((x0 - hf.x) * MT_LO_SCALE, (x1 - hf.y) * MT_LO_SCALE);
+    // packed fp32 pairs (FADD2 / FMUL2): both halves are ordinary round-to-nearest operations
+    const float2 r = rt_fmul2(rt_fadd2(make_float2(x0, x1), make_float2(-hf.x, -hf.y)), make_float2(MT_LO_SCALE, MT_LO_SCALE));
+    const __half2 l = __floats2half2_rn(r.x, r.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -156,6 +163,11 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = (a.rows + 127) / 128;
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as this grid's CTAs are all
+    // resident, and this kernel's own prologue below (weights -> shared memory, biases, TMEM allocation: none of it produced
+    // by the previous kernel) runs while the previous grid drains.  griddepcontrol.wait, further down, is the point after
+    // which data written by the previous kernel may be read and anything may be written.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // weights of all layers -> shared memory (already in core-matrix layout); layer l starts at w_off[l]
     int w_off[RT_MLP_MAX_LAYERS + 1];
@@ -196,6 +208,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
     mt_fence_after();
     const uint32_t tm = tmem_slot;
     const uint32_t tD = tm, tAhi = tm + a.nsplit * a.d_cols, tAlo = tAhi + a.a_cols;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel's outputs (our inputs) are complete and visible
 
     if (warp == MT_WORKER_WARPS) {
         // ===== MMA issuer =====
@@ -415,6 +428,14 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                         // max over the ns consecutive rows (= lanes) of a centre; 128 % ns == 0 so groups never straddle tiles
                         int col0 = 0, cnt = 16;
                         bool writer = true;
+                        if (a.ns == 32 && a.layer[l].act == RT_ACT_RELU) {
+                            // the 32 lanes of the warp are one centre and every value is >= +0 after ReLU, so IEEE order is
+                            // unsigned-integer order of the bit patterns: one redux.sync.max per column (16 instructions
+                            // instead of the 31 shuffles + selects of the butterfly)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rt_redux_max_u32(__float_as_uint(v[i]) & 0x7fffffffu));   // -0.0 -> +0.0
+                            writer = lane == 0;
+                        } else
                         switch (a.ns) {
                             case 32: mt_group_max<32>(v, lane, col0, cnt, writer); break;
                             case 16: mt_group_max<16>(v, lane, col0, cnt, writer); break;
@@ -528,8 +549,30 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     const long long ntiles = (a.rows + 127) / 128;
     long long grid = (long long)sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    if (gather) mlp_tc_kernel<RT_MLP_LOAD_GATHER><<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
-    else mlp_tc_kernel<RT_MLP_LOAD_ROWS><<<(int)grid, MT_THREADS, wbytes + gc_bytes, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(MT_THREADS);
+    cfg.dynamicSmemBytes = (size_t)(wbytes + gc_bytes);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see the kernel prologue
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // Measured on B200 (tools/ab.sh, profiles/r2_ab_pdl_ring_fps.txt): with the attribute the 32-pair step is 1 % SLOWER
+    // (2063 vs 2042 us): the early-resident CTAs of the next launch hold registers / shared memory while they wait, which
+    // costs the running grid more than the overlapped prologue saves.  Off by default; RT_MLP_PDL=1 enables it for A/B.
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char *env = getenv("RT_MLP_PDL");
+        use_pdl = (env && atoi(env) == 1) ? 1 : 0;
+    }
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    const cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_GATHER>, a)
+                                  : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_ROWS>, a);
+    if (le != cudaSuccess) {
+        rt_set_error("mlp_tc_kernel: launch failed: %s", cudaGetErrorString(le));
+        return (int)le;
+    }
     return rt_check_launch("mlp_tc_kernel");
 }
 

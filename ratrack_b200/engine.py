@@ -179,17 +179,18 @@ class FusedBackbone:
                 pass
 
     def set_flags(self, costvol_tc: bool = True, mlp_tc: bool = True, two_lanes: bool = False, fps_exclusive: bool = True,
-                  knn_early: bool = True, own_stream: bool = True, morton: bool = True):
+                  knn_early: bool = True, own_stream: bool = True, morton: bool = True, fps_identity: bool = True):
         """A/B switches.  Arithmetic: tcgen05 kernels (default) vs the fp32 SIMT kernels of the same dataflow,
         separately for the cost-volume core (costvol_tc.cu) and for every other dense layer (mlp_tc.cu).
         Scheduling (results are bit-identical either way): two_lanes = run the two halves of a batch (>= 8 pairs)
         concurrently on separate stream sets; fps_exclusive = every FPS CTA claims a whole SM so co-running kernels
         cannot stretch its latency chain; knn_early = the cost-volume kNN runs beside the FPS chain instead of after
         it; own_stream = the feature path runs on an engine-owned stream of middle priority; morton = the cost-volume
-        kernels walk pc1 in Morton order so that the points of a tile share gathered neighbour rows."""
+        kernels walk pc1 in Morton order so that the points of a tile share gathered neighbour rows; fps_identity = levels 2
+        and 3 of the FPS chain (512 of 512 points) are answered by a parallel identity check where it proves the serial result."""
         _cabi.call("rt_engine_set_flags", self._handle,
                    (1 if costvol_tc else 0) | (2 if mlp_tc else 0) | (4 if two_lanes else 0) | (8 if fps_exclusive else 0) |
-                   (16 if knn_early else 0) | (32 if own_stream else 0) | (64 if morton else 0))
+                   (16 if knn_early else 0) | (32 if own_stream else 0) | (64 if morton else 0) | (512 if fps_identity else 0))
         self._ws_key = None   # the workspace layout depends on the lane split
 
     def _to_simt(self, why):

@@ -9,7 +9,8 @@
 
 What stays on the host is what the reference's API makes host-side by construction: the dicts / lists of per-object
 tensors it returns and the track-id bookkeeping (one small device->host read of labels and matches per frame).
-Batch 1 per call, like the reference (`squeeze(0)` at :56).  SURVEY.md section 8(f) rows 1-2.
+`forward` takes the reference's batch-1 call unchanged; `forward_batch` runs B independent sequences per call (one batched
+backbone pass, per-sequence association).  SURVEY.md section 8(f) rows 1-3.
 """
 import numpy as np
 import torch
@@ -69,8 +70,35 @@ class Track4D(Track4DBackbone):
 
     # -- reference-shaped methods ----------------------------------------------------------------------------------
     def forward(self, pc1, pc2, feature1, feature2, h, objects_prev):
+        """Batch 1 with `objects_prev` a dict: the reference's call (track4d.py:49-65), same 10-tuple.
+        Batch B with `objects_prev` a list of B dicts (B independent sequences at the same time step): see forward_batch."""
+        if isinstance(objects_prev, (list, tuple)):
+            return self.forward_batch(pc1, pc2, feature1, feature2, h, objects_prev)
         out = self.backbone(pc1, pc2, feature1, feature2, h)
         return self.track(pc1, feature1, out, objects_prev)
+
+    def forward_batch(self, pc1, pc2, feature1, feature2, h, objects_prev, max_ids=None):
+        """B independent sequences per call: ONE batched backbone pass (h is (5,B,128), one recurrent state per sequence),
+        then clustering / affinity / Sinkhorn / id bookkeeping per sequence -- the reference hard-codes batch 1 here
+        (`squeeze(0)`, track4d.py:56).  `max_ids` = one id counter per sequence (default: the module-wide counter, ids then
+        unique across sequences).  -> (h (5,B,128), pc1_warp (B,3,N), cls (B,N), frames, max_ids) with frames[b] = the
+        per-sequence tail of the reference's tuple: (aff_list, aff_mat, indices1, confs, objects, timeout_obj_curr, objects_curr)."""
+        B = pc1.shape[0]
+        if len(objects_prev) != B:
+            raise ValueError(f"forward_batch: {len(objects_prev)} object dicts for a batch of {B}")
+        out = self.backbone(pc1, pc2, feature1, feature2, h)
+        frames, new_ids = [], []
+        shared = self.max_id
+        for b in range(B):
+            ob = tuple(None if o is None else (o[:, b:b + 1] if i == 1 else o[b:b + 1]) for i, o in enumerate(out))
+            if max_ids is not None:
+                self.max_id = int(max_ids[b])
+            r = self.track(pc1[b:b + 1], feature1[b:b + 1], ob, objects_prev[b])
+            frames.append(r[3:])
+            if max_ids is not None:
+                new_ids.append(self.max_id)
+                self.max_id = shared
+        return out[1], pc1 + out[0], out[2], frames, (new_ids if max_ids is not None else None)
 
     def track(self, pc1, feature1, backbone_out, objects_prev):
         """Everything of `forward` after the backbone (reference :52-65), given the backbone's 7-tuple."""

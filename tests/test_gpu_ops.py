@@ -40,6 +40,32 @@ def test_fps_massive_ties_and_temp():
         assert np.array_equal(got, P.furthest_point_sample(xyz, 64)), N
 
 
+@pytest.mark.parametrize("N,S", [(1024, 512), (700, 512), (256, 512), (322, 512), (1024, 256), (2000, 1024), (512, 128)])
+def test_fps_of_an_fps_ordered_cloud_identity_shortcut(N, S):
+    """Levels 2 and 3 of PNHead sample S of the S points level 1 selected.  fps_identity_kernel answers that with the identity
+    permutation where it can PROVE the serial sampler would (csrc/fps.cu); everything else falls through to the serial
+    kernel.  Against the oracle: FPS-ordered clouds (shortcut taken), N < S (level 1 pads with repeats of one point: ties,
+    shortcut refused), exact duplicates inside the cloud, a shuffled cloud (not in FPS order) and a mixed batch."""
+    xyz = _cloud(4, N, seed=N + S)
+    lvl1 = P.furthest_point_sample(xyz, S)
+    q = np.ascontiguousarray(np.stack([xyz[b, lvl1[b]] for b in range(4)]))            # what level 2 sees
+    q[1, S // 2] = q[1, 3]                                                              # a duplicate inside an ordered cloud
+    q[2] = q[2, np.random.default_rng(1).permutation(S)]                                # not in FPS order at all
+    want = P.furthest_point_sample(q, S)
+    got = U.furthest_point_sample(_cu(q), S).cpu().numpy()
+    assert np.array_equal(got, want)
+    if N >= 2 * S:
+        assert np.array_equal(want[0], np.arange(S)) and not np.array_equal(want[2], np.arange(S))
+    # the running-minimum buffer is left as the serial kernel leaves it
+    from ratrack_b200 import pointnet2_cuda as C
+    temp = torch.full((4, S), 1e10, device="cuda")
+    idx = torch.empty(4, S, dtype=torch.int32, device="cuda")
+    C.furthest_point_sampling_wrapper(4, S, S, _cu(q), temp, idx)
+    _, temp2 = P.furthest_point_sample(q, S, return_temp=True)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(temp.cpu().numpy(), temp2)
+
+
 def test_vod_frames_golden():
     g = np.load(os.path.join(GOLDEN, "pointnet2_vod_frames.npz"))
     for tag in sorted(k[4:] for k in g.files if k.startswith("xyz_")):
