@@ -14,6 +14,10 @@
 // All base offsets are formed in 64 bits (the reference's int32 offsets overflow at large B).
 #include "common.cuh"
 
+bool rt_segsum_supported(int n_dst, long long e_total);   // segsum.cu
+int rt_launch_segmented_scatter(int b, int c, int n_dst, long long e_total, int src_div, const float *grad_out, const int *idx,
+                                const float *weight, float *grad_points, cudaStream_t st, const char *what);
+
 namespace {
 
 constexpr int G_THREADS = 256;
@@ -200,6 +204,10 @@ int launch_scatter(int b, int c, int n, long long e_total, const float *grad_out
                    cudaStream_t st, const char *what) {
     if (b == 0 || c == 0 || e_total == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "%s: batch > 65535", what);
+    // default: deterministic segmented sum over the inverse index (segsum.cu); the atomic kernel below is the reference's
+    // primitive, kept for shapes the inverse index does not cover and for A/B timing (RT_GRAD_ATOMIC=1)
+    if (rt_segsum_supported(n, e_total))
+        return rt_launch_segmented_scatter(b, c, n, e_total, 1, grad_out, idx, nullptr, grad_points, st, what);
     // (a shared-memory variant of this scatter, like three_interpolate_grad_smem_kernel below, was measured SLOWER for
     // grouping gradients -- 421 vs 374 us at C=64, ns=32: ball-query padding repeats one index through the tail of a
     // group, and 32 lanes adding to one shared-memory word serialise; the L2 atomic units absorb that better)
@@ -262,6 +270,9 @@ RT_API int rt_three_interpolate_grad(int b, int c, int n, int m, const float *gr
                "three_interpolate_grad: bad arguments");
     if (b == 0 || c == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "three_interpolate_grad: batch > 65535");
+    if (rt_segsum_supported(m, (long long)n * 3))
+        return rt_launch_segmented_scatter(b, c, m, (long long)n * 3, 3, grad_out, idx, weight, grad_points, (cudaStream_t)stream,
+                                           "three_interpolate_grad");
     const int slab = smem_slab(c, m);
     if (slab > 0 && smem_opt_in(three_interpolate_grad_smem_kernel)) {
         dim3 sgrid(rt_divup(c, slab), b);

@@ -191,3 +191,46 @@ def test_knn_expanded_matches_torch_cpu_topk(n, m, k):
     strict = dist < kth                                        # everything strictly inside the k-th distance must be there
     member = torch.zeros_like(dist, dtype=torch.bool).scatter_(2, got, True)
     assert (member | ~strict).all()
+
+
+def test_gather_type_gradients_are_bitwise_repeatable():
+    """group_points / gather_points / three_interpolate gradients: segmented sums in a fixed order (csrc/segsum.cu) --
+    repeated calls agree bit for bit, including ball-query style indices where one point is repeated many times."""
+    from ratrack_b200 import pointnet2_cuda as C
+
+    rng = np.random.default_rng(11)
+    B, Cc, N, P, S = 3, 37, 700, 512, 32
+    idx = rng.integers(0, N, (B, P, S)).astype(np.int32)
+    idx[:, :, 8:] = idx[:, :, :1]                                  # padding repeats the first neighbour
+    g = rng.normal(size=(B, Cc, P, S)).astype(np.float32)
+    outs = []
+    for _ in range(3):
+        grad = torch.zeros(B, Cc, N, device="cuda")
+        C.group_points_grad_wrapper(B, Cc, N, P, S, _cu(g), _cu(idx), grad)
+        outs.append(grad)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    want = P_group_grad(g, idx, N)
+    assert np.abs(outs[0].cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+    n, m = 1000, 512
+    i3 = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w3 = rng.random((B, n, 3)).astype(np.float32)
+    g3 = rng.normal(size=(B, Cc, n)).astype(np.float32)
+    outs = []
+    for _ in range(3):
+        grad = torch.zeros(B, Cc, m, device="cuda")
+        C.three_interpolate_grad_wrapper(B, Cc, n, m, _cu(g3), _cu(i3), _cu(w3), grad)
+        outs.append(grad)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    want = np.zeros((B, Cc, m), np.float64)
+    for b in range(B):
+        for q in range(3):
+            np.add.at(want[b].T, i3[b, :, q], (g3[b] * w3[b, :, q]).T.astype(np.float64))
+    assert np.abs(outs[0].cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def P_group_grad(g, idx, N):
+    B, Cc = g.shape[:2]
+    want = np.zeros((B, Cc, N), np.float64)
+    for b in range(B):
+        np.add.at(want[b].T, idx[b].reshape(-1), g[b].reshape(Cc, -1).T.astype(np.float64))
+    return want

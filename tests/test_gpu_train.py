@@ -94,8 +94,9 @@ def test_train_step_vs_reference_golden(name, batch, n, monkeypatch):
             assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), key
 
 
-def test_train_step_is_deterministic_given_same_inputs():
-    """Two identical steps give the same loss and (up to atomicAdd ordering in the scatter kernels) the same gradients."""
+def test_train_step_is_bitwise_repeatable():
+    """Two identical steps give the same loss and the SAME gradients, bit for bit: every scatter-add of the backward pass
+    is a segmented sum in a fixed order (csrc/segsum.cu), none is an fp32 atomicAdd (the reference's are: VERDICT r1)."""
     g = np.load(os.path.join(GOLDEN, "train_step_n256_b1.npz"))
     d = synthetic.make_batch(1, 256, seed=1234)
     res = []
@@ -105,6 +106,7 @@ def test_train_step_is_deterministic_given_same_inputs():
         net = net.cuda().train()
         _, sf, seg, trk, total = _step(net, d, g, 1)
         total.backward()
-        res.append((float(total), net.pn_head.sa1.mlps[0][0].conv.weight.grad.clone()))
+        res.append((float(total), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
     assert res[0][0] == res[1][0]
-    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
+    differing = [k for k in res[0][1] if not torch.equal(res[0][1][k], res[1][1][k])]
+    assert not differing, differing[:5]
