@@ -155,6 +155,17 @@ int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const floa
                         float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
                         long long workspace_bytes, void *stream);
 
+/* Variable-size batch.  Real radar frames have 240..350 points each (reference: src/dataset_classes/track_vod_3d.py:49-122)
+ * and the reference runs them one at a time (batch 1, src/models/track4d.py:56).  Here b pairs of different sizes share one
+ * call: the clouds are zero-padded to n columns and npts1 / npts2 -- HOST arrays of b ints -- give the valid points of every
+ * pc1 / pc2 cloud (16 <= npts <= n).  Padded points do not exist for the network: every neighbour search is restricted to a
+ * cloud's own points and every cloud is sampled with the tie-break of its own size, so each pair's outputs equal, bit for
+ * bit, what rt_backbone_forward returns for that pair alone at its own size; output columns of padded points are zero. */
+int rt_backbone_forward_varlen(rt_engine *e, int b, int n, const int *npts1, const int *npts2, const float *pc1,
+                               const float *pc2, const float *ft1, const float *ft2, const float *h_in, float *flow,
+                               float *h_out, float *cls, float *cor, float *f1, float *f2, float *prop, int *knn12,
+                               int *knn11, void *workspace, long long workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Section 3 -- association
  * ------------------------------------------------------------------------------------------ */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "rt_engine_last_status": [_P, ctypes.POINTER(ctypes.c_int)],
     "rt_engine_status_async": [_P, _P, _P],
     "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
+    "rt_backbone_forward_varlen": [_P, _I, _I] + [_P] * 17 + [ctypes.c_longlong, _P],
 }
 # entries whose return value is not an error code
 OTHER = {

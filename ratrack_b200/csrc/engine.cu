@@ -13,6 +13,7 @@
 #include <new>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/ratrack_b200.h"
 #include "engine_kernels.cuh"
@@ -90,7 +91,7 @@ struct Carver {
 
 struct Ws {
     float *xyz0, *ft0, *xyz[3], *temp;
-    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11, *perm1, *fps_ok;
+    int *fps[3], *bq[3][2], *nn_idx[3], *knn12, *knn11, *perm1, *fps_ok, *npts, *fps_list;
     float *nn_w[3];
     float *proj, *xa, *xb, *pooled, *l1, *l2, *l3, *l2p, *l1p, *interp, *feat, *prop;
     float *gmax, *gprop, *cb_a, *cb_b, *p1, *p2, *cost1, *cor, *h1, *h2, *h3, *flow_rows, *gru_h, *gru_gh;
@@ -105,6 +106,8 @@ void carve(Carver &c, Ws &w, int b, int n, int S) {
     w.temp = c.take<float>(3 * B2 * (size_t)max(n, S));   // one FPS scratch per level
     for (int l = 0; l < 3; ++l) w.fps[l] = c.take<int>(B2 * S);
     w.fps_ok = c.take<int>(B2);
+    w.npts = c.take<int>(B2);       // variable-size batches: valid points per cloud (pc1 clouds, then pc2 clouds)
+    w.fps_list = c.take<int>(B2);
     for (int l = 0; l < 3; ++l)
         for (int s = 0; s < 2; ++s) w.bq[l][s] = c.take<int>(B2 * S * kLevels[l].ns[s]);
     // three_nn of FP3 (xyz2 <- xyz3), FP2 (xyz1 <- xyz2), FP1 (xyz0 <- xyz1)
@@ -208,6 +211,7 @@ struct rt_engine {
                                    // bit 5: the feature path runs on an engine-owned stream of middle priority (geometry above it, kNN
                                    //        and API-layout outputs below it) forked from / joined to the caller's stream
     const int *last_status[2] = {nullptr, nullptr};
+    std::vector<int> npts_host[2];   // per lane: point counts of a variable-size batch, kept alive across the async copy
     // optional stage profile (rt_engine_stage_profile): timing events recorded on the feature-path stream of lane 0 at the
     // boundaries of the forward, so the critical path can be read without a profiler's launch overhead distorting it
     static constexpr int kStages = 16;
@@ -229,7 +233,7 @@ inline void stage_mark(rt_engine *e, int lane_idx, cudaStream_t st) {
 
 // geometry of all 2b clouds: FPS chain, ball queries, three_nn (+weights), cost-volume kNN.
 // Every stage records an event the feature path (and the dependent geometry stages) wait on.
-int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
+int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n, const int *npts_host) {
     const int B2 = 2 * b, S = e->npoint;
     cudaStream_t s_fps = L.geo_stream[0], s_nbr = L.geo_stream[1], s_knn = L.geo_stream[2];
     const float *lvl_in[3] = {w.xyz0, w.xyz[0], w.xyz[1]};
@@ -245,12 +249,14 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     // bit 8: the self-kNN (pc1 -> pc1) is needed only by the patch-to-patch sum: it is launched by the feature path after
     // the last SA level of pn_head (run_self_knn) and fills the under-occupied FP / projection stages instead of competing
     // with the SA kernels
-    const bool knn11_late = (e->flags & 256) != 0 && (e->flags & 2) != 0;   // the hook lives in the tensor-core head
+    const bool knn11_late = (e->flags & 256) != 0 && (e->flags & 2) != 0 && !npts_host;   // the hook lives in the tensor-core head
+    // variable-size batch: per-cloud point counts on the device (pc1 clouds first, then pc2 clouds); nullptr = all n
+    const int *cnt1 = npts_host ? w.npts : nullptr, *cnt2 = npts_host ? w.npts + b : nullptr;
     if (knn_early) {
-        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn, cnt2));
         cudaEventRecord(L.ev_knn, s_knn);
         if (!knn11_late) {
-            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn, cnt1));
             cudaEventRecord(L.ev_knn11, s_knn);
         }
         e->launches += 2;
@@ -267,8 +273,14 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
         }
         rt_fps_set_skip(l >= 1 && identity ? w.fps_ok : nullptr);
         // one launch per level on the dependent chain: min-distance init, sampling and the gather of new_xyz are fused
-        int rc = rt_launch_fps_fused(B2, lvl_n[l], S, lvl_in[l], w.fps[l], w.xyz[l], s_fps);
+        int rc = (l == 0 && npts_host)
+                     ? rt_launch_fps_fused_varlen(B2, n, S, lvl_in[0], npts_host, w.npts, w.fps_list, w.fps[0], w.xyz[0], s_fps)
+                     : rt_launch_fps_fused(B2, lvl_n[l], S, lvl_in[l], w.fps[l], w.xyz[l], s_fps);
         rt_fps_set_skip(nullptr);
+        if (rc == RT_ERR_UNSUPPORTED && l == 0 && npts_host) {
+            rt_set_error("backbone_forward_varlen: a cloud size has no register-resident FPS kernel (1 <= n <= 4096 expected)");
+            return rc;
+        }
         if (rc == RT_ERR_UNSUPPORTED) {   // cloud too large for the register-resident kernel
             RT_TRY(rt_launch_fill(w.temp + (size_t)l * B2 * max(n, S), (long long)B2 * lvl_n[l], 1e10f, s_fps));
             RT_TRY(rt_furthest_point_sampling(B2, lvl_n[l], S, lvl_in[l], w.temp + (size_t)l * B2 * max(n, S), w.fps[l], s_fps));
@@ -282,7 +294,7 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
         // both radii of the level in one pass; rows without a hit are zero-filled by the kernel (the reference zero-fills
         // the buffer from Python, lib/pointnet2_utils.py:246)
         RT_TRY(rt_launch_ball_query2(B2, lvl_n[l], S, kLevels[l].radius[0], kLevels[l].ns[0], w.bq[l][0], kLevels[l].radius[1],
-                                     kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], 1, s_nbr));
+                                     kLevels[l].ns[1], w.bq[l][1], w.xyz[l], lvl_in[l], 1, s_nbr, l == 0 ? cnt1 : nullptr));
         cudaEventRecord(L.ev_lvl[l], s_nbr);
         e->launches += 2;
     }
@@ -302,10 +314,10 @@ int run_geometry(rt_engine *e, Lane &L, Ws &w, int b, int n) {
     // beside it), so the throughput-bound kNN is ordered behind it and overlaps the SA / FP kernels instead.
     if (!knn_early) {
         cudaStreamWaitEvent(s_knn, L.ev_fps[2], 0);
-        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn));
+        RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc2, w.knn12, s_knn, cnt2));
         cudaEventRecord(L.ev_knn, s_knn);
         if (!knn11_late) {
-            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn));
+            RT_TRY(rt_launch_knn_expanded(b, n, n, kKnn, pc1, pc1, w.knn11, s_knn, cnt1));
             cudaEventRecord(L.ev_knn11, s_knn);
         }
         e->launches += 2;
@@ -772,7 +784,8 @@ RT_API int rt_engine_status_async(rt_engine *e, int *host_status, void *stream) 
 // h_in / h_out are (5, b_total, 128), so their layer stride is h_stride = b_total * 128.
 static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_stride, int n, const float *pc1, const float *pc2,
                         const float *ft1, const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
-                        float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace, cudaStream_t st) {
+                        float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace, cudaStream_t st,
+                        const int *npts_host = nullptr) {
     Carver c(workspace);
     Ws w;
     carve(c, w, b, n, e->npoint);
@@ -788,8 +801,16 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     // fork: geometry depends only on xyz, so it runs on its own stream and the feature path joins stage by stage
     if (lane_idx == 0) e->stage_n = 0;
     stage_mark(e, lane_idx, st);   // (the inputs->rows kernels precede this mark; "start" is recorded by the caller below)
+    if (npts_host) {   // 2b counts (pc1 clouds, then pc2 clouds) of a padded variable-size batch
+        const cudaError_t ce = cudaMemcpyAsync(w.npts, npts_host, sizeof(int) * 2 * (size_t)b, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) {
+            rt_set_error("backbone_forward_varlen: %s", cudaGetErrorString(ce));
+            return (int)ce;
+        }
+    }
+    const int *cnt1 = npts_host ? w.npts : nullptr, *cnt2 = npts_host ? w.npts + b : nullptr;
     cudaEventRecord(L.ev_in, st);
-    RT_TRY(run_geometry(e, L, w, b, n));
+    RT_TRY(run_geometry(e, L, w, b, n, npts_host));
     // hidden half of the GRU (depends on h_in only): off the critical path, on the output stream
     cudaStreamWaitEvent(L.aux_stream, L.ev_in, 0);
     RT_TRY(rt_launch_gru_hh(b, h_in, e->w.gru.whh, e->w.gru.bhh, h_stride, w.gru_gh, L.aux_stream));
@@ -807,7 +828,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         RT_TRY(run_head(e, L, e->w.pn, w, B2, n, &seg_ft, 1, nullptr, w.feat, st));
     }
     stage_mark(e, lane_idx, st);   // pn_head FP done
-    RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st));
+    RT_TRY(rt_launch_cloud_max(B2, n, 128, w.feat, 128, w.gmax, st, cnt1));   // cnt1 = the 2b counts, pc1 clouds then pc2 clouds
     // API outputs pc1_features / pc2_features = cat(local, broadcast global) (track4d.py:89-95): off the critical path
     cudaStream_t aux = tc_mlp ? L.aux_stream : st;
     if (aux != st) {
@@ -818,6 +839,10 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.feat + half128, 128, 0, f2, 256, 0, aux));
     RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax, f1, 256, 128, aux));
     RT_TRY(rt_launch_broadcast_cm(b, 128, n, w.gmax + (size_t)b * 128, f2, 256, 128, aux));
+    if (npts_host) {   // columns of padded points are defined: zero
+        RT_TRY(rt_launch_mask_cm(b, 256, n, cnt1, f1, aux));
+        RT_TRY(rt_launch_mask_cm(b, 256, n, cnt2, f2, aux));
+    }
     e->launches += 5;
 
     // FeatureCorrelator (model_utils.py:193-250)
@@ -883,6 +908,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         cudaStreamWaitEvent(aux, L.ev_cor, 0);
     }
     RT_TRY(rt_launch_rows_to_cm(b, 256, n, w.cor, 256, 0, cor, 256, 0, aux));
+    if (npts_host) RT_TRY(rt_launch_mask_cm(b, 256, n, cnt1, cor, aux));
     e->launches += 10;
 
     // FlowDecoder (model_utils.py:281-305): cls head on the cost volume (independent of the mse head: output stream)
@@ -902,6 +928,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 32, w.h2, 64, 64, cp.w3, cp.b3, RT_ACT_RELU, w.h3, 32), st));
     }
     RT_TRY(rt_launch_cls_tail(pts, w.h3, cp.w4, cp.lin_w, cp.lin_b, cls, aux));
+    if (npts_host) RT_TRY(rt_launch_mask_cm(b, 1, n, cnt1, cls, aux));
     // second PNHead over embeddings = cat(feature1, pc1_features, cor_features) on pc1's geometry
     const HeadW &mse = e->w.mse;
     RT_TRY(rt_launch_cloud_matvec(b, 32, 128, mse.wf_glob, 128, w.gmax, 128, nullptr, w.cb_a, st));
@@ -920,8 +947,9 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         cudaStreamWaitEvent(aux, L.ev_prop, 0);
     }
     RT_TRY(rt_launch_rows_to_cm(b, 128, n, w.prop, 128, 0, prop, 128, 0, aux));
+    if (npts_host) RT_TRY(rt_launch_mask_cm(b, 128, n, cnt1, prop, aux));
     if (aux != st) cudaEventRecord(L.ev_aux, aux);
-    RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st));
+    RT_TRY(rt_launch_cloud_max(b, n, 128, w.prop, 128, w.gprop, st, cnt1));
     cudaStreamWaitEvent(st, L.ev_gh, 0);
     RT_TRY(rt_launch_gru(b, w.gprop, h_in, e->w.gru.wih, e->w.gru.bih, w.gru_gh, h_out, h_stride, st));
     stage_mark(e, lane_idx, st);   // GRU done
@@ -946,6 +974,7 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
         RT_TRY(rt_launch_rowgemm(gemm1(pts, 3, w.h3, 32, 32, fp.w4, nullptr, RT_ACT_NONE, w.flow_rows, 3), st));
     }
     RT_TRY(rt_launch_rows_to_cm(b, 3, n, w.flow_rows, 3, 0, flow, 3, 0, st));
+    if (npts_host) RT_TRY(rt_launch_mask_cm(b, 3, n, cnt1, flow, st));
     e->launches += 11;
     if (aux != st) cudaStreamWaitEvent(st, L.ev_aux, 0);   // join the output stream
     // fp16-range guard fired anywhere in this lane's step -> its results become NaN (never silently saturated values)
@@ -959,10 +988,10 @@ static int forward_lane(rt_engine *e, Lane &L, int lane_idx, int b, size_t h_str
     return rt_check_launch("backbone_forward");
 }
 
-RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
-                               const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
-                               float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
-                               long long workspace_bytes, void *stream) {
+static int backbone_forward_impl(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                                 const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                                 float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                                 long long workspace_bytes, void *stream, const int *npts1, const int *npts2) {
     RT_REQUIRE(e && pc1 && pc2 && ft1 && ft2 && h_in && flow && h_out && cls && cor && f1 && f2 && prop && workspace,
                "backbone_forward: null argument");
     RT_REQUIRE(b >= 1 && n >= 1, "backbone_forward: b=%d n=%d", b, n);
@@ -972,15 +1001,29 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
     cudaStream_t st = (cudaStream_t)stream;
     const size_t hs = (size_t)b * 128;
     e->last_status[0] = e->last_status[1] = nullptr;
+    // variable-size batch: per lane, the counts of its pc1 clouds followed by those of its pc2 clouds (host memory that
+    // stays alive until the lane's cudaMemcpyAsync has staged it)
+    const bool varlen = npts1 != nullptr;
+    auto lane_counts = [&](int lane, int o, int bl) -> const int * {
+        if (!varlen) return nullptr;
+        std::vector<int> &v = e->npts_host[lane];
+        v.assign(npts1 + o, npts1 + o + bl);
+        v.insert(v.end(), npts2 + o, npts2 + o + bl);
+        return v.data();
+    };
+    if (varlen)
+        for (int i = 0; i < b; ++i)
+            RT_REQUIRE(npts1[i] >= kKnn && npts1[i] <= n && npts2[i] >= kKnn && npts2[i] <= n,
+                       "backbone_forward_varlen: pair %d has %d / %d points (need %d..%d)", i, npts1[i], npts2[i], kKnn, n);
     if (rt_engine_num_lanes(e, b) == 1) {
         if (!(e->flags & 32))
             return forward_lane(e, e->lanes[0], 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12,
-                                knn11, workspace, st);
+                                knn11, workspace, st, lane_counts(0, 0, b));
         Lane &L = e->lanes[0];
         cudaEventRecord(e->ev_fork, st);
         cudaStreamWaitEvent(L.main_stream, e->ev_fork, 0);
         RT_TRY(forward_lane(e, L, 0, b, hs, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12, knn11,
-                            workspace, L.main_stream));
+                            workspace, L.main_stream, lane_counts(0, 0, b)));
         cudaEventRecord(L.ev_done, L.main_stream);
         cudaStreamWaitEvent(st, L.ev_done, 0);
         return rt_check_launch("backbone_forward");
@@ -1000,9 +1043,30 @@ RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, con
         RT_TRY(forward_lane(e, L, l, bl, hs, n, pc1 + o * 3 * n, pc2 + o * 3 * n, ft1 + o * 2 * n, ft2 + o * 2 * n, h_in + o * 128,
                             flow + o * 3 * n, h_out + o * 128, cls + o * n, cor + o * 256 * n, f1 + o * 256 * n, f2 + o * 256 * n,
                             prop + o * 128 * n, knn12 ? knn12 + o * n * kKnn : nullptr, knn11 ? knn11 + o * n * kKnn : nullptr,
-                            (char *)workspace + (l ? ws0 : 0), L.main_stream));
+                            (char *)workspace + (l ? ws0 : 0), L.main_stream, lane_counts(l, (int)o, bl)));
         cudaEventRecord(L.ev_done, L.main_stream);
         cudaStreamWaitEvent(st, L.ev_done, 0);
     }
     return rt_check_launch("backbone_forward");
+}
+
+RT_API int rt_backbone_forward(rt_engine *e, int b, int n, const float *pc1, const float *pc2, const float *ft1,
+                               const float *ft2, const float *h_in, float *flow, float *h_out, float *cls, float *cor,
+                               float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                               long long workspace_bytes, void *stream) {
+    return backbone_forward_impl(e, b, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12, knn11, workspace,
+                                 workspace_bytes, stream, nullptr, nullptr);
+}
+
+// Variable-size batch (real radar frames have 240..350 points each: src/dataset_classes/track_vod_3d.py:49-122): the clouds
+// are padded to n columns, npts1 / npts2 (HOST arrays of b ints) give the valid points of every pc1 / pc2 cloud.  Every pair is
+// computed exactly as rt_backbone_forward computes it alone at its own size (FPS tie-breaks included: one FPS launch per size
+// class); output columns of padded points are zero.
+RT_API int rt_backbone_forward_varlen(rt_engine *e, int b, int n, const int *npts1, const int *npts2, const float *pc1, const float *pc2,
+                                      const float *ft1, const float *ft2, const float *h_in, float *flow, float *h_out, float *cls,
+                                      float *cor, float *f1, float *f2, float *prop, int *knn12, int *knn11, void *workspace,
+                                      long long workspace_bytes, void *stream) {
+    RT_REQUIRE(npts1 && npts2, "backbone_forward_varlen: null point counts");
+    return backbone_forward_impl(e, b, n, pc1, pc2, ft1, ft2, h_in, flow, h_out, cls, cor, f1, f2, prop, knn12, knn11, workspace,
+                                 workspace_bytes, stream, npts1, npts2);
 }

@@ -438,10 +438,13 @@ __global__ void __launch_bounds__(KX_THREADS) knn_expanded_kernel(int n, int m, 
 // (distance bits first, then index: ties -> lower index).  No divergent per-thread insertion lists.
 constexpr int KW_WARPS = 8, KW_QPW = 2, KW_TILE = 1024;
 
-__global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n, int m, int k, const float *__restrict__ q,
-                                                                           const float *__restrict__ s, int *__restrict__ idx) {
+__global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n, int m_stride, int k, const float *__restrict__ q,
+                                                                           const float *__restrict__ s, int *__restrict__ idx,
+                                                                           const int *__restrict__ mcounts) {
     __shared__ float4 s_pts[KW_TILE];
     const int cloud = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // mcounts (optional): valid search points per cloud of a padded batch; the cloud stride stays m_stride
+    const int m = mcounts ? min(m_stride, __ldg(mcounts + cloud)) : m_stride;
     const int q0 = (blockIdx.x * KW_WARPS + warp) * KW_QPW;
     float qx[KW_QPW], qy[KW_QPW], qz[KW_QPW], q2[KW_QPW];
     uint32_t car_d[KW_QPW], car_i[KW_QPW];   // carried best list: lane l < k holds the l-th smallest so far
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(32 * KW_WARPS) knn_expanded_warp_kernel(int n,
         const int tn = min(KW_TILE, m - base);
         __syncthreads();
         for (int t = threadIdx.x; t < tn; t += 32 * KW_WARPS) {
-            const float *p = s + ((long long)cloud * m + base + t) * 3;
+            const float *p = s + ((long long)cloud * m_stride + base + t) * 3;
             const float x = __ldg(p + 0), y = __ldg(p + 1), z = __ldg(p + 2);
             s_pts[t] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
         }
@@ -599,13 +602,16 @@ __global__ void __launch_bounds__(256) gather_rows3_kernel(int clouds, int npts_
     }
 }
 
-__global__ void __launch_bounds__(256) cloud_max_kernel(int npts, int c, const float *__restrict__ f, int ldf, float *__restrict__ g) {
+__global__ void __launch_bounds__(256) cloud_max_kernel(int npts, int c, const float *__restrict__ f, int ldf, float *__restrict__ g,
+                                                        const int *__restrict__ counts) {
     // grid (cloud, channel-block of 32); 256 threads = 8 point-lanes x 32 channels
+    // counts (optional): valid points per cloud of a padded batch (rows beyond are ignored; the row stride stays npts)
     __shared__ float s[8][33];
     const int cloud = blockIdx.x, ch = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+    const int np = counts ? min(npts, __ldg(counts + cloud)) : npts;
     float m = -__int_as_float(0x7f800000);
     if (ch < c)
-        for (int p = pl; p < npts; p += 8) m = fmaxf(m, __ldg(f + ((long long)cloud * npts + p) * ldf + ch));
+        for (int p = pl; p < np; p += 8) m = fmaxf(m, __ldg(f + ((long long)cloud * npts + p) * ldf + ch));
     s[pl][threadIdx.x & 31] = m;
     __syncthreads();
     if (pl == 0 && ch < c) {
@@ -924,12 +930,13 @@ int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st) {
     weighted_sum_generic_kernel<<<rt_divup(ncp, WS_PTS), 256, smem, st>>>(a);
     return rt_check_launch("weighted_sum_generic_kernel");
 }
-int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st) {
+int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st,
+                           const int *mcounts) {
     if (clouds <= 0 || n <= 0) return RT_OK;
     RT_REQUIRE(k >= 1 && k <= 32 && m >= 1, "knn_expanded: k=%d outside [1,32] or empty search cloud", k);
     RT_REQUIRE(k <= m, "knn_expanded: k=%d > search points %d", k, m);
     dim3 grid(rt_divup(n, KW_WARPS * KW_QPW), clouds);
-    knn_expanded_warp_kernel<<<grid, 32 * KW_WARPS, 0, st>>>(n, m, k, q, s, idx);
+    knn_expanded_warp_kernel<<<grid, 32 * KW_WARPS, 0, st>>>(n, m, k, q, s, idx, mcounts);
     return rt_check_launch("knn_expanded_warp_kernel");
 }
 int rt_launch_nn_weights(long long rows, float *d, cudaStream_t st) {
@@ -950,10 +957,10 @@ int rt_launch_gather_rows(int clouds, int npts_out, int n_in, int c, const float
     gather_rows3_kernel<<<grid_for(total, 256), 256, 0, st>>>(clouds, npts_out, n_in, c, src, idx, dst);
     return rt_check_launch("gather_rows3_kernel");
 }
-int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, float *g, cudaStream_t st) {
+int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, float *g, cudaStream_t st, const int *counts) {
     if (clouds <= 0) return RT_OK;
     dim3 grid(clouds, rt_divup(c, 32));
-    cloud_max_kernel<<<grid, 256, 0, st>>>(npts, c, f, ldf, g);
+    cloud_max_kernel<<<grid, 256, 0, st>>>(npts, c, f, ldf, g, counts);
     return rt_check_launch("cloud_max_kernel");
 }
 int rt_launch_cloud_matvec(int clouds, int nout, int k, const float *w, int ldw, const float *g, int ldg, const float *bias,
@@ -1041,6 +1048,16 @@ int rt_launch_poison_on_status(const int *status, float *flow, long long nflow, 
                                size_t h_stride, cudaStream_t st) {
     poison_on_status_kernel<<<64, 256, 0, st>>>(status, flow, nflow, cls, ncls, h_out, b, h_stride);
     return rt_check_launch("poison_on_status_kernel");
+}
+// dst (b, c, n) channel-major: columns at and beyond counts[b] are set to zero (padded points of a variable-size batch)
+__global__ void __launch_bounds__(256) mask_cm_kernel(int c, int n, const int *__restrict__ counts, float *__restrict__ dst) {
+    const int b = blockIdx.z, ch = blockIdx.y, n0 = __ldg(counts + b);
+    for (int p = n0 + blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) dst[((long long)b * c + ch) * n + p] = 0.0f;
+}
+int rt_launch_mask_cm(int b, int c, int n, const int *counts, float *dst, cudaStream_t st) {
+    if (b <= 0 || c <= 0 || n <= 0) return RT_OK;
+    mask_cm_kernel<<<dim3(2, c, b), 256, 0, st>>>(c, n, counts, dst);
+    return rt_check_launch("mask_cm_kernel");
 }
 int rt_launch_fill(float *p, long long n, float v, cudaStream_t st) {
     if (n <= 0) return RT_OK;

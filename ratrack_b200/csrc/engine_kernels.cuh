@@ -65,7 +65,9 @@ int rt_launch_weighted_sum(const RtWeightedSum &a, cudaStream_t st);
 
 // expanded-form k-NN used by the cost volume (reference: utils/model_utils/model_utils.py:17-39, 85-99):
 // d = max((-2 q.s + |q|^2) + |s|^2, 0) in the reference's fp32 rounding order; idx (clouds, n, k) ascending.
-int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st);
+// mcounts (optional): valid search points per cloud of a padded variable-size batch (cloud stride stays m)
+int rt_launch_knn_expanded(int clouds, int n, int m, int k, const float *q, const float *s, int *idx, cudaStream_t st,
+                           const int *mcounts = nullptr);
 
 // inverse-distance weights of three_nn (reference: lib/pointnet2_modules.py:141-144), in place dist2 -> weight
 int rt_launch_nn_weights(long long rows, float *dist2_to_w, cudaStream_t st);
@@ -76,7 +78,8 @@ int rt_launch_interp3(int clouds, int n, int m, int c, const float *f, int ldf, 
 int rt_launch_gather_rows(int clouds, int npts_out, int n_in, int c, const float *src, const int *idx, float *dst,
                           cudaStream_t st);
 // g[cloud, c] = max_p F[(cloud,p), c]
-int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, float *g, cudaStream_t st);
+// counts (optional): valid rows per cloud of a padded batch
+int rt_launch_cloud_max(int clouds, int npts, int c, const float *f, int ldf, float *g, cudaStream_t st, const int *counts = nullptr);
 // cb[cloud, o] = W[o, :k] . g[cloud, :k] + bias[o]
 int rt_launch_cloud_matvec(int clouds, int nout, int k, const float *w, int ldw, const float *g, int ldg,
                            const float *bias, float *cb, cudaStream_t st);
@@ -103,7 +106,16 @@ int rt_launch_poison_on_status(const int *status, float *flow, long long nflow, 
 // results are bit-identical to the identity order.
 int rt_launch_morton_perm(int clouds, int n, const float *xyz, int *perm, cudaStream_t st);
 // neighbors.cu: ball query of two radii over the same centres in one launch
+// counts (optional): valid points per searched cloud of a padded variable-size batch (cloud stride stays n)
 int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
-                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st);
+                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st,
+                          const int *counts = nullptr);
 // fps.cu: FPS from the reference's initial state that also emits new_xyz = xyz[idx]; RT_ERR_UNSUPPORTED -> use the 3-launch path
 int rt_launch_fps_fused(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st);
+// variable-size batch: cloud i has counts_host[i] (== counts_dev[i]) valid points, cloud stride n_stride.  Every cloud is
+// sampled exactly as a stand-alone cloud of its own size would be (the tie-break depends on the reference's CTA size for
+// that size), one launch per size class.  list_dev: scratch for b cloud indices.
+int rt_launch_fps_fused_varlen(int b, int n_stride, int m, const float *xyz, const int *counts_host, const int *counts_dev,
+                               int *list_dev, int *idx, float *new_xyz, cudaStream_t st);
+// dst (b, c, n): zero the columns at and beyond counts[b]
+int rt_launch_mask_cm(int b, int c, int n, const int *counts, float *dst, cudaStream_t st);

@@ -27,6 +27,8 @@ namespace {
 int g_fps_exclusive = 0;
 int g_fps_pair = 0;
 const int *g_fps_skip = nullptr;   // per-cloud flags: clouds already served by fps_identity_kernel (their CTAs exit at once)
+const int *g_fps_counts = nullptr, *g_fps_list = nullptr;   // variable-size batch: per-cloud point counts, clouds of the launch
+int g_fps_stride = 0;                                        // ... and the cloud stride (0: the launch's own n)
 constexpr size_t kFpsHogBytes = 226 * 1024;   // + static + the 1 KB per-CTA reserve = the SM's 228 KB: no other CTA fits beside it
 
 __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
@@ -46,7 +48,8 @@ __host__ __device__ __forceinline__ unsigned bitrev_bits(unsigned v, int bits) {
 template <int T, int Q, int PH, bool FUSED, int CPB>
 __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int m, const float *__restrict__ xyz_all,
                                                          float *__restrict__ temp_all, int *__restrict__ idx_all,
-                                                         float *__restrict__ new_xyz_all, const int *__restrict__ skip) {
+                                                         float *__restrict__ new_xyz_all, const int *__restrict__ skip,
+                                                         const int *__restrict__ counts, const int *__restrict__ list) {
     constexpr int PPT = Q * PH;
     constexpr int NW = (T + 31) / 32;
     constexpr int LOGT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : (T == 256) ? 8 : (T == 512) ? 9 : 10;
@@ -57,15 +60,21 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
     __shared__ __align__(8) uint64_t s_bar_all[CPB];
 
     const int grp = (CPB == 1) ? 0 : (int)threadIdx.x / T;       // which cloud of the CTA this thread works on
-    const int cloud = blockIdx.x * CPB + grp;
-    if (cloud >= nclouds || (skip && skip[cloud])) return;       // whole group leaves together (named barriers are per group)
-    float *s_xyz = s_xyz_all + (size_t)grp * ((n * 3 + 3) & ~3);
+    const int slot = blockIdx.x * CPB + grp;
+    if (slot >= nclouds) return;                                 // whole group leaves together (named barriers are per group)
+    // variable-size batch: `list` names the clouds of this launch's size class, `counts` their point counts; the cloud
+    // stride stays n (the padded size), everything else of the round loop sees the cloud's own count
+    const int cloud = list ? __ldg(list + slot) : slot;
+    if (skip && skip[cloud]) return;
+    const int n_stride = n;
+    if (counts) n = __ldg(counts + cloud);
+    float *s_xyz = s_xyz_all + (size_t)grp * ((n_stride * 3 + 3) & ~3);
     // exchange slots, as plain pointers computed once (indexing the 3-D array inside the round loop made the compiler
     // re-derive the address behind a branch every round: +75 cycles per round)
     uint2 *const red_base = &s_red_all[grp][0][0];
     uint64_t &s_bar = s_bar_all[grp];
-    const float *xyz = xyz_all + (size_t)cloud * n * 3;
-    float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n;
+    const float *xyz = xyz_all + (size_t)cloud * n_stride * 3;
+    float *temp = FUSED ? nullptr : temp_all + (size_t)cloud * n_stride;
     int *idx = idx_all + (size_t)cloud * m;
     float *new_xyz = FUSED ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
     const int t = (CPB == 1) ? (int)threadIdx.x : (int)threadIdx.x % T;   // thread within the group
@@ -357,7 +366,8 @@ __global__ void __launch_bounds__(256) fps_generic_kernel(int n, int m, int bs, 
 
 template <int T, int Q, int PH, bool FUSED, int CPB>
 int launch_reg3(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t st) {
-    size_t smem = (size_t)CPB * ((n * 3 + 3) & ~3) * sizeof(float);
+    const int n_kernel = g_fps_stride ? g_fps_stride : n;   // variable-size batch: clouds are strided by the padded size
+    size_t smem = (size_t)CPB * ((n_kernel * 3 + 3) & ~3) * sizeof(float);
     // SM-exclusive mode (rt_fps_set_exclusive): every round of this kernel is a dependent latency chain, and any CTA
     // sharing the SM stretches each round 2-3x (measured on B200).  Asking for (nearly) the whole shared memory of the
     // SM keeps every other CTA off it, so the chain runs at its stand-alone speed whatever else is in flight.
@@ -371,7 +381,7 @@ int launch_reg3(int b, int n, int m, const float *xyz, float *temp, int *idx, fl
         }
         attr.mark(rt_current_device());
     }
-    fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n, m, xyz, temp, idx, new_xyz, g_fps_skip);
+    fps_reg_kernel<T, Q, PH, FUSED, CPB><<<(b + CPB - 1) / CPB, T * CPB, smem, st>>>(b, n_kernel, m, xyz, temp, idx, new_xyz, g_fps_skip, g_fps_counts, g_fps_list);
     return rt_check_launch("fps_reg_kernel");
 }
 template <int T, int Q, int PH, bool FUSED>
@@ -524,6 +534,15 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
     return RT_OK;
 }
 
+// template selection by n_class (the size class's largest cloud), cloud stride / staging by n_stride
+static int fps_dispatch_sized(int b, int n_class, int n_stride, int m, const float *xyz, float *temp, int *idx, float *new_xyz,
+                              cudaStream_t st, int *launched) {
+    g_fps_stride = n_stride;
+    const int rc = fps_dispatch(b, n_class, m, xyz, temp, idx, new_xyz, st, launched);
+    g_fps_stride = 0;
+    return rc;
+}
+
 // engine-internal: FPS from the reference's initial state (temp = 1e10) that also emits new_xyz (b,m,3) = xyz[idx].
 // Returns RT_ERR_UNSUPPORTED when the shape has no register-resident variant (caller falls back to fill + FPS + gather).
 int rt_launch_fps_fused(int b, int n, int m, const float *xyz, int *idx, float *new_xyz, cudaStream_t st) {
@@ -532,6 +551,48 @@ int rt_launch_fps_fused(int b, int n, int m, const float *xyz, int *idx, float *
     const int rc = fps_dispatch(b, n, m, xyz, nullptr, idx, new_xyz, st, &launched);
     if (rc != RT_OK) return rc;
     return launched ? RT_OK : RT_ERR_UNSUPPORTED;
+}
+
+// engine-internal: variable-size batch (see engine_kernels.cuh).  One launch per size class bs = rt_ref_block_size(count):
+// the register-resident kernel for (bs, passes of the class's largest cloud) reproduces, for every cloud of the class, exactly
+// what a stand-alone launch for that cloud's own size computes (slots beyond a cloud's count are padding).
+int rt_launch_fps_fused_varlen(int b, int n_stride, int m, const float *xyz, const int *counts_host, const int *counts_dev,
+                               int *list_dev, int *idx, float *new_xyz, cudaStream_t st) {
+    if (m <= 0 || b == 0) return RT_OK;
+    RT_REQUIRE(b <= 65535, "fps_varlen: batch > 65535");
+    int *order = (int *)malloc(sizeof(int) * (size_t)b);
+    RT_REQUIRE(order, "fps_varlen: out of host memory");
+    int filled = 0, rc = RT_OK;
+    for (int bs = 1; bs <= 1024 && rc == RT_OK; bs *= 2) {
+        const int first = filled;
+        int nmax = 0;
+        for (int i = 0; i < b; ++i)
+            if (rt_ref_block_size(counts_host[i]) == bs) {
+                order[filled++] = i;
+                nmax = counts_host[i] > nmax ? counts_host[i] : nmax;
+            }
+        if (filled == first) continue;
+        const cudaError_t ce = cudaMemcpyAsync(list_dev + first, order + first, sizeof(int) * (size_t)(filled - first), cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) {
+            rt_set_error("fps_varlen: %s", cudaGetErrorString(ce));
+            rc = (int)ce;
+            break;
+        }
+        // dispatch on the class's largest cloud (it fixes bs and the number of passes); the kernel strides clouds by n_stride
+        g_fps_counts = counts_dev;
+        g_fps_list = list_dev + first;
+        int launched = 0;
+        rc = fps_dispatch_sized(filled - first, nmax, n_stride, m, xyz, nullptr, idx, new_xyz, st, &launched);
+        g_fps_counts = g_fps_list = nullptr;
+        if (rc == RT_OK && !launched) rc = RT_ERR_UNSUPPORTED;
+    }
+    // pageable host memory: the copies above were staged before cudaMemcpyAsync returned
+    free(order);
+    if (rc == RT_OK && filled != b) {
+        rt_set_error("fps_varlen: a cloud has %s points", "0 or more than the register-resident kernels cover");
+        rc = RT_ERR_UNSUPPORTED;
+    }
+    return rc;
 }
 
 // C-ABI.  replaces furthest_point_sampling_wrapper (reference: src/lib/src/sampling.cpp:37-47)

@@ -55,11 +55,13 @@ __device__ __forceinline__ void bq_compact(bool hit_a, bool hit_b, int cand, int
 __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, float radius_a, int nsample_a, int *__restrict__ idx_a,
                                                                 float radius_b, int nsample_b, int *__restrict__ idx_b,
                                                                 const float *__restrict__ new_xyz,
-                                                                const float *__restrict__ xyz, int zero_fill) {
+                                                                const float *__restrict__ xyz, int zero_fill,
+                                                                const int *__restrict__ counts) {
     extern __shared__ __align__(16) float s_pts[];  // roundup32(min(n, TILE_PTS))*3
     __shared__ __align__(8) uint64_t s_bar;
     const int cloud = blockIdx.y;
     const float *pts = xyz + (size_t)cloud * n * 3;
+    if (counts) n = min(n, __ldg(counts + cloud));   // padded variable-size batch: only the cloud's own points are candidates
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float r2a = __fmul_rn(radius_a, radius_a), r2b = __fmul_rn(radius_b, radius_b);
     const float r2max = nsample_b > 0 ? fmaxf(r2a, r2b) : r2a;
@@ -337,18 +339,18 @@ RT_API int rt_ball_query(int b, int n, int m, float radius, int nsample, const f
     RT_REQUIRE(b <= 65535, "ball_query: batch > 65535");
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
-                                                                                 new_xyz, xyz, 0);
+                                                                                 new_xyz, xyz, 0, nullptr);
     return rt_check_launch("ball_query_kernel");
 }
 
 // engine-internal: two radii over the same centres in one launch (same results as two rt_ball_query calls)
 int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, int *idx_a, float radius_b, int nsample_b,
-                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st) {
+                          int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st, const int *counts) {
     if (b == 0 || m == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535 && nsample_a > 0 && nsample_b > 0, "ball_query2: bad arguments");
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
-                                                              new_xyz, xyz, zero_fill);
+                                                              new_xyz, xyz, zero_fill, counts);
     return rt_check_launch("ball_query_kernel(2 radii)");
 }
 

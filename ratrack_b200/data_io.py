@@ -5,11 +5,15 @@ host batches for the engine, tracking result lines out.  Host code only.
                            float32 records of 7 columns [x, y, z, RCS, v_r, v_r_compensated, time].
 * `frame_pair_inputs`   -- the slicing `main_utils.epoch` does before the model call (src/main_utils.py:76-79):
                            pc = columns 0:3 as (1,3,N), features = columns 3:5 as (1,2,N).
-* `PinnedBatcher`       -- groups frame pairs BY POINT COUNT into pinned (B,3,N) / (B,2,N) buffers.  The kernels take
-                           one N per call, and padding a cloud is not neutral here: a duplicated or sentinel point
-                           changes furthest-point sampling, ball-query slot filling and the kNN sets, so no padding
-                           convention can reproduce the reference's per-frame results.  Real VoD frames carry 240-350
-                           points; frames of equal N are batched together, the rest run as smaller batches.
+* `PaddedBatcher`       -- the batcher for real data: frame pairs of ANY point counts (real VoD frames carry 240-350
+                           points each) go into one pinned batch, zero-padded to the largest count, together with the
+                           per-cloud counts `npts1` / `npts2`.  Padding is not neutral for a point-cloud network -- a
+                           sentinel point would change furthest-point sampling, ball-query slot filling and the kNN sets
+                           -- so the convention is that padded points DO NOT EXIST: the engine's variable-size entry
+                           (`rt_backbone_forward_varlen`, `Track4DBackbone.backbone(..., npts1=, npts2=)`) restricts every
+                           search to a cloud's own points and samples every cloud with the tie-break of its own size, so a
+                           pair's results are bit-identical to running it alone; output columns of padded points are zero.
+* `PinnedBatcher`       -- the round-1 batcher: groups frame pairs BY POINT COUNT (one N per batch, no counts needed).
 * `format_result_line`  -- one line of the reference's per-frame result file (src/main_utils.py:165-184).
 """
 from collections import defaultdict
@@ -81,6 +85,51 @@ class PinnedBatcher:
             if self._pending[n]:
                 items, self._pending[n] = self._pending[n], []
                 yield self._emit(n, items)
+
+
+class PaddedBatcher:
+    """Collect frame pairs of any sizes, hand out pinned zero-padded batches with their point counts.
+
+        b = PaddedBatcher(batch=32)
+        b.add(key, frame1, frame2)                                # (N1,7), (N2,7) arrays: the two frames may differ in size
+        for keys, pc1, pc2, ft1, ft2, npts1, npts2 in b.ready():  # (B,3,Nmax) / (B,2,Nmax) pinned tensors, (B,) int32 counts
+        for ... in b.flush():                                     # whatever is left, as a partial batch
+    """
+
+    def __init__(self, batch=32, pin=True, multiple=4):
+        self.batch, self.multiple = int(batch), int(multiple)
+        self.pin = pin and torch.cuda.is_available()
+        self._pending = []
+
+    def add(self, key, frame1, frame2):
+        f1, f2 = np.asarray(frame1, np.float32), np.asarray(frame2, np.float32)
+        self._pending.append((key, f1, f2))
+
+    def _emit(self, items):
+        b = len(items)
+        nmax = max(max(f1.shape[0], f2.shape[0]) for _, f1, f2 in items)
+        nmax = (nmax + self.multiple - 1) // self.multiple * self.multiple      # 16-byte aligned clouds for the bulk-copy engine
+        mk = lambda c: (torch.zeros(b, c, nmax).pin_memory() if self.pin else torch.zeros(b, c, nmax))  # noqa: E731
+        pc1, pc2, ft1, ft2 = mk(3), mk(3), mk(2), mk(2)
+        n1 = torch.tensor([f1.shape[0] for _, f1, _ in items], dtype=torch.int32)
+        n2 = torch.tensor([f2.shape[0] for _, _, f2 in items], dtype=torch.int32)
+        for i, (_, f1, f2) in enumerate(items):
+            pc1[i, :, :f1.shape[0]] = torch.from_numpy(f1[:, 0:3].T.copy())
+            ft1[i, :, :f1.shape[0]] = torch.from_numpy(f1[:, 3:5].T.copy())
+            pc2[i, :, :f2.shape[0]] = torch.from_numpy(f2[:, 0:3].T.copy())
+            ft2[i, :, :f2.shape[0]] = torch.from_numpy(f2[:, 3:5].T.copy())
+        return [it[0] for it in items], pc1, pc2, ft1, ft2, n1, n2
+
+    def ready(self):
+        while len(self._pending) >= self.batch:
+            items, self._pending = self._pending[:self.batch], self._pending[self.batch:]
+            yield self._emit(items)
+
+    def flush(self):
+        yield from self.ready()
+        if self._pending:
+            items, self._pending = self._pending, []
+            yield self._emit(items)
 
 
 def format_result_line(obj_id, conf, obj):

@@ -272,9 +272,17 @@ class FusedBackbone:
         base = self._workspace.data_ptr()
         return (base + 255) // 256 * 256, self._workspace.numel() - 256
 
-    def __call__(self, pc1, pc2, feature1, feature2, h=None, want_knn=False):
+    def __call__(self, pc1, pc2, feature1, feature2, h=None, want_knn=False, npts1=None, npts2=None):
+        """npts1 / npts2: (B,) point counts of a zero-padded variable-size batch (data_io.PaddedBatcher); every pair is then
+        computed exactly as it would be alone at its own size, output columns of padded points are zero."""
         self._poll_status()
         b, _, n = pc1.shape
+        if (npts1 is None) != (npts2 is None):
+            raise _cabi.RatrackError("fused backbone: npts1 and npts2 go together")
+        if npts1 is not None:
+            counts = [torch.as_tensor(x, dtype=torch.int32).cpu().contiguous() for x in (npts1, npts2)]
+            if any(c.numel() != b for c in counts):
+                raise _cabi.RatrackError(f"fused backbone: point counts must have one entry per pair ({b})")
         f32 = dict(dtype=torch.float32, device=self.device)
         args = [t.to(**f32).contiguous() for t in (pc1, pc2, feature1, feature2)]
         if h is None:
@@ -291,11 +299,14 @@ class FusedBackbone:
                torch.empty(b, n, 16, dtype=torch.int32, device=self.device)) if want_knn else (None, None)
         ws_ptr, ws_bytes = self._ws(b, n)
         with torch.cuda.device(self.device):
-            _cabi.call("rt_backbone_forward", self._handle, b, n, args[0].data_ptr(), args[1].data_ptr(),
-                       args[2].data_ptr(), args[3].data_ptr(), h.data_ptr(), flow.data_ptr(), h_out.data_ptr(),
-                       cls.data_ptr(), cor.data_ptr(), f1.data_ptr(), f2.data_ptr(), prop.data_ptr(),
-                       knn[0].data_ptr() if want_knn else None, knn[1].data_ptr() if want_knn else None,
-                       ws_ptr, ws_bytes, torch.cuda.current_stream(self.device).cuda_stream)
+            tail = (args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(), h.data_ptr(), flow.data_ptr(),
+                    h_out.data_ptr(), cls.data_ptr(), cor.data_ptr(), f1.data_ptr(), f2.data_ptr(), prop.data_ptr(),
+                    knn[0].data_ptr() if want_knn else None, knn[1].data_ptr() if want_knn else None,
+                    ws_ptr, ws_bytes, torch.cuda.current_stream(self.device).cuda_stream)
+            if npts1 is None:
+                _cabi.call("rt_backbone_forward", self._handle, b, n, *tail)
+            else:
+                _cabi.call("rt_backbone_forward_varlen", self._handle, b, n, counts[0].data_ptr(), counts[1].data_ptr(), *tail)
             if self.tensor_cores and self._status_event is None:
                 _cabi.call("rt_engine_status_async", self._handle, self._status_host.data_ptr(),
                            torch.cuda.current_stream(self.device).cuda_stream)

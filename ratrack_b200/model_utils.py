@@ -332,9 +332,17 @@ class Track4DBackbone(nn.Module):
             self.flow_head(feature1, h, pc1, pc1_features, pc2, pc2_features, xyz1_new, xyz2_new)
         return output, h, cls, cor_features, pc1_features, pc2_features, prop_features
 
-    def backbone(self, pc1, pc2, feature1, feature2, h):
+    def backbone(self, pc1, pc2, feature1, feature2, h, npts1=None, npts2=None):
         """pc (B,3,N), feature (B,2,N), h (5,B,128)|None ->
-        (output (B,3,N), h, cls (B,N), cor_features (B,256,N), pc1_features, pc2_features (B,256,N), prop_features (B,128,N))"""
+        (output (B,3,N), h, cls (B,N), cor_features (B,256,N), pc1_features, pc2_features (B,256,N), prop_features (B,128,N))
+        npts1 / npts2 (optional, beyond the reference's signature): (B,) point counts of a zero-padded variable-size batch
+        (data_io.PaddedBatcher) -- served by the fused engine only."""
+        if npts1 is not None:
+            if not (self.use_fused and not self.training and not torch.is_grad_enabled()):
+                raise RuntimeError("variable-size batches (npts1 / npts2) are served by the fused inference engine only")
+            eng = self._fused_engine()
+            run = eng.run_checked if self.checked_forward else eng
+            return run(pc1, pc2, feature1, feature2, h, want_knn=self.capture_knn, npts1=npts1, npts2=npts2)
         if self.use_fused and not self.training and not torch.is_grad_enabled():
             # fp16-range guard of the tensor-core kernels: a forward that trips it returns NaN in flow / cls / h (the device
             # overwrites them), reports through a status word polled without synchronisation at the next call, and the

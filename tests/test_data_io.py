@@ -68,3 +68,21 @@ def test_result_line_format():
     obj[0, 3:6, 0] = torch.tensor([1.0, 2.0, 3.0])
     obj[0, 3:6, 1] = torch.tensor([4.0, 5.0, 6.5])
     assert data_io.format_result_line(7, 0.25, obj) == "NA 1 -1 -1 0.25 7 1.0 2.0 3.0 4.0 5.0 6.5\n"
+
+
+def test_padded_batcher_keeps_every_frame_at_its_own_size():
+    """Frames of different point counts share one zero-padded batch; the counts travel with it."""
+    f = _frames()                                                        # 322, 352, 242 points
+    b = data_io.PaddedBatcher(batch=3, pin=False)
+    b.add("a", f[0], f[1])
+    b.add("b", f[1], f[2])
+    assert list(b.ready()) == []
+    b.add("c", f[2], f[0])
+    (keys, pc1, pc2, ft1, ft2, n1, n2), = list(b.ready())
+    assert keys == ["a", "b", "c"] and n1.tolist() == [322, 352, 242] and n2.tolist() == [352, 242, 322]
+    assert tuple(pc1.shape) == (3, 3, 352) and tuple(ft2.shape) == (3, 2, 352) and n1.dtype == torch.int32
+    assert np.array_equal(pc1[2, :, :242].numpy(), f[2][:, 0:3].T) and float(pc1[2, :, 242:].abs().max()) == 0.0
+    assert np.array_equal(ft2[1, :, :242].numpy(), f[2][:, 3:5].T) and float(ft2[1, :, 242:].abs().max()) == 0.0
+    b.add("d", f[0], f[0])
+    (keys, pc1, *_rest), = list(b.flush())
+    assert keys == ["d"] and tuple(pc1.shape) == (1, 3, 324)             # padded to a multiple of 4 points

@@ -257,3 +257,66 @@ def test_engine_snapshot_follows_the_parameters():
         want = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], None)[0]
     assert float((a - b).abs().max()) > 1e-3
     assert float((b - want).abs().max()) <= TOL["flow"] * max(1.0, float(want.abs().max()))
+
+
+def _vod_like_frames():
+    """The three real VoD radar frames the reference ships (xyz from the fixture, synthetic RCS / radial velocity)."""
+    g = np.load(os.path.join(GOLDEN, "pointnet2_vod_frames.npz"))
+    rng = np.random.default_rng(3)
+    out = []
+    for tag in sorted(k[4:] for k in g.files if k.startswith("xyz_")):
+        xyz = g[f"xyz_{tag}"]
+        rec = np.zeros((xyz.shape[0], 7), np.float32)
+        rec[:, 0:3] = xyz
+        rec[:, 3] = rng.normal(-13, 12, xyz.shape[0])
+        rec[:, 4] = rng.normal(-2, 1.6, xyz.shape[0])
+        out.append(rec)
+    return out
+
+
+def test_variable_size_batch_equals_every_pair_alone():
+    """SURVEY 8f row 4 / VERDICT r1 'missing' 4: real frames have 242..352 points each.  One padded batch with per-cloud
+    counts (rt_backbone_forward_varlen) must give, for every pair, bit for bit what that pair gives alone at its own size:
+    FPS with the tie-break of the cloud's own size (two size classes here: 242 -> CTA size 128, 322 / 352 -> 256), ball query /
+    kNN / global max-pool restricted to the cloud's own points; columns of padded points are zero."""
+    from ratrack_b200 import data_io
+
+    f = _vod_like_frames()
+    syn = synthetic.make_batch(2, 300, seed=9)
+    extra = np.concatenate([syn["pc1"][0].T, syn["ft1"][0].T, np.zeros((300, 2), np.float32)], axis=1)      # a 300-point frame
+    pairs = [(f[0], f[1]), (f[1], f[2]), (f[2], f[0]), (f[2], f[2]), (extra, f[0])]
+    net, _ = _net(True)
+    batcher = data_io.PaddedBatcher(batch=len(pairs), pin=False)
+    for i, (a, b) in enumerate(pairs):
+        batcher.add(i, a, b)
+    (keys, pc1, pc2, ft1, ft2, n1, n2), = list(batcher.flush())
+    h = torch.randn(5, len(pairs), 128, device="cuda") * 0.1
+    with torch.no_grad():
+        out = [o.clone() for o in net.backbone(pc1.cuda(), pc2.cuda(), ft1.cuda(), ft2.cuda(), h, npts1=n1, npts2=n2)]
+    torch.cuda.synchronize()
+    net._engine.check_status()
+    names = ["flow", "h", "cls", "cor", "f1", "f2", "prop"]
+    for i, (a, b) in enumerate(pairs):
+        na, nb = a.shape[0], b.shape[0]
+        if na != nb:
+            # alone, a pair must have one N for both clouds (the reference's loader resamples): check the pc1-side outputs of
+            # unequal pairs through a second variable-size call of batch 1 instead
+            with torch.no_grad():
+                solo = net.backbone(pc1[i:i + 1].cuda(), pc2[i:i + 1].cuda(), ft1[i:i + 1].cuda(), ft2[i:i + 1].cuda(), h[:, i:i + 1].contiguous(),
+                                    npts1=n1[i:i + 1], npts2=n2[i:i + 1])
+            for nm, x, y in zip(names, out, solo):
+                xs = x[:, i:i + 1] if nm == "h" else x[i:i + 1]
+                assert torch.equal(xs, y), (i, nm)
+            continue
+        p1, p2, q1, q2 = data_io.frame_pair_inputs(a, b)
+        with torch.no_grad():
+            solo = net.backbone(torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda(), torch.from_numpy(q1).cuda(),
+                                torch.from_numpy(q2).cuda(), h[:, i:i + 1].contiguous())
+        for nm, x, y in zip(names, out, solo):
+            if nm == "h":
+                assert torch.equal(x[:, i:i + 1], y), (i, nm)
+            else:
+                assert torch.equal(x[i:i + 1, ..., :na], y), (i, nm, float((x[i:i + 1, ..., :na] - y).abs().max()))
+                assert float(x[i, ..., (nb if nm == "f2" else na):].abs().max() if x.shape[-1] > max(na, nb) else 0.0) == 0.0
+    # equal-size pairs exist in the batch (pair 3: 242 / 242), unequal ones too
+    assert any(a.shape[0] == b.shape[0] for a, b in pairs) and any(a.shape[0] != b.shape[0] for a, b in pairs)
