@@ -200,7 +200,7 @@ struct rt_engine {
     long long launches = 0;
     Lane lanes[2];
     cudaEvent_t ev_fork = nullptr;
-    int flags = 571;               // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
+    int flags = 1595;              // bit 0: tensor-core cost volume (costvol_tc.cu); bit 1: tensor-core MLP chains
                                    // (mlp_tc.cu); cleared bits select the fp32 SIMT kernels of the same dataflow;
                                    // bit 2 (off by default: measured 4 % slower at 32 pairs, neutral at 128): split batches of >= 8 pairs over two lanes
                                    // bit 3: FPS CTAs claim a whole SM each (fps.cu launch_reg) so co-running kernels cannot stretch the chain
@@ -480,7 +480,10 @@ int run_head_tc(rt_engine *e, Lane &L, int lane_idx, const HeadW &hw, const Head
             if (cfg.c3[s]) { mlp_layer(m, pk.w3[s], sw[l][s].b3, cfg.c2[s], cfg.c3[s], RT_ACT_RELU); clast = cfg.c3[s]; }
             mlp_out(m, w.pooled, pooled_c, coff, clast);
             m.status = w.status;
-            RT_TRY(rt_launch_mlp_tc(m, st));
+            // bit 10: scales with one tensor-core layer gather from a shared-memory copy of the cloud's projections (sa_tc.cu)
+            int rc = (e->flags & 1024) ? rt_launch_sa_tc(m, clouds, st) : RT_ERR_UNSUPPORTED;
+            if (rc == RT_ERR_UNSUPPORTED) rc = rt_launch_mlp_tc(m, st);
+            RT_TRY(rc);
             coff += clast;
         }
         // Linear after the max-pool; for levels 1 and 2 the next level's projection rides in the same launch as a second

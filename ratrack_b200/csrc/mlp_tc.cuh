@@ -47,6 +47,9 @@ struct RtMlpTc {
     int tmem_cols, d_cols, a_cols, ns_shift, nsplit;  // filled by the launcher (nsplit: accumulators per layer, 1 or 2)
 };
 int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st);
+// sa_tc.cu: the same job for a gather / max-pool scale with one tensor-core layer, gathering from a shared-memory copy of the
+// cloud's projected features; RT_ERR_UNSUPPORTED (no error text) when the shape is not covered -> use rt_launch_mlp_tc
+int rt_launch_sa_tc(const RtMlpTc &m, int clouds, cudaStream_t st);
 
 // device-side weight packing: W (n_real x sum k_s, given as column segments of row-major fp32 matrices) ->
 // the layout above with every segment padded to 16 columns and n padded to n_pad rows (zeros)
