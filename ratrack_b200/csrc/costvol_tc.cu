@@ -77,8 +77,14 @@ struct CostVolTcArgs {
     const float *b2, *b3, *bc, *wa, *ba, *wb, *bb;
     float *out;
     int *status;
+    unsigned long long *trace;   // RT_CV_TRACE: clock64 stamps of CTA 0 (worker warp 0, MMA thread), 32 per tile per role
     int debug;   // timing experiments only (RT_CV_DEBUG): 1 no MMAs, 2 no layer-1 work, 4 no mid epilogue, 8 no final epilogue, 16 / 32 no lo / hi weight traffic
 };
+
+#define CT_TRACE(role, slot)                                                                                      \
+    do {                                                                                                          \
+        if (DBG && a.trace && blockIdx.x == 0 && trace_it < 6) a.trace[(trace_it * 2 + (role)) * 32 + (slot)] = clock64(); \
+    } while (0)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 // workers back off between probes (a spinning warp steals issue slots from the warps that have work) ...
@@ -349,7 +355,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             const uint32_t aw_hi = rt_smem_u32(s_aw), aw_lo = aw_hi + CT_AW_PLANE;
             const uint32_t wc_hi = rt_smem_u32(s_wc), wc_lo = wc_hi + CT_WC_PLANE;
             const uint32_t hi0 = rt_smem_u32(s_hi);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int trace_it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++trace_it) {
+                CT_TRACE(1, 0);
                 if (tile != (int)blockIdx.x) {
                     // layer 2 accumulates into R0, which holds the previous tile's WeightNet accumulator until every
                     // worker warp has read it
@@ -357,6 +365,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                     e_phase ^= 1;
                     ct_fence_after();
                 }
+                CT_TRACE(1, 1);
                 for (int layer = 0; layer < 2; ++layer, ++fill) {
                     const uint32_t tD = layer == 0 ? tR0 : tR1, tA = layer == 0 ? tR1 : tR0;
                     // Correction products first (lo*hi + hi*lo over all of K, carrying the 2^11 of the scaled lo planes),
@@ -367,6 +376,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         if ((c & 1) == 0) {
                             ct_mbar_spin(&bar_a[c >> 1], a_phase);   // K steps 4g .. 4g+3 of the A operand have landed in TMEM:
                             ct_fence_after();                        // the MMAs start while the workers still produce later groups
+                            CT_TRACE(1, 2 + 12 * layer + (c >> 1));   // group g arrived
                         }
                         ct_mbar_spin(&bar_hfull[c], (uint32_t)fill & 1u);
                         ct_mbar_spin(&bar_full[stage], phase);
@@ -382,6 +392,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         }
                         ct_commit(&bar_empty[stage]);  // frees the lo ring slot when these MMAs have read it
                         if (++stage == CT_LSTAGES) { stage = 0; phase ^= 1; }
+                        if (c & 1) CT_TRACE(1, 6 + 12 * layer + (c >> 1));   // corrections of group g issued
                     }
                     if (layer == 0) {
                         // main products of layer 2 as two N halves over the whole of K (all hi planes are resident):
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                                 if (half == 1) ct_commit(&bar_hempty[c]);   // the next layer's hi plane may land here
                             }
                             ct_commit(&bar_d2[half]);
+                            CT_TRACE(1, 10 + half);
                         }
                     } else {
                         for (int c = 0; c < CT_CHUNKS; ++c) {
@@ -418,6 +430,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                         ct_mma_ss(tR0, ct_desc(aw_hi, 2048, 128), ct_desc(wc_lo, 4096, 128), CT_IDESC, 1);
                         ct_mma_ss_rescale(tR0, ct_desc(aw_hi, 2048, 128), ct_desc(wc_hi, 4096, 128), CT_IDESC);
                         ct_commit(bar_d3);
+                        CT_TRACE(1, 22);
                     }
                     a_phase ^= 1;
                 }
@@ -434,7 +447,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
         float amax = 0.0f;
         CtRow cur;
         if ((int)blockIdx.x < ntiles) ct_issue_row(a, blockIdx.x, row, 16 * part, cur);
+        const int trace_it_base = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int trace_it = (warp == 0 && lane == 0) ? it + trace_it_base : 99;
+            CT_TRACE(0, 0);
             // ---------- layer 1 ----------  (row operands + first chunk were issued during the previous tile)
             const int p_out = cur.p;
             const bool valid_out = cur.valid;
@@ -468,6 +484,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             const int buf = it & 1;
             ct_mbar_wait(&bar_pf[buf], (uint32_t)(it >> 1) & 1u);
             const float *p1row = reinterpret_cast<const float *>(s_p1 + buf * CT_P1_BYTES) + (row >> 4) * CT_C;
+            CT_TRACE(0, 1);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = 16 * (part + 4 * ch);   // K step part + 4 ch
@@ -476,7 +493,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    if (DBG && (a.debug & 2)) break;
+                    if (DBG && (a.debug & 2)) { hi[2 * g] = hi[2 * g + 1] = lo[2 * g] = lo[2 * g + 1] = 0; continue; }
                     const int c = c0 + 4 * g;
                     const float4 u = cur.u[g];
                     const float4 v1 = *reinterpret_cast<const float4 *>(p1row + c);   // 16 lanes share a row: broadcast
@@ -515,22 +532,26 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                     rt_mbar_arrive(&bar_a[ch]);
                     if (ch == 3) rt_mbar_arrive(&bar_pe[buf]);   // this warp is done with the tile's P1 rows
                 }
+                CT_TRACE(0, 2 + ch);
             }
 
             // ---------- mid epilogue: layer-2 accumulator -> bias, LeakyReLU -> A operand of layer 3, in place ----------
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = 16 * (part + 4 * ch);
-                if (ch == 0) { ct_mbar_wait(&bar_d2[0], d_phase); ct_fence_after(); }   // columns [0,128)
-                if (ch == 2) { ct_mbar_wait(&bar_d2[1], d_phase); ct_fence_after(); }   // columns [128,256)
+                if (ch == 0) { ct_mbar_wait(&bar_d2[0], d_phase); ct_fence_after(); CT_TRACE(0, 6); }   // columns [0,128)
+                if (ch == 2) { ct_mbar_wait(&bar_d2[1], d_phase); ct_fence_after(); CT_TRACE(0, 7); }   // columns [128,256)
                 uint32_t r[16], hi[8], lo[8];
                 if (!(DBG && (a.debug & 4))) {
-                ct_ld16(tR0 + lane_base + c0, r);
-                ct_ld_wait();
+                    ct_ld16(tR0 + lane_base + c0, r);
+                    ct_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = 0;
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (DBG && (a.debug & 4)) break;
+                    if (DBG && (a.debug & 4)) { hi[i] = lo[i] = 0; continue; }
                     const float2 b = *reinterpret_cast<const float2 *>(s_b2 + c0 + 2 * i);
                     const float2 x = leaky01x2(rt_ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
                                                         make_float2(CT_WINV, CT_WINV), b));
@@ -544,17 +565,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
                 ct_fence_before();
                 __syncwarp();
                 if (lane == 0) rt_mbar_arrive(&bar_a[ch]);   // layer 3 starts on this K group (its accumulator is R1: dead)
+                CT_TRACE(0, 8 + ch);
             }
             // next tile's index / xyz / first P2 chunk: in flight during the layer-3 MMAs and the final epilogue
             if (tile + (int)gridDim.x < ntiles) ct_issue_row(a, tile + gridDim.x, row, 16 * part, cur);
 
             // ---------- final epilogue: LeakyReLU(layer 3) * ReLU(WeightNet), summed over the 16 neighbours ----------
+            CT_TRACE(0, 12);
             ct_mbar_wait(bar_d3, d_phase);
             d_phase ^= 1;
             ct_fence_after();
+            CT_TRACE(0, 13);
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
-                if (DBG && (a.debug & 8)) break;
+                if (DBG && (a.debug & 8)) continue;
                 // two of the warp's K-step column blocks per pass: 32 values per row, as in the 32-column butterfly
                 const int ca = 16 * (part + 8 * hc), cb = ca + 64;
                 uint32_t rd[32], rw[32];
@@ -612,6 +636,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             ct_fence_before();
             __syncwarp();
             if (lane == 0) rt_mbar_arrive(bar_epi);
+            CT_TRACE(0, 14);
         }
         // fp16 range guard (|x| < 65504): report, never silently saturate
         if (!(amax < 65000.0f)) atomicOr(a.status, 2);
@@ -659,9 +684,30 @@ int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2,
     const int ntiles = (total_pts + CT_PTS - 1) / CT_PTS;
     if (const char *env = getenv("RT_CV_GRID")) sms = atoi(env) > 0 ? atoi(env) : sms;   // experiment: fewer CTAs (is the kernel SM-local or L2-bound?)
     CostVolTcArgs a{total_pts, n, p1, p2, xyz1, xyz2, knn, perm, w1x, (const __half *)wpack, (const __half *)wcpack,
-                    b2, b3, bc, wa, ba, wb, bb, out, status, 0};
+                    b2, b3, bc, wa, ba, wb, bb, out, status, nullptr, 0};
     if (const char *env = getenv("RT_CV_DEBUG")) a.debug = atoi(env);
+    static unsigned long long *trace_buf = nullptr;
+    const bool trace = getenv("RT_CV_TRACE") != nullptr;
+    if (trace) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 6 * 2 * 32 * 8);
+        cudaMemsetAsync(trace_buf, 0, 6 * 2 * 32 * 8, st);
+        a.trace = trace_buf;
+        if (!a.debug) a.debug = 64;
+    }
     if (a.debug) costvol_tc_kernel<true><<<ntiles < sms ? ntiles : sms, CT_THREADS, SM_TOTAL, st>>>(a);   // phase knock-outs: timing only
     else costvol_tc_kernel<false><<<ntiles < sms ? ntiles : sms, CT_THREADS, SM_TOTAL, st>>>(a);
+    if (trace) {   // debugging aid: per-phase clock64 stamps of CTA 0, relative to the first stamp of each tile
+        unsigned long long h[6 * 2 * 32];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int it = 1; it < 4; ++it) {
+            const unsigned long long t0 = h[(it * 2) * 32];
+            fprintf(stderr, "[costvol trace] tile %d worker:", it);
+            for (int i = 0; i < 15; ++i) fprintf(stderr, " %lld", h[(it * 2) * 32 + i] ? (long long)(h[(it * 2) * 32 + i] - t0) : -1ll);
+            fprintf(stderr, "\n[costvol trace] tile %d mma   :", it);
+            for (int i = 0; i < 23; ++i) fprintf(stderr, " %lld", h[(it * 2 + 1) * 32 + i] ? (long long)(h[(it * 2 + 1) * 32 + i] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+    }
     return rt_check_launch("costvol_tc_kernel");
 }

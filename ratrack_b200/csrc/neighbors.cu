@@ -11,6 +11,8 @@
 //     gives each hit its slot in index order (the reference's "first nsample in scan order"),
 //     whole-warp early exit once nsample hits are found;
 //   * three_nn / knn use one thread per query reading the tile with shared-memory broadcasts.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -139,6 +141,105 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(int n, int m, fl
             const int fill = st[i].fb >= 0 ? st[i].fb : 0;
             for (int s = st[i].cb + lane; s < nsample_b; s += 32) out[s] = fill;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ball_query, one THREAD per query (round 2).  The warp-per-query kernel above pays a ballot / popcount / prefix step
+// for every 32 candidates of every query (~13 issued instructions per distance); here a thread owns a query and walks
+// the cloud from shared memory two candidates at a time with packed fp32 pairs (FADD2 / FMUL2 / FFMA2: every half is
+// the same round-to-nearest operation as rt_sqdist, so the distances are bit-identical): 6 arithmetic instructions and
+// one combined test per pair.  A hit (rare per step) branches into an in-order append, which is the reference's
+// "first nsample in scan order" by construction.  A full list disables itself by dropping its threshold to -1 (no
+// distance is negative); the warp leaves the scan when all of its 32 queries are full.
+// Candidates are staged NEGATED and as pairs: (-x0,-x1,-y0,-y1) / (-z0,-z1), so q - p is one packed add; slots past
+// the cloud hold -inf (distance +inf, never a hit).
+constexpr int BQT_THREADS = 128;
+
+__device__ __forceinline__ void bqt_append(float d, int k, float &ta, float &tb, int &ca, int &cb, int &fa, int &fb, int nsa, int nsb,
+                                           int *__restrict__ oa, int *__restrict__ ob) {
+    if (d < ta) {
+        if (fa < 0) fa = k;
+        oa[ca] = k;
+        if (++ca == nsa) ta = -1.0f;
+    }
+    if (d < tb) {
+        if (fb < 0) fb = k;
+        ob[cb] = k;
+        if (++cb == nsb) tb = -1.0f;
+    }
+}
+
+__global__ void __launch_bounds__(BQT_THREADS) ball_query_thread_kernel(int n, int m, float radius_a, int nsample_a, int *__restrict__ idx_a,
+                                                                         float radius_b, int nsample_b, int *__restrict__ idx_b,
+                                                                         const float *__restrict__ new_xyz,
+                                                                         const float *__restrict__ xyz, int zero_fill,
+                                                                         const int *__restrict__ counts) {
+    __shared__ float4 s_xy[TILE_PTS / 2];
+    __shared__ float2 s_z[TILE_PTS / 2];
+    const int cloud = blockIdx.y;
+    const float *pts = xyz + (size_t)cloud * n * 3;
+    if (counts) n = min(n, __ldg(counts + cloud));   // padded variable-size batch: only the cloud's own points are candidates
+    const int q = blockIdx.x * BQT_THREADS + threadIdx.x;
+    const bool ok = q < m;
+    const float *c = new_xyz + ((size_t)cloud * m + (ok ? q : 0)) * 3;
+    const float qx = __ldg(c + 0), qy = __ldg(c + 1), qz = __ldg(c + 2);
+    const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz);
+    // thresholds: squared radius while the list is open, -1 once it is full (or for an out-of-range query / disabled list)
+    float ta = ok ? __fmul_rn(radius_a, radius_a) : -1.0f;
+    float tb = (ok && nsample_b > 0) ? __fmul_rn(radius_b, radius_b) : -1.0f;
+    int ca = 0, cb = 0, fa = -1, fb = -1;
+    int *oa = idx_a + ((size_t)cloud * m + (ok ? q : 0)) * nsample_a;
+    int *ob = idx_b + ((size_t)cloud * m + (ok ? q : 0)) * nsample_b;
+    const float ninf = __int_as_float(0xff800000);
+
+    for (int base = 0; base < n; base += TILE_PTS) {
+        const int tn = min(TILE_PTS, n - base);
+        const int npairs = (((tn + 1) >> 1) + 3) & ~3;   // pairs, padded to the unroll factor
+        if (base > 0) __syncthreads();  // everyone finished reading the previous tile
+        for (int p = threadIdx.x; p < npairs; p += BQT_THREADS) {
+            const int k0 = 2 * p, k1 = 2 * p + 1;
+            const float *g = pts + (size_t)(base + k0) * 3;
+            const float x0 = k0 < tn ? -__ldg(g + 0) : ninf, y0 = k0 < tn ? -__ldg(g + 1) : ninf, z0 = k0 < tn ? -__ldg(g + 2) : ninf;
+            const float x1 = k1 < tn ? -__ldg(g + 3) : ninf, y1 = k1 < tn ? -__ldg(g + 4) : ninf, z1 = k1 < tn ? -__ldg(g + 5) : ninf;
+            s_xy[p] = make_float4(x0, x1, y0, y1);
+            s_z[p] = make_float2(z0, z1);
+        }
+        __syncthreads();
+        for (int p0 = 0; p0 < npairs; p0 += 4) {
+            if (__all_sync(0xffffffffu, fmaxf(ta, tb) < 0.0f)) break;   // every query of the warp has both lists full
+            float2 d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 xy = s_xy[p0 + u];
+                const float2 z = s_z[p0 + u];
+                const float2 dx = rt_fadd2(qx2, make_float2(xy.x, xy.y)), dy = rt_fadd2(qy2, make_float2(xy.z, xy.w)),
+                             dz = rt_fadd2(qz2, z);
+                d[u] = rt_ffma2(dz, dz, rt_ffma2(dx, dx, rt_fmul2(dy, dy)));   // rt_sqdist's order: dy*dy, +dx*dx, +dz*dz
+            }
+            const float tmax = fmaxf(ta, tb);
+            const float dmin = fminf(fminf(fminf(d[0].x, d[0].y), fminf(d[1].x, d[1].y)), fminf(fminf(d[2].x, d[2].y), fminf(d[3].x, d[3].y)));
+            if (dmin < tmax) {   // (NaN distances are never hits: fminf drops them, as `d < r2` does)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = base + 2 * (p0 + u);
+                    bqt_append(d[u].x, k, ta, tb, ca, cb, fa, fb, nsample_a, nsample_b, oa, ob);
+                    bqt_append(d[u].y, k + 1, ta, tb, ca, cb, fa, fb, nsample_a, nsample_b, oa, ob);
+                }
+            }
+        }
+        if (__syncthreads_and(fmaxf(ta, tb) < 0.0f)) break;   // (uniform exit: the loop head has a CTA barrier)
+    }
+    // pad unused slots with the first hit; queries with no hit leave the caller's buffer untouched (the reference's
+    // Python zero-fills it first) unless `zero_fill` asks this kernel to write the zeros itself (engine: no memset launch)
+    if (!ok) return;
+    if (fa >= 0 || zero_fill) {
+        const int fill = fa >= 0 ? fa : 0;
+        for (int s2 = ca; s2 < nsample_a; ++s2) oa[s2] = fill;
+    }
+    if (nsample_b > 0 && (fb >= 0 || zero_fill)) {
+        const int fill = fb >= 0 ? fb : 0;
+        for (int s2 = cb; s2 < nsample_b; ++s2) ob[s2] = fill;
     }
 }
 
@@ -331,12 +432,28 @@ inline size_t tile_bytes_pad32(int n) { return (size_t)((min(n, TILE_PTS) + 31) 
 
 }  // namespace
 
+// RT_BQ_WARP=1 selects the round-1 warp-per-query kernel (A/B timing)
+static bool bq_use_thread_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char *env = getenv("RT_BQ_WARP");
+        v = (env && atoi(env) == 1) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // replaces ball_query_wrapper_fast (reference: src/lib/src/ball_query.cpp:18-29)
 RT_API int rt_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
                          int *idx, void *stream) {
     RT_REQUIRE(b >= 0 && n >= 0 && m >= 0 && nsample >= 0 && new_xyz && xyz && idx, "ball_query: bad arguments");
     if (b == 0 || m == 0 || nsample == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "ball_query: batch > 65535");
+    if (bq_use_thread_kernel()) {
+        dim3 grid(rt_divup(m, BQT_THREADS), b);
+        ball_query_thread_kernel<<<grid, BQT_THREADS, 0, (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx, new_xyz, xyz, 0,
+                                                                                  nullptr);
+        return rt_check_launch("ball_query_thread_kernel");
+    }
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), (cudaStream_t)stream>>>(n, m, radius, nsample, idx, 0.0f, 0, idx,
                                                                                  new_xyz, xyz, 0, nullptr);
@@ -348,6 +465,12 @@ int rt_launch_ball_query2(int b, int n, int m, float radius_a, int nsample_a, in
                           int *idx_b, const float *new_xyz, const float *xyz, int zero_fill, cudaStream_t st, const int *counts) {
     if (b == 0 || m == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535 && nsample_a > 0 && nsample_b > 0, "ball_query2: bad arguments");
+    if (bq_use_thread_kernel()) {
+        dim3 grid(rt_divup(m, BQT_THREADS), b);
+        ball_query_thread_kernel<<<grid, BQT_THREADS, 0, st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b, new_xyz, xyz,
+                                                                zero_fill, counts);
+        return rt_check_launch("ball_query_thread_kernel(2 radii)");
+    }
     dim3 grid(rt_divup(m, BQ_QPB), b);
     ball_query_kernel<<<grid, BQ_THREADS, tile_bytes_pad32(n), st>>>(n, m, radius_a, nsample_a, idx_a, radius_b, nsample_b, idx_b,
                                                               new_xyz, xyz, zero_fill, counts);
