@@ -15,6 +15,9 @@ enum {
 
 void rt_set_error(const char *fmt, ...);
 int rt_check_launch(const char *what);  // cudaGetLastError() -> code (+ message)
+// stream-ordered scratch from a per-device pool that keeps its memory cached (runtime.cu)
+int rt_scratch_alloc(void **p, size_t bytes, cudaStream_t st, const char *what);
+void rt_scratch_free(void *p, cudaStream_t st);
 
 #define RT_REQUIRE(cond, ...)                \
     do {                                     \

@@ -154,14 +154,11 @@ RT_API int rt_dbscan(int b, int n, int d, const float *x, float eps, int min_sam
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *scratch = nullptr;
     if (big) {
-        const cudaError_t e = cudaMallocAsync(&scratch, adj_bytes * (size_t)b, st);
-        if (e != cudaSuccess) {
-            rt_set_error("dbscan: cudaMallocAsync(%zu): %s", adj_bytes * (size_t)b, cudaGetErrorString(e));
-            return (int)e;
-        }
+        const int ae = rt_scratch_alloc((void **)&scratch, adj_bytes * (size_t)b, st, "dbscan");
+        if (ae != RT_OK) return ae;
     }
     dbscan_kernel<<<b, DB_THREADS, smem, st>>>(n, d, x, (double)eps * (double)eps, min_samples, labels, scratch);
     const int rc = rt_check_launch("dbscan_kernel");
-    if (scratch) cudaFreeAsync(scratch, st);
+    rt_scratch_free(scratch, st);
     return rc;
 }

@@ -606,21 +606,21 @@ RT_API int rt_furthest_point_sampling(int b, int n, int m, const float *xyz, flo
     // (and every other shape) take the serial kernel
     int *ok = nullptr;
     if (m == n && n >= 128 && n <= 1024 && b <= 65535) {
-        if (cudaMallocAsync(&ok, sizeof(int) * (size_t)b, st) == cudaSuccess) {
+        if (rt_scratch_alloc((void **)&ok, sizeof(int) * (size_t)b, st, "furthest_point_sampling") == RT_OK) {
             const int rc0 = rt_launch_fps_identity(b, n, xyz, temp, ok, idx, nullptr, nullptr, nullptr, st);
             if (rc0 != RT_OK) {
-                cudaFreeAsync(ok, st);
+                rt_scratch_free(ok, st);
                 return rc0;
             }
         } else {
-            ok = nullptr;
+            ok = nullptr;   // no scratch: the serial kernel alone is always correct
             (void)cudaGetLastError();
         }
     }
     g_fps_skip = ok;
     const int rc = fps_dispatch(b, n, m, xyz, temp, idx, nullptr, st, &launched);
     g_fps_skip = nullptr;
-    if (ok) cudaFreeAsync(ok, st);
+    rt_scratch_free(ok, st);
     if (rc != RT_OK || launched) return rc;
     RT_REQUIRE(!ok, "furthest_point_sampling: internal (identity shortcut without a register-resident kernel)");
     const int bs = rt_ref_block_size(n);

@@ -25,13 +25,13 @@ constexpr int G_CH_SLAB = 16;  // channels per CTA (grid.y = ceil(C / slab))
 
 // out[b,c,e] = points[b,c,idx[b,e]]   for e in [0, E): gather_points (E = npoints) and
 // group_points (E = npoints*nsample) are the same operation.
-__global__ void __launch_bounds__(G_THREADS) gather_rows_kernel(int c, int n, long long e_total,
+__global__ void __launch_bounds__(G_THREADS) gather_rows_kernel(int c, int n, long long e_total, int slab,
                                                                 const float *__restrict__ points,
                                                                 const int *__restrict__ idx,
                                                                 float *__restrict__ out) {
     const int b = blockIdx.z;
-    const int c0 = blockIdx.y * G_CH_SLAB;
-    const int c1 = min(c, c0 + G_CH_SLAB);
+    const int c0 = blockIdx.y * slab;
+    const int c1 = min(c, c0 + slab);
     const long long e0 = ((long long)blockIdx.x * G_THREADS + threadIdx.x) * 4;
     if (e0 >= e_total) return;
     const int *ix = idx + (size_t)b * e_total + e0;
@@ -106,6 +106,53 @@ __global__ void __launch_bounds__(G_THREADS) three_interpolate_kernel(int c, int
         *dst = __fmaf_rn(w2, __ldg(src + i2), t);
         src += m;
         dst += n;
+    }
+}
+
+// The same interpolation with the slab of source rows (slab x m floats) staged in shared memory: the three gathers per
+// output become shared-memory reads (a few bank conflicts) instead of L1 requests that touch up to 32 sectors each, a
+// thread owns 4 consecutive outputs (indices / weights loaded once as 128-bit vectors) and stores 128 bits per channel.
+// (A point-major slab -- one 128-bit shared-memory load per source and 4 channels -- was measured slower: 28.6 vs 22.5 us
+// at C=128, the transposing stores of the staging cost more than the gathers save.)
+constexpr int TI_THREADS = 256;
+__global__ void __launch_bounds__(TI_THREADS) three_interpolate_smem_kernel(int c, int m, int n, int slab,
+                                                                               const float *__restrict__ points,
+                                                                               const int *__restrict__ idx,
+                                                                               const float *__restrict__ weight,
+                                                                               float *__restrict__ out) {
+    extern __shared__ __align__(16) float s_src[];   // slab x m
+    const int b = blockIdx.z, c0 = blockIdx.y * slab, nc = min(slab, c - c0);
+    const float *src = points + ((size_t)b * c + c0) * m;
+    const int total = nc * m;
+    if ((m & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int i = threadIdx.x; i < total / 4; i += TI_THREADS) reinterpret_cast<float4 *>(s_src)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < total; i += TI_THREADS) s_src[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // n % 4 == 0 (checked by the launcher): groups of 4 outputs never straddle the end
+    for (int j0 = (blockIdx.x * TI_THREADS + threadIdx.x) * 4; j0 < n; j0 += gridDim.x * TI_THREADS * 4) {
+        const int4 *ix = reinterpret_cast<const int4 *>(idx + ((size_t)b * n + j0) * 3);
+        const float4 *wp = reinterpret_cast<const float4 *>(weight + ((size_t)b * n + j0) * 3);
+        const int4 ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
+        const float4 wa = __ldg(wp), wb = __ldg(wp + 1), wc = __ldg(wp + 2);
+        const int i[12] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w, ic.x, ic.y, ic.z, ic.w};
+        const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+        float *dst = out + ((size_t)b * c + c0) * n + j0;
+        const float *row = s_src;
+        for (int ch = 0; ch < nc; ++ch) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // fma(w2, p[i2], fma(w0, p[i0], w1 * p[i1])): the reference's sm_100 evaluation order
+                float t = __fmul_rn(w[3 * q + 1], row[i[3 * q + 1]]);
+                t = __fmaf_rn(w[3 * q + 0], row[i[3 * q + 0]], t);
+                v[q] = __fmaf_rn(w[3 * q + 2], row[i[3 * q + 2]], t);
+            }
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1], v[2], v[3]));
+            dst += n;
+            row += m;
+        }
     }
 }
 
@@ -195,8 +242,11 @@ int launch_gather(int b, int c, int n, long long e_total, const float *points, c
                   cudaStream_t st, const char *what) {
     if (b == 0 || c == 0 || e_total == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "%s: batch > 65535", what);
-    dim3 grid(rt_divup(e_total, (long long)G_THREADS * 4), rt_divup(c, G_CH_SLAB), b);
-    gather_rows_kernel<<<grid, G_THREADS, 0, st>>>(c, n, e_total, points, idx, out);
+    // channels per CTA: 16 amortise the index loads; narrow tensors (xyz: C = 3) take one channel per CTA instead, or the
+    // whole op is a handful of half-empty CTAs walking the channels serially (gather_points C=3: 9.1 -> 7.0 us)
+    const int slab = c >= 32 ? G_CH_SLAB : (c >= 8 ? 4 : 1);
+    dim3 grid(rt_divup(e_total, (long long)G_THREADS * 4), rt_divup(c, slab), b);
+    gather_rows_kernel<<<grid, G_THREADS, 0, st>>>(c, n, e_total, slab, points, idx, out);
     return rt_check_launch(what);
 }
 
@@ -258,6 +308,20 @@ RT_API int rt_three_interpolate(int b, int c, int m, int n, const float *points,
                "three_interpolate: bad arguments");
     if (b == 0 || c == 0 || n == 0) return RT_OK;
     RT_REQUIRE(b <= 65535, "three_interpolate: batch > 65535");
+    const int slab = smem_slab(c, m);
+    const bool aligned = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (slab > 0 && aligned && smem_opt_in(three_interpolate_smem_kernel)) {
+        // split the outputs of a (cloud, slab) over CTAs only while there are too few (cloud, slab) pairs to fill the GPU
+        const int pairs = b * rt_divup(c, slab);
+        int split = pairs >= 296 ? 1 : rt_divup(296, pairs);
+        const int max_split = rt_divup(n, TI_THREADS * 4);
+        split = split > max_split ? max_split : split;
+        dim3 sgrid(split, rt_divup(c, slab), b);
+        three_interpolate_smem_kernel<<<sgrid, TI_THREADS, (size_t)slab * m * sizeof(float), (cudaStream_t)stream>>>(c, m, n, slab, points,
+                                                                                                              idx, weight, out);
+        return rt_check_launch("three_interpolate");
+    }
     dim3 grid(rt_divup(n, G_THREADS), rt_divup(c, G_CH_SLAB), b);
     three_interpolate_kernel<<<grid, G_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
     return rt_check_launch("three_interpolate");

@@ -175,17 +175,14 @@ RT_API int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha,
     cudaStream_t st = (cudaStream_t)stream;
     float *zscratch = nullptr;
     if (!in_smem) {   // more than 127 objects on a side: the reference has no limit (track4d.py:166-180), so neither has this entry
-        const cudaError_t e = cudaMallocAsync(&zscratch, zbytes * (size_t)b, st);
-        if (e != cudaSuccess) {
-            rt_set_error("sinkhorn_match: cudaMallocAsync(%zu): %s", zbytes * (size_t)b, cudaGetErrorString(e));
-            return (int)e;
-        }
+        const int ae = rt_scratch_alloc((void **)&zscratch, zbytes * (size_t)b, st, "sinkhorn_match");
+        if (ae != RT_OK) return ae;
     }
     if (M <= 96 && N <= 96)
         sinkhorn_match_kernel<8><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
     else
         sinkhorn_match_kernel<32><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
     const int rc = rt_check_launch("sinkhorn_match_kernel");
-    if (zscratch) cudaFreeAsync(zscratch, st);
+    rt_scratch_free(zscratch, st);
     return rc;
 }
