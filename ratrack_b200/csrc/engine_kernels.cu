@@ -604,20 +604,54 @@ __global__ void __launch_bounds__(256) gather_rows3_kernel(int clouds, int npts_
 
 __global__ void __launch_bounds__(256) cloud_max_kernel(int npts, int c, const float *__restrict__ f, int ldf, float *__restrict__ g,
                                                         const int *__restrict__ counts) {
-    // grid (cloud, channel-block of 32); 256 threads = 8 point-lanes x 32 channels
+    // grid (cloud, channel-block of 32); 256 threads = 32 point-lanes x 8 channel quads (128-bit loads), four independent
+    // loads in flight per thread (the first version walked its points with one dependent 32-bit load at a time: 22 us for
+    // 33 MB).  max is exact in any order.
     // counts (optional): valid points per cloud of a padded batch (rows beyond are ignored; the row stride stays npts)
-    __shared__ float s[8][33];
-    const int cloud = blockIdx.x, ch = blockIdx.y * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+    __shared__ float4 s[32][9];
+    const int cloud = blockIdx.x, cq = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int ch = blockIdx.y * 32 + 4 * cq;
     const int np = counts ? min(npts, __ldg(counts + cloud)) : npts;
-    float m = -__int_as_float(0x7f800000);
-    if (ch < c)
-        for (int p = pl; p < np; p += 8) m = fmaxf(m, __ldg(f + ((long long)cloud * npts + p) * ldf + ch));
-    s[pl][threadIdx.x & 31] = m;
+    const float ninf = -__int_as_float(0x7f800000);
+    float4 m = make_float4(ninf, ninf, ninf, ninf);
+    const float *base = f + (long long)cloud * npts * ldf + ch;
+    if (ch + 3 < c && (ldf & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        int p = pl;
+        for (; p + 96 < np; p += 128) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4 *>(base + (long long)p * ldf));
+            const float4 a1 = __ldg(reinterpret_cast<const float4 *>(base + (long long)(p + 32) * ldf));
+            const float4 a2 = __ldg(reinterpret_cast<const float4 *>(base + (long long)(p + 64) * ldf));
+            const float4 a3 = __ldg(reinterpret_cast<const float4 *>(base + (long long)(p + 96) * ldf));
+            m.x = fmaxf(fmaxf(m.x, a0.x), fmaxf(fmaxf(a1.x, a2.x), a3.x));
+            m.y = fmaxf(fmaxf(m.y, a0.y), fmaxf(fmaxf(a1.y, a2.y), a3.y));
+            m.z = fmaxf(fmaxf(m.z, a0.z), fmaxf(fmaxf(a1.z, a2.z), a3.z));
+            m.w = fmaxf(fmaxf(m.w, a0.w), fmaxf(fmaxf(a1.w, a2.w), a3.w));
+        }
+        for (; p < np; p += 32) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4 *>(base + (long long)p * ldf));
+            m.x = fmaxf(m.x, a0.x); m.y = fmaxf(m.y, a0.y); m.z = fmaxf(m.z, a0.z); m.w = fmaxf(m.w, a0.w);
+        }
+    } else {
+        for (int p = pl; p < np; p += 32) {
+            if (ch + 0 < c) m.x = fmaxf(m.x, __ldg(base + (long long)p * ldf + 0));
+            if (ch + 1 < c) m.y = fmaxf(m.y, __ldg(base + (long long)p * ldf + 1));
+            if (ch + 2 < c) m.z = fmaxf(m.z, __ldg(base + (long long)p * ldf + 2));
+            if (ch + 3 < c) m.w = fmaxf(m.w, __ldg(base + (long long)p * ldf + 3));
+        }
+    }
+    s[pl][cq] = m;
     __syncthreads();
-    if (pl == 0 && ch < c) {
-#pragma unroll
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, s[i][threadIdx.x & 31]);
-        g[(long long)cloud * c + ch] = m;
+    if (pl == 0) {
+#pragma unroll 8
+        for (int i = 1; i < 32; ++i) {
+            const float4 o = s[i][cq];
+            m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); m.z = fmaxf(m.z, o.z); m.w = fmaxf(m.w, o.w);
+        }
+        float *o = g + (long long)cloud * c + ch;
+        if (ch + 0 < c) o[0] = m.x;
+        if (ch + 1 < c) o[1] = m.y;
+        if (ch + 2 < c) o[2] = m.z;
+        if (ch + 3 < c) o[3] = m.w;
     }
 }
 

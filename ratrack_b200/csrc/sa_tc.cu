@@ -35,6 +35,8 @@ struct SaTcArgs {
     const float *wx, *b1;        // [C1, 3], [C1]
     const void *wpack;           // second conv, fp16 hi/lo planes of 2^10 W in core-matrix layout
     const float *b2;
+    const void *wpack3;          // optional third conv (C3 > 0) and its bias
+    const float *b3;
     float *out;                  // out[(cloud * npts + centre) * ldo + ooff + c]
     int ldo, ooff;
     int *status;
@@ -124,27 +126,32 @@ __device__ __forceinline__ void sa_group_max(float *v, int lane, int &col0, int 
 template <int C1>
 constexpr int sa_ystride() { return C1 + 4; }   // floats; = 4 (mod 32): 8 lanes reading 16 B of rows r..r+7 hit 32 distinct banks
 
-template <int C1, int C2>
+template <int C1, int C2, int C3>
 constexpr int sa_slot_cols() {   // TMEM columns of one tile slot: accumulator + A planes, a power of two so 4 slots tile the 512
-    int need = C2 + C1, c = 32;
+    int need = (C2 > C3 ? C2 : C3) + (C1 > C2 || C3 == 0 ? C1 : C2), c = 32;
     while (c < need) c *= 2;
     return c;
 }
 
-template <int C1, int C2, int NS>
+template <int C1, int C2, int C3, int NS>
 __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
     constexpr int NS_SHIFT = NS == 32 ? 5 : NS == 16 ? 4 : NS == 8 ? 3 : NS == 4 ? 2 : NS == 2 ? 1 : 0;
     constexpr int YS = sa_ystride<C1>();
-    constexpr int SLOT_COLS = sa_slot_cols<C1, C2>();
-    constexpr int WBYTES = 4 * C1 * C2;
+    constexpr int SLOT_COLS = sa_slot_cols<C1, C2, C3>();
+    constexpr int DCOLS = C2 > C3 ? C2 : C3;                       // accumulator columns
+    constexpr int ACOLS = (C1 > C2 || C3 == 0) ? C1 : C2;          // A operand columns (hi plane + lo plane)
+    constexpr int CL = C3 > 0 ? C3 : C2;                           // channels of the pooled output
+    constexpr int WBYTES = 4 * C1 * C2, WBYTES3 = 4 * C2 * C3;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_d[SA_SLOTS];
     __shared__ uint32_t tmem_slot;
     // carve-up: weights | gather constants | bias | xyz of the points | centres | Y table
     uint8_t *s_w = smem;
-    float4 *s_gc = reinterpret_cast<float4 *>(smem + WBYTES);               // [C1 / 2][2]: {wx0,wx1,wy0,wy1} {wz0,wz1,b0,b1}
+    uint8_t *s_w3 = smem + WBYTES;
+    float4 *s_gc = reinterpret_cast<float4 *>(smem + WBYTES + WBYTES3);     // [C1 / 2][2]: {wx0,wx1,wy0,wy1} {wz0,wz1,b0,b1}
     float *s_b2 = reinterpret_cast<float *>(s_gc + C1);
-    float4 *s_xyz = reinterpret_cast<float4 *>(s_b2 + C2);
+    float *s_b3 = s_b2 + C2;
+    float4 *s_xyz = reinterpret_cast<float4 *>(s_b3 + (C3 > 0 ? C3 : 4));
     float4 *s_ctr = s_xyz + a.n_in;
     float *s_y = reinterpret_cast<float *>(s_ctr + a.npts);
 
@@ -156,6 +163,12 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.wpack);
         uint4 *dst = reinterpret_cast<uint4 *>(s_w);
         for (int i = tid; i < WBYTES / 16; i += SA_THREADS) dst[i] = __ldg(src + i);
+        if (C3 > 0) {
+            const uint4 *src3 = reinterpret_cast<const uint4 *>(a.wpack3);
+            uint4 *dst3 = reinterpret_cast<uint4 *>(s_w3);
+            for (int i = tid; i < WBYTES3 / 16; i += SA_THREADS) dst3[i] = __ldg(src3 + i);
+            for (int i = tid; i < C3; i += SA_THREADS) s_b3[i] = a.b3 ? __ldg(a.b3 + i) : 0.0f;
+        }
         for (int i = tid; i < C1 / 2; i += SA_THREADS) {
             const int c = 2 * i;
             s_gc[2 * i] = make_float4(__ldg(a.wx + c * 3 + 0), __ldg(a.wx + c * 3 + 3), __ldg(a.wx + c * 3 + 1), __ldg(a.wx + c * 3 + 4));
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
     __syncthreads();
     sa_fence_after();
     const uint32_t tm = tmem_slot;
-    const uint32_t tD = tm + slot * SLOT_COLS, tAhi = tD + C2, tAlo = tAhi + C1 / 2;
+    const uint32_t tD = tm + slot * SLOT_COLS, tAhi = tD + DCOLS, tAlo = tAhi + ACOLS / 2;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
 
     const int T = (a.npts * NS) / 128;   // tiles per cloud (the launcher guarantees divisibility)
@@ -263,10 +276,50 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
             sa_mbar_wait(&bar_d[slot], d_phase);
             d_phase ^= 1;
             sa_fence_after();
+            if (C3 > 0) {
+                // ---------- mid epilogue: bias, ReLU -> A operand of the third conv; its MMAs; wait ----------
+#pragma unroll
+                for (int c0 = 0; c0 < C2; c0 += 16) {
+                    uint32_t r[16], hi_[8], lo_[8];
+                    sa_ld16(tD + lane_base + c0, r);
+                    sa_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 x = rt_ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
+                                                  make_float2(SA_WINV, SA_WINV), *reinterpret_cast<const float2 *>(s_b2 + c0 + 2 * i));
+                        sa_split2(make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)), hi_[i], lo_[i], amax);
+                    }
+                    sa_st8(tAhi + lane_base + c0 / 2, hi_);
+                    sa_st8(tAlo + lane_base + c0 / 2, lo_);
+                }
+                sa_st_wait();
+                sa_fence_before();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");   // A complete, accumulator read by all four warps
+                if (rit == 0) {
+                    sa_fence_after();
+                    constexpr uint32_t LBO3 = ((C3 > 0 ? C3 : 8) / 8) * 128;
+                    const uint32_t hi_base = rt_smem_u32(s_w3), lo_base = hi_base + 2 * C2 * C3;
+                    constexpr uint32_t IDESC3 = sa_idesc(C3 > 0 ? C3 : 8);
+#pragma unroll
+                    for (int kk = 0; kk < C2 / 16; ++kk) {
+                        sa_mma_ts(tD, tAlo + 8 * kk, sa_desc(hi_base + kk * 2 * LBO3, LBO3, 128), IDESC3, kk > 0);
+                        sa_mma_ts(tD, tAhi + 8 * kk, sa_desc(lo_base + kk * 2 * LBO3, LBO3, 128), IDESC3, 1);
+                    }
+                    sa_mma_ts_rescale(tD, tAhi, sa_desc(hi_base, LBO3, 128), IDESC3);
+#pragma unroll
+                    for (int kk = 1; kk < C2 / 16; ++kk) sa_mma_ts(tD, tAhi + 8 * kk, sa_desc(hi_base + kk * 2 * LBO3, LBO3, 128), IDESC3, 1);
+                    sa_commit(&bar_d[slot]);
+                }
+                __syncwarp();
+                sa_mbar_wait(&bar_d[slot], d_phase);
+                d_phase ^= 1;
+                sa_fence_after();
+            }
             // ---------- epilogue: bias, ReLU, max over the NS rows of a centre ----------
+            const float *s_bl = C3 > 0 ? s_b3 : s_b2;
             float *orow = a.out + ((size_t)cloud * a.npts + centre) * a.ldo + a.ooff;
 #pragma unroll
-            for (int c0 = 0; c0 < C2; c0 += 16) {
+            for (int c0 = 0; c0 < CL; c0 += 16) {
                 uint32_t r[16];
                 sa_ld16(tD + lane_base + c0, r);
                 sa_ld_wait();
@@ -274,7 +327,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float2 x = rt_ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(SA_WINV, SA_WINV),
-                                              *reinterpret_cast<const float2 *>(s_b2 + c0 + i));
+                                              *reinterpret_cast<const float2 *>(s_bl + c0 + i));
                     v[i] = fmaxf(x.x, 0.0f);
                     v[i + 1] = fmaxf(x.y, 0.0f);
                 }
@@ -308,36 +361,38 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_tc_kernel(SaTcArgs a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
 
-template <int C1, int C2, int NS>
+template <int C1, int C2, int C3, int NS>
 int sa_launch(const SaTcArgs &a, size_t smem_bytes, int grid, cudaStream_t st) {
     static RtPerDevice attr_set;
     if (!attr_set.done(rt_current_device())) {
-        const cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel<C1, C2, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+        const cudaError_t e = cudaFuncSetAttribute(sa_tc_kernel<C1, C2, C3, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
         if (e != cudaSuccess) {
             rt_set_error("sa_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
         attr_set.mark(rt_current_device());
     }
-    sa_tc_kernel<C1, C2, NS><<<grid, SA_THREADS, smem_bytes, st>>>(a);
+    sa_tc_kernel<C1, C2, C3, NS><<<grid, SA_THREADS, smem_bytes, st>>>(a);
     return rt_check_launch("sa_tc_kernel");
 }
 
 }  // namespace
 
-// Tries the shared-memory-table kernel for a gather-mode / max-pool RtMlpTc job with ONE tensor-core layer.  Returns
+// Tries the shared-memory-table kernel for a gather-mode / max-pool RtMlpTc job with one or two tensor-core layers.  Returns
 // RT_ERR_UNSUPPORTED (without setting an error text) when the shape is not instantiated or the table does not fit: the
 // caller then launches the generic kernel.
 int rt_launch_sa_tc(const RtMlpTc &m, int clouds, cudaStream_t st) {
-    if (m.load_mode != RT_MLP_LOAD_GATHER || m.out_mode != RT_MLP_OUT_MAXPOOL || m.nlayers != 1 || m.cloud_bias || m.mid_out)
+    if (m.load_mode != RT_MLP_LOAD_GATHER || m.out_mode != RT_MLP_OUT_MAXPOOL || m.nlayers < 1 || m.nlayers > 2 || m.cloud_bias || m.mid_out)
         return RT_ERR_UNSUPPORTED;
-    const int c1 = m.c1, c2 = m.layer[0].n, ns = m.ns;
-    if (m.layer[0].k != c1 || m.layer[0].act != RT_ACT_RELU || m.n_out != c2) return RT_ERR_UNSUPPORTED;
+    const int c1 = m.c1, c2 = m.layer[0].n, c3 = m.nlayers == 2 ? m.layer[1].n : 0, ns = m.ns;
+    if (m.layer[0].k != c1 || m.layer[0].act != RT_ACT_RELU || m.n_out != (c3 ? c3 : c2)) return RT_ERR_UNSUPPORTED;
+    if (c3 && (m.layer[1].k != c2 || m.layer[1].act != RT_ACT_RELU)) return RT_ERR_UNSUPPORTED;
     if (clouds <= 0 || m.rows != (long long)clouds * m.npts * ns || (m.npts * ns) % 128 != 0) return RT_ERR_UNSUPPORTED;
     if ((m.ldy & 3) || (m.yoff & 3) || (reinterpret_cast<uintptr_t>(m.y) & 15) || (m.ldo & 3) || (m.ooff & 3) ||
         (reinterpret_cast<uintptr_t>(m.out) & 15))
         return RT_ERR_UNSUPPORTED;
-    const size_t smem_bytes = (size_t)4 * c1 * c2 + (size_t)c1 * 16 + (size_t)c2 * 4 + (size_t)(m.n_in + m.npts) * 16 + (size_t)m.n_in * (c1 + 4) * 4;
+    const size_t smem_bytes = (size_t)4 * c1 * c2 + (size_t)4 * c2 * c3 + (size_t)c1 * 16 + (size_t)c2 * 4 + (size_t)(c3 ? c3 : 4) * 4 +
+                              (size_t)(m.n_in + m.npts) * 16 + (size_t)m.n_in * (c1 + 4) * 4;
     if (smem_bytes > 227 * 1024 - 256) return RT_ERR_UNSUPPORTED;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -347,13 +402,15 @@ int rt_launch_sa_tc(const RtMlpTc &m, int clouds, cudaStream_t st) {
     long long grid = tiles / 8;
     grid = grid < 1 ? 1 : (grid > sms ? sms : grid);
     SaTcArgs a{clouds, m.npts, m.n_in, m.y, m.ldy, m.yoff, m.idx, m.xyz_in, m.xyz_c, m.wx, m.b1, m.layer[0].wpack, m.layer[0].bias,
-               m.out, m.ldo, m.ooff, m.status};
-#define SA_CASE(C1, C2, NS) \
-    if (c1 == C1 && c2 == C2 && ns == NS) return sa_launch<C1, C2, NS>(a, smem_bytes, (int)grid, st)
-    SA_CASE(32, 32, 8);
-    SA_CASE(32, 64, 16);
-    SA_CASE(64, 64, 16);
-    SA_CASE(64, 64, 32);
+               c3 ? m.layer[1].wpack : nullptr, c3 ? m.layer[1].bias : nullptr, m.out, m.ldo, m.ooff, m.status};
+#define SA_CASE(C1, C2, C3, NS) \
+    if (c1 == C1 && c2 == C2 && c3 == C3 && ns == NS) return sa_launch<C1, C2, C3, NS>(a, smem_bytes, (int)grid, st)
+    SA_CASE(16, 16, 32, 4);    // level 1 (three convolutions)
+    SA_CASE(16, 16, 32, 8);
+    SA_CASE(32, 32, 0, 8);     // level 2
+    SA_CASE(32, 64, 0, 16);
+    SA_CASE(64, 64, 0, 16);    // level 3
+    SA_CASE(64, 64, 0, 32);
 #undef SA_CASE
     return RT_ERR_UNSUPPORTED;
 }
