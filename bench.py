@@ -18,6 +18,7 @@ Printed JSON (one line, rank 0):
   ref_gpu      (informational) the reference's own CUDA kernels (oracle/_ref) under the same torch modules
   train        (informational, BASELINE configs[2]) the training step at batch 256 per GPU with the time and bytes of its
                two collectives (gradient all_reduce, affinity all_gather)
+  train_cfg4   (informational, BASELINE configs[4]) the same step at N=3000 points, 16 pairs per GPU (= batch 128 on 8 GPUs)
 --impl reference times the reference's CPU path (the oracle port: the reference has no CPU implementation of
 its native ops, and its Python cannot travel to the GPU box) on the host cores.
 """
@@ -186,7 +187,7 @@ def _collective_ms(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-def train_record(dev, rank, world, B, N, steps, warmup):
+def train_record(dev, rank, world, B, N, steps, warmup, label="configs[2] geometry"):
     """Training step (ratrack_b200/train.py) on synthetic frame pairs and synthetic targets: forward (train-mode BatchNorm)
     + track_4d_loss + backward + gradient all-reduce (overlapped with the tail of backward, ranks > 1) + Adam; weak scaling
     (B pairs per GPU).  -> dict (rank 0) with frames/s, step time, peak memory and the two collectives' time / bytes."""
@@ -256,7 +257,7 @@ def train_record(dev, rank, world, B, N, steps, warmup):
     rec = {"metric": "frames/sec on Bx%d-pt radar pairs (training step: forward + multi-task loss + backward + Adam)" % N,
            "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": ms / steps, "scaling": "weak", "dtype": "f32",
-           "config": {"workload": f"synthetic N={N} pts, batch={B} per GPU, forward+backward multi-task loss (configs[2] geometry)",
+           "config": {"workload": f"synthetic N={N} pts, batch={B} per GPU, forward+backward multi-task loss ({label})",
                       "batch_per_gpu": B, "points": N, "npoints": 512,
                       "path": "modular (CUDA pointnet2 ops + deterministic grad kernels under autograd)", "parallelism": f"dp{world}"},
            "collectives": coll, "gpu_launches": _cabi.launch_count, "clocks": clk, "final_loss": float(loss),
@@ -410,7 +411,7 @@ def main():
     pairs_total, ms = sharding.job_throughput(count * a.steps, ms, device=dev)          # SUM of pairs, MAX of device time
     _, ms_e2e = sharding.job_throughput(count * a.steps, ms_e2e, device=dev)
 
-    train = None
+    train = train4 = None
     if not a.no_train and not a.modular:
         del t, flush
         net._engine = None
@@ -419,6 +420,13 @@ def main():
             train = train_record(dev, rank, world, 256, N, steps=3, warmup=2)
         except Exception as e:  # informational only
             train = {"unavailable": str(e)[:200]}
+        try:
+            # BASELINE configs[4]: N~3000 (3 accumulated VoD frames), batch 128 over 8 GPUs = 16 pairs per GPU (weak scaling:
+            # the same 16-pair shard per GPU at every N, so N=8 is the configuration itself)
+            train4 = train_record(dev, rank, world, 16, 3000, steps=2, warmup=1,
+                                  label="configs[4] geometry: N~3000, batch 128 / 8 GPUs = 16 per GPU")
+        except Exception as e:  # informational only
+            train4 = {"unavailable": str(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -458,6 +466,8 @@ def main():
     }
     if train is not None:
         out["train"] = train
+    if train4 is not None:
+        out["train_cfg4"] = train4
     if world == 1 and not a.no_cpu:
         v, cores, dt = cpu_reference_rate(pairs=32, micro=8, points=N)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

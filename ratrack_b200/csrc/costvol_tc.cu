@@ -536,36 +536,46 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             }
 
             // ---------- mid epilogue: layer-2 accumulator -> bias, LeakyReLU -> A operand of layer 3, in place ----------
+            // two K steps (one per N half ... of the same half) per TMEM round trip: load both, convert both, store both
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const int c0 = 16 * (part + 4 * ch);
-                if (ch == 0) { ct_mbar_wait(&bar_d2[0], d_phase); ct_fence_after(); CT_TRACE(0, 6); }   // columns [0,128)
-                if (ch == 2) { ct_mbar_wait(&bar_d2[1], d_phase); ct_fence_after(); CT_TRACE(0, 7); }   // columns [128,256)
-                uint32_t r[16], hi[8], lo[8];
+            for (int hp = 0; hp < 2; ++hp) {
+                ct_mbar_wait(&bar_d2[hp], d_phase);   // columns [128 hp, 128 hp + 128)
+                ct_fence_after();
+                CT_TRACE(0, 6 + hp);
+                const int ca = 16 * (part + 8 * hp), cb = ca + 64;   // K steps part + 8 hp and part + 8 hp + 4
+                uint32_t r[32], hi[16], lo[16];
                 if (!(DBG && (a.debug & 4))) {
-                    ct_ld16(tR0 + lane_base + c0, r);
+                    ct_ld16(tR0 + lane_base + ca, r);
+                    ct_ld16(tR0 + lane_base + cb, r + 16);
                     ct_ld_wait();
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = 0;
+                    for (int i = 0; i < 32; ++i) r[i] = 0;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     if (DBG && (a.debug & 4)) { hi[i] = lo[i] = 0; continue; }
-                    const float2 b = *reinterpret_cast<const float2 *>(s_b2 + c0 + 2 * i);
+                    const int c = (i < 8 ? ca : cb - 16) + 2 * i;
+                    const float2 b = *reinterpret_cast<const float2 *>(s_b2 + c);
                     const float2 x = leaky01x2(rt_ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])),
                                                         make_float2(CT_WINV, CT_WINV), b));
                     split2(x.x, x.y, hi[i], lo[i], amax);
                 }
                 if (!(DBG && (a.debug & 4))) {
-                ct_st8(tR0 + lane_base + c0, hi);
-                ct_st8(tR0 + lane_base + c0 + 8, lo);
+                    ct_st8(tR0 + lane_base + ca, hi);
+                    ct_st8(tR0 + lane_base + ca + 8, lo);
+                    ct_st8(tR0 + lane_base + cb, hi + 8);
+                    ct_st8(tR0 + lane_base + cb + 8, lo + 8);
                 }
                 ct_st_wait();
                 ct_fence_before();
                 __syncwarp();
-                if (lane == 0) rt_mbar_arrive(&bar_a[ch]);   // layer 3 starts on this K group (its accumulator is R1: dead)
-                CT_TRACE(0, 8 + ch);
+                if (lane == 0) {   // layer 3 starts on these K groups (its accumulator is R1: dead)
+                    rt_mbar_arrive(&bar_a[2 * hp]);
+                    rt_mbar_arrive(&bar_a[2 * hp + 1]);
+                }
+                CT_TRACE(0, 8 + 2 * hp);
+                CT_TRACE(0, 9 + 2 * hp);
             }
             // next tile's index / xyz / first P2 chunk: in flight during the layer-3 MMAs and the final epilogue
             if (tile + (int)gridDim.x < ntiles) ct_issue_row(a, tile + gridDim.x, row, 16 * part, cur);
@@ -639,7 +649,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
             CT_TRACE(0, 14);
         }
         // fp16 range guard (|x| < 65504): report, never silently saturate
-        if (!(amax < 65000.0f)) atomicOr(a.status, 2);
+        if (!(amax < 65000.0f) && !(DBG && (a.debug & 48))) atomicOr(a.status, 2);   // (stale weights of the traffic knock-outs are not data)
     }
     ct_fence_before();
     __syncthreads();
@@ -650,24 +660,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) costvol_tc_kernel(CostVolTcArgs
 
 // engine-internal launcher.  wpack = [layer 2,3][8 chunks][hi,lo][kc 4][row group 32][8][8] fp16 of 2^10 * W;
 // wcpack = [hi,lo][kc 2][row group 32][8][8] fp16 of 2^10 * Wc (K 8 padded to 16).
-int rt_launch_costvol_tc_v2(int total_pts, int n, const float *p1, const float *p2, const float *xyz1, const float *xyz2,
-                            const int *knn, const int *perm, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
-                            const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
-                            float *out, int *status, cudaStream_t st);
-
 int rt_launch_costvol_tc(int total_pts, int n, const float *p1, const float *p2, const float *xyz1, const float *xyz2,
                          const int *knn, const int *perm, const float *w1x, const void *wpack, const void *wcpack, const float *b2,
                          const float *b3, const float *bc, const float *wa, const float *ba, const float *wb, const float *bb,
                          float *out, int *status, cudaStream_t st) {
     if (total_pts <= 0) return RT_OK;
-    static int use_v2 = -1;   // RT_CV_V2=1: the round-1 kernel (8 worker warps, serial MMA / epilogue phases) for A/B timing
-    if (use_v2 < 0) {
-        const char *env = getenv("RT_CV_V2");
-        use_v2 = (env && atoi(env) == 1) ? 1 : 0;
-    }
-    if (use_v2)
-        return rt_launch_costvol_tc_v2(total_pts, n, p1, p2, xyz1, xyz2, knn, perm, w1x, wpack, wcpack, b2, b3, bc, wa, ba, wb, bb, out,
-                                       status, st);
     static RtPerDevice attr_set;
     if (!attr_set.done(rt_current_device())) {
         cudaError_t e = cudaFuncSetAttribute(costvol_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);

@@ -168,13 +168,13 @@ __global__ void __launch_bounds__(T *CPB) fps_reg_kernel(int nclouds, int n, int
             if (lane == 0) red_mine[boff] = make_uint2(wmax, (uint32_t)wi);
             group_sync();
             const uint2 *rb = red_base + boff;
-            uint2 b = rb[0];
-#pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const uint2 c = rb[w];
-                if (c.x > b.x) b = c;
-            }
-            win = (int)b.y;
+            // every warp picks the winner of the NW warp maxima with one more redux / ballot / shuffle (lane w reads warp
+            // w's entry; the lowest warp wins ties, as a serial `>` scan would).  ncu had half of a round's stall samples on
+            // the serial scan of the 8 entries (profiles/r2_ncu_fps.txt).  Key 0 is below every ordered key of a finite value.
+            const uint2 mine = lane < NW ? rb[lane] : make_uint2(0u, 0u);
+            const uint32_t kmax = rt_redux_max_u32(mine.x);
+            const uint32_t v2 = __ballot_sync(0xffffffffu, lane < NW && mine.x == kmax);
+            win = (int)__shfl_sync(0xffffffffu, mine.y, __ffs(v2) - 1);
         }
         old = win;
         if (t == 0) idx[j] = old;
