@@ -341,4 +341,5 @@ def roofline_of_dominant(batch, points, dom_ms, peaks, launch_pairs=None):
     return {"kernel": "costvol_tc_kernel: gather + cost-volume MLP (2 x [rows x 256 x 256], LeakyReLU) + WeightNet sum",
             "bound": "tensor", "achieved": ach, "peak": peak, "peak_source": peaks["src"] + " dense bf16 (sustained)",
             "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "avg_launch_ms": avg_ms, "flops_per_launch": flops,
+            "traffic_source": "profiles/costvol_traffic.json: dram__bytes_read + dram__bytes_write of one launch of this kernel (ncu --set full capture, tools/collect_profiles.sh)",
             "note": "achieved counts the fp32-accurate useful FLOPs; the tensor pipe executes 3x that (fp16 hi/lo split products)"}

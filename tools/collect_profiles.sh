@@ -1,17 +1,38 @@
 #!/bin/bash
-# copy the evidence of tools/gpu_final.sh from gpurun_out/ (scratch) into profiles/ (tracked); run in the dev container
+# copy the evidence of tools/gpu_final_r2.sh from gpurun_out/ (scratch) into profiles/ (tracked); run in the dev container
 set -e
 cd "$(dirname "$0")/.."
-R=${1:-r1}
+R=${1:-r2}
 cp gpurun_out/bench_final.json profiles/${R}_bench_final.json
 cp gpurun_out/bench_reference.json profiles/${R}_bench_reference_arm.json
-cp gpurun_out/bench_train.json profiles/${R}_bench_train.json
 cp gpurun_out/ops_roofline.json profiles/${R}_ops_roofline.json
 cp gpurun_out/ops_roofline.txt profiles/${R}_ops_roofline.txt
-cp gpurun_out/timeline.txt profiles/${R}_timeline_final.txt
-{ echo "# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised) of: python bench.py --steps 2 --warmup 1 --no-cpu"
-  echo "# = 3 device-resident forwards + 4 forwards of the end-to-end leg; one-time kernels (pack_umma) belong to engine creation"
-  python tools/launch_digest.py gpurun_out/launches_bench.csv 7; } > profiles/${R}_launches_fused_final.txt
+cp gpurun_out/timeline.txt profiles/${R}_timeline.txt
+cp gpurun_out/stage_profile.txt profiles/${R}_stage_profile.txt
+cp gpurun_out/train_profile.txt profiles/${R}_train_profile.txt
+{ echo "# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised) of: python bench.py --total 64 --steps 2 --warmup 1 --no-cpu --no-train"
+  echo "# = 6 device-resident forwards + 6 forwards of the end-to-end leg (2 micro-batches of 32 pairs per step); one-time kernels (pack_umma) belong to engine creation"
+  python tools/launch_digest.py gpurun_out/launches_bench.csv 12; } > profiles/${R}_launches.txt
 { cat gpurun_out/host.log; tail -n 3 gpurun_out/pytest_gpu.log; tail -n 1 gpurun_out/smoke.log; } > profiles/${R}_gpu_tests.txt
-[ -f gpurun_out/parity_report.txt ] && cp gpurun_out/parity_report.txt profiles/${R}_parity_report.txt
-ls profiles
+{ echo "# ncu --set full --clock-control none --import-source on, one launch, B=32 N=1024 (python tools/run_forward.py 32 1); digest by tools/ncu_digest.py + tools/ncu_lines.py"
+  python tools/ncu_digest.py gpurun_out/r2_costvol_final.ncu-rep 24; python tools/ncu_lines.py gpurun_out/r2_costvol_final.ncu-rep 24; } > profiles/${R}_ncu_costvol_tc.txt
+{ echo "# ncu --set full, one launch: sa_tc_kernel<64,64,0,32> = SA3 ns=32 scale of pn_head (64 clouds, 1 M rows), B=32 N=1024"
+  python tools/ncu_digest.py gpurun_out/r2_sa3_final.ncu-rep 16; python tools/ncu_lines.py gpurun_out/r2_sa3_final.ncu-rep 16; } > profiles/${R}_ncu_sa_tc.txt
+{ echo "# ncu --set full, one launch: ball_query_thread_kernel, level 1 (64 clouds, 512 centres x 1024 points, radii 2 / 4)"
+  python tools/ncu_digest.py gpurun_out/r2_bq_final.ncu-rep 12; python tools/ncu_lines.py gpurun_out/r2_bq_final.ncu-rep 12; } > profiles/${R}_ncu_ball_query.txt
+# DRAM traffic of the dominant kernel for bench.py's roofline.traffic: from the same capture
+python - <<PY
+import csv, json, subprocess
+raw = subprocess.run(["ncu", "-i", "gpurun_out/r2_costvol_final.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+h, u, r = rows[0], rows[1], rows[2]
+def val(k):
+    i = h.index(k); v = float(r[i].replace(",", "")); unit = u[i]
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+json.dump({"kernel": "costvol_tc_kernel", "batch": 32, "points": 1024, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
+           "source": "profiles/${R}_ncu_costvol_tc.txt (ncu --set full, one launch, B=32 N=1024, the round-2 kernel)"},
+          open("profiles/costvol_traffic.json", "w"), indent=1)
+print("costvol traffic", rd + wr)
+PY
+ls profiles | wc -l
