@@ -20,8 +20,10 @@
 
 namespace {
 
-constexpr int MT_WORKER_WARPS = 8;   // two per TMEM lane quarter: they split the 16-column chunks of a row between them
-constexpr int MT_THREADS = 32 * (MT_WORKER_WARPS + 1);
+// worker warps: NW / 4 per TMEM lane quarter, they split the 16-column chunks of a row between them.  8 for the narrow shapes
+// that keep 2-3 CTAs resident per SM; 16 for the shapes that fill an SM's TMEM / shared memory with ONE CTA (N = 256 layers),
+// where 9 warps leave the SM's schedulers idle between the TMEM round trips of the loader and the epilogues
+constexpr int mt_threads(int nw) { return 32 * (nw + 1); }
 constexpr float MT_WINV = 1.0f / 1024.0f;
 // x = hi + lo with two fp16 planes; the lo plane is stored as 2^11 * lo so that it is a NORMAL fp16 number whenever hi is
 // (an unscaled lo of an activation below 0.25 is subnormal and loses up to 10 bits: tools/tc_precision.cu, data set 2)
@@ -156,8 +158,9 @@ __device__ __forceinline__ void mt_gather_issue(const RtMlpTc &a, long long tile
     r.yrow = a.y + g * a.ldy + a.yoff;
 }
 
-template <int LOAD_MODE>
-__global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
+template <int LOAD_MODE, int MT_WORKER_WARPS>
+__global__ void __launch_bounds__(mt_threads(MT_WORKER_WARPS), MT_WORKER_WARPS == 8 ? 3 : 1) mlp_tc_kernel(RtMlpTc a) {
+    constexpr int MT_THREADS = mt_threads(MT_WORKER_WARPS), NPART = MT_WORKER_WARPS / 4;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_a, bar_d, bar_w;
     __shared__ uint32_t tmem_slot;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
         __syncwarp();
     } else {
         // ===== worker warps: one thread per row =====
-        const int q = warp & 3, hlf = warp >> 2;        // TMEM lane quarter, chunk parity
+        const int q = warp & 3, hlf = warp >> 2;        // TMEM lane quarter, chunk residue (mod NPART)
         const int row_in_tile = 32 * q + lane;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         uint32_t d_phase = 0;
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                         const float *r2 = a.seg[s].x + (cbase + __ldg(ix + 2)) * a.seg[s].ldx;
                         const float w0 = __ldg(ww + 0), w1 = __ldg(ww + 1), w2 = __ldg(ww + 2);
                         for (int o = 0; o < ks; o += 16, c0 += 16) {
-                            if (((c0 >> 4) & 1) != hlf) continue;
+                            if (((c0 >> 4) % NPART) != hlf) continue;
                             float v[16];
                             float4 q0[4], q1[4], q2[4];
                             if ((a.seg[s].ldx & 7) == 0) {   // rows are 32-byte aligned: 256-bit loads
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                     const float *x = a.seg[s].x + rc * a.seg[s].ldx;
                     const bool vec = (a.seg[s].ldx & 3) == 0;
                     for (int o = 0; o < ks; o += 16, c0 += 16) {
-                        if (((c0 >> 4) & 1) != hlf) continue;
+                        if (((c0 >> 4) % NPART) != hlf) continue;
                         float v[16];
                         if (vec && o + 16 <= ks) {
                             float4 t[4];
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                 }
             } else {
                 // index, xyz difference and row pointer were fetched during the previous tile; the row itself now
-                for (int c0 = 16 * hlf; c0 < a.c1; c0 += 32) {
+                for (int c0 = 16 * hlf; c0 < a.c1; c0 += 16 * NPART) {
                     float v[16];
                     float4 t[4];
                     if ((a.ldy & 7) == 0 && (a.yoff & 7) == 0) {
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(MT_THREADS, 3) mlp_tc_kernel(RtMlpTc a) {
                 const float *cb = (l == 0 && a.cloud_bias)
                                       ? a.cloud_bias + (size_t)((uint32_t)rc / (uint32_t)a.rows_per_cloud) * a.cloud_bias_ld : nullptr;
                 const bool last = l == a.nlayers - 1;
-                for (int c0 = 16 * hlf; c0 < n; c0 += 32) {
+                for (int c0 = 16 * hlf; c0 < n; c0 += 16 * NPART) {
                     uint32_t r[16];
                     mt_ld16(tD + lane_base + c0, r);
                     if (a.nsplit == 2 && a.layer[l].k >= 64) {   // second K half accumulated separately (see the issuer)
@@ -524,9 +527,11 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     RT_REQUIRE(wbytes <= 200 * 1024, "mlp_tc: %d bytes of weights do not fit in shared memory", wbytes);
     static RtPerDevice smem_set;
     if (!smem_set.done(rt_current_device())) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_ROWS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+            e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_GATHER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_tc_kernel<RT_MLP_LOAD_ROWS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e != cudaSuccess) {
             rt_set_error("mlp_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
@@ -550,8 +555,15 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
     long long grid = (long long)sms * per_sm;
     if (grid > ntiles) grid = ntiles;
     cudaLaunchConfig_t cfg = {};
+    // one CTA per SM anyway (TMEM or shared memory): give it 16 worker warps
+    static int wide_env = -1;
+    if (wide_env < 0) {
+        const char *env = getenv("RT_MLP_WIDE");   // RT_MLP_WIDE=0: always 8 worker warps (A/B timing)
+        wide_env = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    const bool wide = wide_env && per_sm == 1 && !gather;
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(MT_THREADS);
+    cfg.blockDim = dim3(mt_threads(wide ? 16 : 8));
     cfg.dynamicSmemBytes = (size_t)(wbytes + gc_bytes);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -567,8 +579,9 @@ int rt_launch_mlp_tc(RtMlpTc a, cudaStream_t st) {
         use_pdl = (env && atoi(env) == 1) ? 1 : 0;
     }
     cfg.numAttrs = use_pdl ? 1 : 0;
-    const cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_GATHER>, a)
-                                  : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_ROWS>, a);
+    const cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_GATHER, 8>, a)
+                           : wide ? cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_ROWS, 16>, a)
+                                  : cudaLaunchKernelEx(&cfg, mlp_tc_kernel<RT_MLP_LOAD_ROWS, 8>, a);
     if (le != cudaSuccess) {
         rt_set_error("mlp_tc_kernel: launch failed: %s", cudaGetErrorString(le));
         return (int)le;

@@ -1,3 +1,5 @@
 #!/bin/bash
-for t in 256 128; do RT_FPS_THREADS=$t python tools/bench_ops.py 2>/dev/null | grep furthest | sed "s/^/T=$t /"; done
-for t in 256 128; do RT_FPS_THREADS=$t python tools/stage_profile.py 32 10 > /dev/null 2>&1; echo "T=$t $(cat gpurun_out/stage_profile.txt | awk '{printf "%s ", $1}')"; done
+timeout 120 tools/tma_gather_probe
+echo "--- wide mlp_tc A/B"
+timeout 600 python -m pytest tests/test_gpu_backbone.py -m gpu -q --tb=short -x 2>&1 | tail -n 2
+for wv in 0 1; do RT_MLP_WIDE=$wv python tools/stage_profile.py 32 10 > /dev/null 2>&1; echo "RT_MLP_WIDE=$wv $(cat gpurun_out/stage_profile.txt | awk '{printf "%s ", $1}')"; done
