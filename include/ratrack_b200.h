@@ -185,6 +185,36 @@ int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha, int it
  * d <= 16; n <= 1024 keeps the adjacency in shared memory, n <= 16384 uses a stream-ordered scratch (cudaMallocAsync). */
 int rt_dbscan(int b, int n, int d, const float *x, float eps, int min_samples, int *labels, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 4 -- dense layers of the training step on the tcgen05 tensor cores
+ *
+ * The reference trains through torch autograd: every 1x1 convolution / Linear of SharedMLP, FeatureCorrelator,
+ * FlowPredictor, ClsPredictor and PNHead (reference: src/lib/pytorch_utils.py:35-101,
+ * src/utils/model_utils/model_utils.py:223-231, 308-357, 393-424) is a (rows x k).(n x k)^T product over all
+ * (batch, point, neighbour) rows, served by cuDNN / cuBLAS fp32 kernels in forward, dgrad and wgrad.  These entry
+ * points are those three products: fp32 in / out, split-fp16 operands with fp32 TMEM accumulation (fp32-class
+ * accuracy), bit-repeatable.  Row-major operands with explicit leading dimensions (in elements).
+ * ------------------------------------------------------------------------------------------ */
+
+/* amax_out[0] = max |x[i]|, i < count (device scalar; the kernels below read it on the device to scale an operand of
+ * unbounded dynamic range -- a gradient -- into the range of the fp16 planes) */
+int rt_absmax(const float *x, long long count, float *amax_out, void *stream);
+
+/* y[r, j] = act(sum_i x[r, i] * W'[j, i] + bias[j]),  W'[j, i] = w[j * w_sn + i * w_sk],  r < rows, i < k, j < n.
+ * forward: w = the layer's (n x k) weight, w_sn = k, w_sk = 1.  dgrad (dX = dY . W): x = dY, k <-> n, w_sn = 1,
+ * w_sk = (row length of W).  bias (n) and x_amax (device scalar from rt_absmax: max |x|) may be NULL.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).  A value beyond the fp16 range (|x| >= 65504 without x_amax,
+ * |W| >= 64) yields inf / NaN in y, never a silently saturated result. */
+int rt_dense_tc_forward(long long rows, int k, int n, const float *x, long long ldx, const float *w, long long w_sn,
+                        long long w_sk, const float *bias, const float *x_amax, int act, float *y, long long ldy,
+                        void *stream);
+
+/* dw[j, i] = sum_r dy[r, j] * x[r, i]  (n x k, contiguous, overwritten).  dy_amax: device scalar max |dy| or NULL.
+ * The rows are split over the grid and the partial sums added in a fixed order (scratch from the library's
+ * stream-ordered pool). */
+int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long long lddy, const float *x, long long ldx,
+                      const float *dy_amax, float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

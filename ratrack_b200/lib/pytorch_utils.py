@@ -12,6 +12,8 @@ from typing import List
 import torch
 import torch.nn as nn
 
+from . import dense_tc
+
 
 class PointwiseConv2d(nn.Conv2d):
     """nn.Conv2d whose 1x1 / stride-1 case is evaluated as what it is: ONE GEMM over the channel axis, rows = all
@@ -36,7 +38,8 @@ class PointwiseConv2d(nn.Conv2d):
             x = x.contiguous(memory_format=torch.channels_last)        # every later layer stays channels-innermost
             dims = [0, 2, 3]
             rows = x.permute(0, 2, 3, 1)
-        y = nn.functional.linear(rows, self.weight.view(self.out_channels, self.in_channels), self.bias)
+        # forward / dgrad / wgrad on the tcgen05 kernels (dense_tc) for GEMM-shaped layers, torch's library GEMM for the rest
+        y = dense_tc.linear(rows, self.weight.view(self.out_channels, self.in_channels), self.bias)
         src = dims + [1]                                               # y's axes in terms of (B,C,H,W) axes
         return y.permute(*[src.index(d) for d in range(4)])            # (B,Cout,H,W) view, channels still innermost
 

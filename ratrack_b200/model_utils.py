@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .lib import pointnet2_utils
+from .lib import dense_tc, pointnet2_utils
 from .lib.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 from .lib.pytorch_utils import PointwiseConv2d
 
@@ -238,7 +238,7 @@ class PNHead(nn.Module):
 
     @staticmethod
     def _lin(layer, x):
-        return layer(x.permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+        return dense_tc.linear(x.permute(0, 2, 1).contiguous(), layer.weight, layer.bias).permute(0, 2, 1).contiguous()
 
     def forward(self, pc, features):
         l0_points = features.contiguous()
