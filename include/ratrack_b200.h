@@ -215,6 +215,19 @@ int rt_dense_tc_forward(long long rows, int k, int n, const float *x, long long 
 int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long long lddy, const float *x, long long ldx,
                       const float *dy_amax, float *dw, void *stream);
 
+/* replaces, in the channels-innermost layout of the training path, QueryAndGroup's chain
+ *   group_points(xyz) - new_xyz ; group_points(features) ; cat     (reference: src/lib/pointnet2_utils.py:269-292)
+ * xyz (b,n,3), new_xyz (b,npoint,3), feat_rows (b,n,c) [features with the channels innermost], idx (b,npoint,nsample)
+ * -> out (b,npoint,nsample,3+c): row = [xyz[idx] - new_xyz (3), feat_rows[idx] (c)] */
+int rt_group_rows(int b, int c, int n, int npoint, int nsample, const float *xyz, const float *new_xyz,
+                  const float *feat_rows, const int *idx, float *out, void *stream);
+
+/* its gradient w.r.t. the features (the reference: group_points_grad_kernel_fast, fp32 atomicAdd,
+ * src/lib/src/group_points_gpu.cu:8-25): grad_rows (b,npoint,nsample,3+c), idx -> grad_feat_rows (b,n,c), overwritten;
+ * a segmented sum in increasing source order: bit-repeatable. */
+int rt_group_rows_grad(int b, int c, int n, int npoint, int nsample, const float *grad_rows, const int *idx,
+                       float *grad_feat_rows, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,8 @@ SIGNATURES = {
     "rt_engine_stage_profile": [_P, _I],
     "rt_engine_last_status": [_P, ctypes.POINTER(ctypes.c_int)],
     "rt_engine_status_async": [_P, _P, _P],
+    "rt_group_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "rt_group_rows_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "rt_absmax": [_P, ctypes.c_longlong, _P, _P],
     "rt_dense_tc_forward": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, ctypes.c_longlong, _P, _P, _I, _P,
                             ctypes.c_longlong, _P],

@@ -38,7 +38,8 @@ namespace {
 constexpr int LT_ROWS = 128, LT_KC = 64, LT_NST = 3;
 constexpr int LT_PLANE = LT_ROWS * LT_KC * 2;   // one fp16 plane of a stage: 16 KB
 constexpr int LT_STAGE = 2 * LT_PLANE;
-constexpr int LT_EPI_WARPS = 4, LT_LOAD_WARPS = 8;
+constexpr int LT_EPI_WARPS = 4, LT_LOAD_WARPS = 16;
+constexpr int LT_TASKS = 32 / LT_LOAD_WARPS;   // warp tasks (8 rows x 4 K groups) per loader warp and stage
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_LOAD_WARPS + 1);
 constexpr float LT_WSCALE = 1024.0f;            // weights are staged as 2^10 W: their lo plane stays normal
 constexpr float LT_LO = 2048.0f;                // lo planes are stored as 2^11 lo
@@ -108,10 +109,13 @@ __device__ __forceinline__ void dt_split2(float x0, float x1, uint32_t &hi, uint
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 __device__ __forceinline__ void dt_split8(const float *v, float s, uint4 &hi, uint4 &lo) {
-    dt_split2(v[0] * s, v[1] * s, hi.x, lo.x);
-    dt_split2(v[2] * s, v[3] * s, hi.y, lo.y);
-    dt_split2(v[4] * s, v[5] * s, hi.z, lo.z);
-    dt_split2(v[6] * s, v[7] * s, hi.w, lo.w);
+    const float2 s2 = make_float2(s, s);
+    const float2 a = rt_fmul2(make_float2(v[0], v[1]), s2), b = rt_fmul2(make_float2(v[2], v[3]), s2);
+    const float2 c = rt_fmul2(make_float2(v[4], v[5]), s2), d = rt_fmul2(make_float2(v[6], v[7]), s2);
+    dt_split2(a.x, a.y, hi.x, lo.x);
+    dt_split2(b.x, b.y, hi.y, lo.y);
+    dt_split2(c.x, c.y, hi.z, lo.z);
+    dt_split2(d.x, d.y, hi.w, lo.w);
 }
 // power-of-two scale that brings an absolute maximum (its fp32 bit pattern) to [2^14, 2^15); 1 for a null pointer
 __device__ __forceinline__ float dt_scale_from_amax(const float *amax) {
@@ -248,51 +252,72 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     } else if (warp >= LT_EPI_WARPS) {
         // ===== loader warps: rows -> fp16 hi/lo planes in the K-major core-matrix layout =====
         // The (tile, K chunk) items of this CTA form one flat sequence; the loads of item i+1 are in flight while item i is
-        // converted and stored (two register sets), so a warp always has 4 x 32 bytes per thread outstanding.
+        // converted and stored (two register sets).  ncu on the first version (8 warps, generic addressing): 92 % of the
+        // kernel's instructions were the loaders', 115 per 32-byte task, two warps per scheduler -> instruction-latency bound
+        // at a third of the HBM rate.  Hence 16 warps and a lean path (whole tile in range, 32-byte aligned rows, full K chunks)
+        // whose per-task cost is one pointer add, one 256-bit load, the split and two 128-bit stores.
         const int lw = warp - LT_EPI_WARPS;
         const int mode = ((a.ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 31) == 0) ? 2
                        : ((a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) ? 1 : 0;
+        const bool lean_k = mode == 2 && (a.k % LT_KC) == 0;
         // a warp task = 8 rows x 4 K groups: lanes l, l+8, l+16, l+24 read 128 contiguous bytes of row (l & 7)
+        int t_r[LT_TASKS], t_kg[LT_TASKS], t_off[LT_TASKS];
+        long long t_src[LT_TASKS];
+#pragma unroll
+        for (int i = 0; i < LT_TASKS; ++i) {
+            const int wt = lw + LT_LOAD_WARPS * i;
+            t_r[i] = 8 * (wt >> 1) + (lane & 7);
+            t_kg[i] = ((wt & 1) << 2) + (lane >> 3);
+            t_off[i] = t_kg[i] * 2048 + (wt >> 1) * 128 + (lane & 7) * 16;   // a quarter warp writes 128 contiguous bytes
+            t_src[i] = (long long)t_r[i] * a.ldx + 8 * t_kg[i];
+        }
         auto issue = [&](long long tile, int kc, float (*v)[8]) {
             const long long row0 = tile * LT_ROWS;
+            if (lean_k && row0 + LT_ROWS <= a.rows) {
+                const float *p = a.x + row0 * a.ldx + kc * LT_KC;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int wt = lw + LT_LOAD_WARPS * i;
-                const int r = 8 * (wt >> 1) + (lane & 7), kg = ((wt & 1) << 2) + (lane >> 3);
-                dt_load8(a.x, a.ldx, row0 + r, row0 + r < a.rows, kc * LT_KC + 8 * kg, a.k, mode, v[i]);
+                for (int i = 0; i < LT_TASKS; ++i) {
+                    float4 lo4, hi4;
+                    rt_ldg256(p + t_src[i], lo4, hi4);
+                    v[i][0] = lo4.x; v[i][1] = lo4.y; v[i][2] = lo4.z; v[i][3] = lo4.w;
+                    v[i][4] = hi4.x; v[i][5] = hi4.y; v[i][6] = hi4.z; v[i][7] = hi4.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < LT_TASKS; ++i)
+                    dt_load8(a.x, a.ldx, row0 + t_r[i], row0 + t_r[i] < a.rows, kc * LT_KC + 8 * t_kg[i], a.k, mode, v[i]);
             }
         };
-        float cur[4][8], nxt[4][8];
-        long long tile = tile0;
-        int kc = 0;
-        if (tile < ntiles) issue(tile, kc, cur);
-        for (uint32_t it = 0; tile < ntiles; ++it) {
-            long long ntile = tile;
-            int nkc = kc + 1;
-            if (nkc == nchunks) { nkc = 0; ntile += tstep; }
-            if (ntile < ntiles) issue(ntile, nkc, nxt);
+        auto convert = [&](uint32_t it, float (*v)[8]) {
             const uint32_t s = it % LT_NST;
             dt_wait(&bar_empty[s], ((it / LT_NST) & 1u) ^ 1u);
             uint8_t *st = s_ring + s * LT_STAGE;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int wt = lw + LT_LOAD_WARPS * i;
-                const int rg = wt >> 1, kg = ((wt & 1) << 2) + (lane >> 3);
+            for (int i = 0; i < LT_TASKS; ++i) {
                 uint4 hi, lo;
-                dt_split8(cur[i], xs, hi, lo);
-                const int off = kg * 2048 + rg * 128 + (lane & 7) * 16;   // a quarter warp writes 128 contiguous bytes
-                *reinterpret_cast<uint4 *>(st + off) = hi;
-                *reinterpret_cast<uint4 *>(st + LT_PLANE + off) = lo;
+                dt_split8(v[i], xs, hi, lo);
+                *reinterpret_cast<uint4 *>(st + t_off[i]) = hi;
+                *reinterpret_cast<uint4 *>(st + LT_PLANE + t_off[i]) = lo;
             }
             rt_fence_proxy_async();
             __syncwarp();
             if (lane == 0) rt_mbar_arrive(&bar_full[s]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cur[i][j] = nxt[i][j];
-            tile = ntile;
-            kc = nkc;
+        };
+        auto advance = [&](long long &tile, int &kc) {
+            if (++kc == nchunks) { kc = 0; tile += tstep; }
+        };
+        float va[LT_TASKS][8], vb[LT_TASKS][8];
+        long long tile = tile0;
+        int kc = 0;
+        if (tile < ntiles) issue(tile, kc, va);
+        for (uint32_t it = 0; tile < ntiles; it += 2) {   // two items per trip: the register sets swap roles without copies
+            advance(tile, kc);
+            if (tile < ntiles) issue(tile, kc, vb);
+            convert(it, va);
+            if (tile >= ntiles) break;
+            advance(tile, kc);
+            if (tile < ntiles) issue(tile, kc, va);
+            convert(it + 1, vb);
         }
     } else {
         // ===== epilogue warps: one thread per row (TMEM lane) =====
@@ -342,8 +367,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
 // ---- wgrad ----------------------------------------------------------------------------------------------------------
 constexpr int WG_RCH = 64;                       // rows per stage = 4 K steps
 constexpr int WG_NST = 2;
+constexpr int WG_MAX_CHAIN = 16384;               // rows per accumulation chain (1024 K steps)
 constexpr int WG_LOAD_WARPS = 16;
-constexpr int WG_TASKS = 6;                     // warp tasks per loader warp and stage: (32 + 64) / 16
+constexpr int WG_TASKS = 6;                     // warp tasks per loader warp and stage: 2 of dy (32 / 16) + up to 4 of x (64 / 16)
 constexpr int WG_THREADS = 32 * (WG_LOAD_WARPS + 1);
 constexpr int WG_APLANE = 128 * WG_RCH * 2;      // 16 KB
 
@@ -417,42 +443,58 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
         __syncwarp();
     } else {
         // ===== loaders: thread = one channel x 8 consecutive rows -> one 16-byte core-matrix row (K = rows) =====
-        // warp task = 32 channels x 8 rows (8 coalesced 128-byte reads); tasks 0..31 = dy (128 channels x 8 row groups),
-        // then the x operand.  All of a warp's tasks of a stage (<= WG_TASKS) are issued before the first is converted.
-        const int nbt = (a.ktw + 31) / 32 * 8, ntasks = 32 + nbt;
+        // warp task = 32 channels x 8 rows (8 coalesced 128-byte reads).  Per stage: 32 tasks of the dy operand (128 channels x
+        // 8 row groups: tasks u = 0, 1 of each of the 16 warps) and up to 64 of the x operand (u = 2 .. 5); all of a warp's
+        // loads of a stage are issued before the first value is converted.  ncu on the first version: 22 instructions per
+        // load in generic addressing and predicates (issue-bound at 72 %), hence the lean path for stages and channel blocks
+        // that are entirely in range: a pointer walk, no predicates.
+        const int nbt = (a.ktw + 31) / 32 * 8;
+        int t_c[WG_TASKS], t_g[WG_TASKS], t_off[WG_TASKS];
+        bool t_live[WG_TASKS], t_full[WG_TASKS], t_ok[WG_TASKS];
+        const float *t_src[WG_TASKS];
+#pragma unroll
+        for (int u = 0; u < WG_TASKS; ++u) {
+            const bool isa = u < 2;
+            const int t2 = warp + WG_LOAD_WARPS * (isa ? u : u - 2);
+            const int c = (t2 >> 3) * 32 + lane, g = t2 & 7;
+            const int cb = (t2 >> 3) * 32;
+            t_c[u] = c;
+            t_g[u] = g;
+            t_live[u] = isa || t2 < nbt;
+            const int ch = (isa ? m0 : k0) + c;
+            t_ok[u] = t_live[u] && (isa ? ch < a.n : (c < a.ktw && ch < a.k));
+            t_full[u] = t_live[u] && (isa ? m0 + cb + 32 <= a.n : (cb + 32 <= a.ktw && k0 + cb + 32 <= a.k));   // warp-uniform
+            t_off[u] = g * (isa ? 2048 : a.ktw * 16) + (c >> 3) * 128 + (c & 7) * 16;
+            t_src[u] = (isa ? a.dy : a.x) + (long long)(8 * g) * (isa ? a.lddy : a.ldx) + ch;
+        }
         for (int it = 0; it < nstages; ++it) {
             const uint32_t s = (uint32_t)it % WG_NST;
             const long long r0 = r_begin + (long long)it * WG_RCH;
+            const bool rows_full = r0 + WG_RCH <= r_end;
             float v[WG_TASKS][8];
 #pragma unroll
             for (int u = 0; u < WG_TASKS; ++u) {
-                const int tk = warp + u * WG_LOAD_WARPS;
-                const bool isa = tk < 32;
-                const int t2 = isa ? tk : tk - 32;
-                const int c = (t2 >> 3) * 32 + lane, g = t2 & 7;
-                const float *src = isa ? a.dy : a.x;
-                const long long ld = isa ? a.lddy : a.ldx;
-                const int ch = (isa ? m0 : k0) + c;
-                const bool ch_ok = tk < ntasks && (isa ? ch < a.n : (c < a.ktw && ch < a.k));
-                const float *p = src + (r0 + 8 * g) * ld + ch;
+                const long long ld = u < 2 ? a.lddy : a.ldx;
+                const float *p = t_src[u] + r0 * ld;
+                if (rows_full && t_full[u]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[u][i] = (ch_ok && r0 + 8 * g + i < r_end) ? __ldg(p + i * ld) : 0.0f;
+                    for (int i = 0; i < 8; ++i, p += ld) v[u][i] = __ldg(p);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i, p += ld) v[u][i] = (t_ok[u] && r0 + 8 * t_g[u] + i < r_end) ? __ldg(p) : 0.0f;
+                }
             }
             dt_wait(&bar_empty[s], (((uint32_t)it / WG_NST) & 1u) ^ 1u);
             uint8_t *sa = smem + s * stage_bytes, *sb = sa + 2 * WG_APLANE;
 #pragma unroll
             for (int u = 0; u < WG_TASKS; ++u) {
-                const int tk = warp + u * WG_LOAD_WARPS;
-                const bool isa = tk < 32;
-                const int t2 = isa ? tk : tk - 32;
-                const int c = (t2 >> 3) * 32 + lane, g = t2 & 7;
-                if (tk >= ntasks || (!isa && c >= a.ktw)) continue;
+                const bool isa = u < 2;
+                if (!t_live[u] || (!isa && t_c[u] >= a.ktw)) continue;
                 uint4 hi, lo;
                 dt_split8(v[u], isa ? ds : 1.0f, hi, lo);
-                const int off = g * (isa ? 2048 : a.ktw * 16) + (c >> 3) * 128 + (c & 7) * 16;
-                uint8_t *dst = isa ? sa : sb;
-                *reinterpret_cast<uint4 *>(dst + off) = hi;
-                *reinterpret_cast<uint4 *>(dst + (isa ? WG_APLANE : bplane) + off) = lo;
+                uint8_t *dst = (isa ? sa : sb) + t_off[u];
+                *reinterpret_cast<uint4 *>(dst) = hi;
+                *reinterpret_cast<uint4 *>(dst + (isa ? WG_APLANE : bplane)) = lo;
             }
             rt_fence_proxy_async();
             __syncwarp();
@@ -587,10 +629,18 @@ RT_API int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long
     const int ktw = ((kp + k_tiles - 1) / k_tiles + 15) / 16 * 16;
     const int m_tiles = (n + 127) / 128;
     const int tiles = m_tiles * k_tiles;
+    // Split of the rows: at least one CTA per SM, and no accumulation chain longer than WG_MAX_CHAIN rows -- the tensor core
+    // truncates its fp32 accumulator at every K step (16 rows), so the error of a chain grows linearly with its length
+    // (measured: 1.9e-5 of max |dW| at 14 k rows per CTA, 7e-5 at 57 k); the partial sums are added in fp32 round-to-nearest.
     long long splits = dt_sm_count() / tiles;
     if (splits < 1) splits = 1;
     const long long max_splits = (rows + 8 * WG_RCH - 1) / (8 * WG_RCH);   // at least 8 stages of work per CTA
     if (splits > max_splits) splits = max_splits;
+    if ((rows + splits - 1) / splits > WG_MAX_CHAIN) {
+        splits = (rows + WG_MAX_CHAIN - 1) / WG_MAX_CHAIN;
+        const long long wave = dt_sm_count() / tiles > 0 ? dt_sm_count() / tiles : 1;
+        splits = (splits + wave - 1) / wave * wave;                         // whole waves of CTAs
+    }
     long long rps = ((rows + splits - 1) / splits + WG_RCH - 1) / WG_RCH * WG_RCH;
     splits = (rows + rps - 1) / rps;
     const size_t stage = 2 * WG_APLANE + (size_t)2 * ktw * WG_RCH * 2;

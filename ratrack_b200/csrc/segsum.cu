@@ -229,6 +229,26 @@ bool rt_segsum_supported(int n_dst, long long e_total) {
     return !atomic_env && n_dst >= 1 && n_dst <= 24 * 1024 && e_total < (1ll << 31);
 }
 
+// the inverse index alone (group_rows.cu): order (b, e_total) = source positions sorted by destination, stable; seg (b, n_dst + 1)
+int rt_launch_inverse_index(int b, int n_dst, long long e_total, const int *idx, int *order, int *seg, cudaStream_t st, const char *what) {
+    constexpr size_t kSmemMax = 200 * 1024;
+    static RtPerDevice attr;
+    const int dev = rt_current_device();
+    if (!attr.done(dev)) {
+        const cudaError_t e = cudaFuncSetAttribute(inverse_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e != cudaSuccess) {
+            rt_set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr.mark(dev);
+    }
+    int rows = (int)(kSmemMax / sizeof(int) / (size_t)n_dst) - 1;
+    rows = rows > II_WARPS ? II_WARPS : rows;
+    rows = rows < 1 ? 1 : rows;
+    inverse_index_kernel<<<b, II_THREADS, (size_t)(rows + 1) * n_dst * sizeof(int), st>>>(n_dst, e_total, rows, idx, order, seg);
+    return rt_check_launch(what);
+}
+
 // grad_points (b, c, n_dst) += scatter of grad_out (b, c, e_total / src_div) through idx (b, e_total) [x weight (b, e_total)]
 int rt_launch_segmented_scatter(int b, int c, int n_dst, long long e_total, int src_div, const float *grad_out, const int *idx,
                                 const float *weight, float *grad_points, cudaStream_t st, const char *what) {

@@ -54,16 +54,17 @@ def forward_raw(x2, ldx, w, w_sn, w_sk, k, n, bias=None, amax=None, act=0):
 
 class _LinearTC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        x2, ldx = _rows2d(x)
+    def forward(ctx, x2, weight, bias):
+        """x2 (rows, k) with unit column stride -> a fresh (rows, n) tensor (never a view: the callers apply in-place
+        activations to views of it)."""
+        ldx = x2.stride(0) if x2.shape[0] > 1 else x2.shape[1]
         w = weight.contiguous()
         n, k = w.shape
         y = forward_raw(x2, ldx, w, k, 1, k, n, bias.contiguous() if bias is not None else None)
         ctx.save_for_backward(x2, w)
         ctx.ldx = ldx
         ctx.has_bias = bias is not None
-        ctx.x_shape = x.shape
-        return y.view(*x.shape[:-1], n)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -75,7 +76,7 @@ class _LinearTC(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX = dY . W: the same kernel on dY with the transposed view of W (W'[i][j] = W[j][i])
-            dx = forward_raw(dy2, lddy, w, 1, k, n, k, None, amax).view(ctx.x_shape)
+            dx = forward_raw(dy2, lddy, w, 1, k, n, k, None, amax)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(n, k, dtype=torch.float32, device=w.device)
             with torch.cuda.device_of(w):
@@ -96,4 +97,5 @@ def linear(x, weight, bias=None):
     """torch.nn.functional.linear(x, weight, bias) on the tensor-core kernels where the shape is covered."""
     if not covered(x, weight):
         return torch.nn.functional.linear(x, weight, bias)
-    return _LinearTC.apply(x, weight, bias)
+    x2, _ = _rows2d(x)
+    return _LinearTC.apply(x2, weight, bias).view(*x.shape[:-1], weight.shape[0])

@@ -146,9 +146,46 @@ GatherOperation = GroupingOperation = _IndexedCopy
 ThreeInterpolate = _Interpolate3
 
 
+class _GroupRows(Function):
+    """QueryAndGroup's [grouped_xyz - new_xyz ; grouped_features] produced directly with the channels innermost:
+    (B,npoint,nsample,3+C) rows, the layout the dense layers consume -- one kernel instead of two channel-major gathers, a
+    subtraction, a cat and the transposing copy in front of the first 1x1 convolution.  Gradient w.r.t. the features only
+    (the reference's xyz never requires grad): a bit-repeatable segmented sum."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, features, idx):
+        from .. import _cabi
+
+        B, C, N = features.shape
+        S, ns = idx.shape[1:]
+        feat_rows = features.transpose(1, 2).contiguous()                       # (B,N,C): small next to the grouped tensor
+        out = _new((B, S, ns, 3 + C), features, torch.float32)
+        with torch.cuda.device_of(features):
+            _cabi.call("rt_group_rows", B, C, N, S, ns, _contig(xyz, "xyz").data_ptr(), _contig(new_xyz, "new_xyz").data_ptr(),
+                       feat_rows.data_ptr(), _contig(idx, "idx").data_ptr(), out.data_ptr(),
+                       torch.cuda.current_stream(features.device).cuda_stream)
+        ctx.idx = idx
+        ctx.shape = (B, C, N, S, ns)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        from .. import _cabi
+
+        B, C, N, S, ns = ctx.shape
+        g = grad_rows.contiguous()
+        grad = _new((B, N, C), g, torch.float32)
+        with torch.cuda.device_of(g):
+            _cabi.call("rt_group_rows_grad", B, C, N, S, ns, g.data_ptr(), ctx.idx.data_ptr(), grad.data_ptr(),
+                       torch.cuda.current_stream(g.device).cuda_stream)
+        return None, None, grad.transpose(1, 2), None
+
+
 # ---- grouping modules ------------------------------------------------------------------------------------------
 class QueryAndGroup(nn.Module):
     """ball_query -> [grouped xyz - centre ; grouped features] with the xyz channels first (reference :259-292)."""
+
+    rows_layout = True   # class-wide switch: False = the reference's op-by-op chain (channel-major result)
 
     def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
@@ -156,6 +193,10 @@ class QueryAndGroup(nn.Module):
 
     def forward(self, xyz, new_xyz, features=None):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        if (self.rows_layout and features is not None and self.use_xyz and features.is_cuda and features.dtype == torch.float32
+                and not xyz.requires_grad and not new_xyz.requires_grad):
+            # same (B,3+C,npoint,nsample) result, stored channels-innermost (torch.channels_last strides)
+            return _GroupRows.apply(xyz, new_xyz, features.contiguous(), idx).permute(0, 3, 1, 2)
         rel = grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"

@@ -35,7 +35,9 @@ def _case(rows, k, n, gscale=1.0, bias=True, seed=0):
     dy[::7] *= 1e-3                                   # gradients span orders of magnitude
     xt, wt = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     bt = b.clone().requires_grad_(True) if bias else None
-    y = dense_tc._LinearTC.apply(xt, wt, bt)
+    dense_tc.MIN_ROWS, dense_tc.MIN_CH = 0, 1
+    y = dense_tc.linear(xt, wt, bt)
+    dense_tc.MIN_ROWS, dense_tc.MIN_CH = 4096, 16
     y.backward(dy)
     x2, w2 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     y2 = torch.nn.functional.linear(x2, w2, b)
