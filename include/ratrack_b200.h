@@ -202,18 +202,19 @@ int rt_absmax(const float *x, long long count, float *amax_out, void *stream);
 
 /* y[r, j] = act(sum_i x[r, i] * W'[j, i] + bias[j]),  W'[j, i] = w[j * w_sn + i * w_sk],  r < rows, i < k, j < n.
  * forward: w = the layer's (n x k) weight, w_sn = k, w_sk = 1.  dgrad (dX = dY . W): x = dY, k <-> n, w_sn = 1,
- * w_sk = (row length of W).  bias (n) and x_amax (device scalar from rt_absmax: max |x|) may be NULL.
- * act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).  A value beyond the fp16 range (|x| >= 65504 without x_amax,
- * |W| >= 64) yields inf / NaN in y, never a silently saturated result. */
+ * w_sk = (row length of W).  bias (n) may be NULL.  x_amax / w_amax: device scalars from rt_absmax (max |x|, max |w|);
+ * with them the operands are scaled by powers of two into the fp16 planes' range and any finite fp32 input is valid.
+ * NULL = unscaled x / 2^10 w: then a value beyond the fp16 range (|x| >= 65504, |w| >= 64) yields inf / NaN in y,
+ * never a silently saturated result.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1). */
 int rt_dense_tc_forward(long long rows, int k, int n, const float *x, long long ldx, const float *w, long long w_sn,
-                        long long w_sk, const float *bias, const float *x_amax, int act, float *y, long long ldy,
-                        void *stream);
+                        long long w_sk, const float *bias, const float *x_amax, const float *w_amax, int act, float *y,
+                        long long ldy, void *stream);
 
-/* dw[j, i] = sum_r dy[r, j] * x[r, i]  (n x k, contiguous, overwritten).  dy_amax: device scalar max |dy| or NULL.
+/* dw[j, i] = sum_r dy[r, j] * x[r, i]  (n x k, contiguous, overwritten).  dy_amax, x_amax: device scalars or NULL.
  * The rows are split over the grid and the partial sums added in a fixed order (scratch from the library's
  * stream-ordered pool). */
 int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long long lddy, const float *x, long long ldx,
-                      const float *dy_amax, float *dw, void *stream);
+                      const float *dy_amax, const float *x_amax, float *dw, void *stream);
 
 /* replaces, in the channels-innermost layout of the training path, QueryAndGroup's chain
  *   group_points(xyz) - new_xyz ; group_points(features) ; cat     (reference: src/lib/pointnet2_utils.py:269-292)

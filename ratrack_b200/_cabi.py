@@ -36,9 +36,9 @@ SIGNATURES = {
     "rt_group_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rt_group_rows_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "rt_absmax": [_P, ctypes.c_longlong, _P, _P],
-    "rt_dense_tc_forward": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, ctypes.c_longlong, _P, _P, _I, _P,
+    "rt_dense_tc_forward": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, ctypes.c_longlong, _P, _P, _P, _I, _P,
                             ctypes.c_longlong, _P],
-    "rt_dense_tc_wgrad": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, _P, _P, _P],
+    "rt_dense_tc_wgrad": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, _P, _P, _P, _P],
     "rt_backbone_forward": [_P, _I, _I] + [_P] * 15 + [ctypes.c_longlong, _P],
     "rt_backbone_forward_varlen": [_P, _I, _I] + [_P] * 17 + [ctypes.c_longlong, _P],
 }

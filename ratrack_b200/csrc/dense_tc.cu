@@ -13,8 +13,8 @@
 //
 // lin_tc_kernel (forward / dgrad): persistent CTAs, tile = 128 rows x one N tile (<= 128 columns, the CTA's weights stay
 // resident in shared memory as fp16 planes in the K-major core-matrix layout).  Warp roles:
-//     8 loader warps   : coalesced 256-bit row reads (8 rows x 128 contiguous bytes per warp instruction), fp32 -> hi/lo
-//                        fp16, 128-bit conflict-free stores into a 3-stage ring of K-major core-matrix planes (64 K per stage)
+//     16 loader warps  : coalesced 128-bit row reads (4 rows x 128 contiguous bytes per warp instruction), fp32 -> hi/lo
+//                        fp16, conflict-free 64-bit stores into a 3-stage ring of K-major core-matrix planes (64 K per stage)
 //     1 MMA thread     : tcgen05.mma kind::f16 M128 N<=128 K16, A and B from shared memory, 3 products per K step
 //     4 epilogue warps : TMEM -> registers -> (main + 2^-11 corr) / scale + bias -> 256-bit row stores
 // with two accumulator pairs in TMEM, so loading tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
@@ -36,10 +36,14 @@
 namespace {
 
 constexpr int LT_ROWS = 128, LT_KC = 64, LT_NST = 3;
-constexpr int LT_PLANE = LT_ROWS * LT_KC * 2;   // one fp16 plane of a stage: 16 KB
+// A-operand stage: K-major core matrices (8 rows x 16 bytes), 8-row groups 128 bytes apart (SBO), K-adjacent core matrices
+// LT_LBO bytes apart.  LBO is 2048 + 32 so that the 16 lanes of a half warp -- two rows x eight 16-byte chunks of a coalesced
+// 128-bit row read -- store their 8-byte half rows to 16 distinct 8-byte bank slots (conflict-free 64-bit stores).
+constexpr int LT_LBO = 16 * LT_ROWS + 32;
+constexpr int LT_PLANE = (LT_KC / 8) * LT_LBO;  // one fp16 plane of a stage
 constexpr int LT_STAGE = 2 * LT_PLANE;
 constexpr int LT_EPI_WARPS = 4, LT_LOAD_WARPS = 16;
-constexpr int LT_TASKS = 32 / LT_LOAD_WARPS;   // warp tasks (8 rows x 4 K groups) per loader warp and stage
+constexpr int LT_TASKS = 64 / LT_LOAD_WARPS;   // warp tasks (4 rows x 128 bytes) per loader warp and stage
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_LOAD_WARPS + 1);
 constexpr float LT_WSCALE = 1024.0f;            // weights are staged as 2^10 W: their lo plane stays normal
 constexpr float LT_LO = 2048.0f;                // lo planes are stored as 2^11 lo
@@ -137,31 +141,11 @@ struct LinTcArgs {
     long long w_sn, w_sk;
     const float *bias;    // n entries or null
     const float *x_amax;  // device scalar: max |x| (null: x is used unscaled)
+    const float *w_amax;  // device scalar: max |w| (null: the weights are staged as 2^10 w)
     float *y;
     long long ldy;
     int act;              // 0 none, 1 ReLU, 2 LeakyReLU(0.1) on the output
 };
-
-// 8 consecutive K values of one row, zero beyond the row / column range
-__device__ __forceinline__ void dt_load8(const float *x, long long ldx, long long row, bool row_ok, int kcol, int k, int mode, float *v) {
-    if (!row_ok || kcol >= k) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-        return;
-    }
-    const float *p = x + row * ldx + kcol;
-    if (kcol + 8 <= k && mode == 2) {
-        float4 a, b;
-        rt_ldg256(p, a, b);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else if (kcol + 8 <= k && mode == 1) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = kcol + j < k ? __ldg(p + j) : 0.0f;
-    }
-}
 
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -194,6 +178,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         }
         rt_fence_mbar_init();
     }
+    const float ws = a.w_amax ? dt_scale_from_amax(a.w_amax) : LT_WSCALE;
     // this CTA's weight tile -> fp16 hi/lo planes, [kg = k/8][n/8][8 rows][8 halfs] (LBO = np * 16, SBO = 128)
     for (int i = threadIdx.x; i < a.np * (a.kp / 8); i += LT_THREADS) {
         const int nl = i % a.np, kg = i / a.np, n = n0 + nl;
@@ -204,7 +189,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
             v[j] = (n < a.n && k < a.k) ? __ldg(a.w + n * a.w_sn + k * a.w_sk) : 0.0f;
         }
         uint4 hi, lo;
-        dt_split8(v, LT_WSCALE, hi, lo);
+        dt_split8(v, ws, hi, lo);
         const int off = kg * (a.np * 16) + (nl >> 3) * 128 + (nl & 7) * 16;
         *reinterpret_cast<uint4 *>(s_whi + off) = hi;
         *reinterpret_cast<uint4 *>(s_wlo + off) = lo;
@@ -237,7 +222,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
                     const int steps = min(LT_KC / 16, ksteps - kc * (LT_KC / 16));
                     for (int j = 0; j < steps; ++j) {
                         const uint32_t kk = (uint32_t)(kc * (LT_KC / 16) + j);
-                        const uint64_t a_hi = dt_desc(st + j * 4096, 2048, 128), a_lo = dt_desc(st + LT_PLANE + j * 4096, 2048, 128);
+                        const uint64_t a_hi = dt_desc(st + j * 2 * LT_LBO, LT_LBO, 128), a_lo = dt_desc(st + LT_PLANE + j * 2 * LT_LBO, LT_LBO, 128);
                         const uint64_t b_hi = dt_desc(whi + kk * 2u * lbo_w, lbo_w, 128), b_lo = dt_desc(wlo + kk * 2u * lbo_w, lbo_w, 128);
                         dt_mma_ss(tC, a_lo, b_hi, idesc, kk > 0);
                         dt_mma_ss(tC, a_hi, b_lo, idesc, 1);
@@ -257,47 +242,53 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         // at a third of the HBM rate.  Hence 16 warps and a lean path (whole tile in range, 32-byte aligned rows, full K chunks)
         // whose per-task cost is one pointer add, one 256-bit load, the split and two 128-bit stores.
         const int lw = warp - LT_EPI_WARPS;
-        const int mode = ((a.ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 31) == 0) ? 2
-                       : ((a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) ? 1 : 0;
-        const bool lean_k = mode == 2 && (a.k % LT_KC) == 0;
-        // a warp task = 8 rows x 4 K groups: lanes l, l+8, l+16, l+24 read 128 contiguous bytes of row (l & 7)
-        int t_r[LT_TASKS], t_kg[LT_TASKS], t_off[LT_TASKS];
+        const bool al16 = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+        const bool lean_k = al16 && (a.k % LT_KC) == 0;
+        // a warp task = one 128-bit load instruction = 4 rows x 128 contiguous bytes (8 lanes per row: one full line per
+        // quarter warp -- the L1 data pipe moves 128 bytes per wavefront; the first version's 256-bit loads with 4 lanes per
+        // row cost a wavefront per 32-byte sector and held that pipe at 77 %)
+        int t_r[LT_TASKS], t_k[LT_TASKS], t_off[LT_TASKS];
         long long t_src[LT_TASKS];
 #pragma unroll
         for (int i = 0; i < LT_TASKS; ++i) {
-            const int wt = lw + LT_LOAD_WARPS * i;
-            t_r[i] = 8 * (wt >> 1) + (lane & 7);
-            t_kg[i] = ((wt & 1) << 2) + (lane >> 3);
-            t_off[i] = t_kg[i] * 2048 + (wt >> 1) * 128 + (lane & 7) * 16;   // a quarter warp writes 128 contiguous bytes
-            t_src[i] = (long long)t_r[i] * a.ldx + 8 * t_kg[i];
+            const int wt = lw + LT_LOAD_WARPS * i, seg = wt & 1, j = lane & 7;
+            t_r[i] = 4 * (wt >> 1) + (lane >> 3);
+            t_k[i] = seg * 32 + 4 * j;
+            t_off[i] = (seg * 4 + (j >> 1)) * LT_LBO + (t_r[i] >> 3) * 128 + (t_r[i] & 7) * 16 + (j & 1) * 8;
+            t_src[i] = (long long)t_r[i] * a.ldx + t_k[i];
         }
-        auto issue = [&](long long tile, int kc, float (*v)[8]) {
+        auto issue = [&](long long tile, int kc, float4 *v) {
             const long long row0 = tile * LT_ROWS;
             if (lean_k && row0 + LT_ROWS <= a.rows) {
                 const float *p = a.x + row0 * a.ldx + kc * LT_KC;
 #pragma unroll
-                for (int i = 0; i < LT_TASKS; ++i) {
-                    float4 lo4, hi4;
-                    rt_ldg256(p + t_src[i], lo4, hi4);
-                    v[i][0] = lo4.x; v[i][1] = lo4.y; v[i][2] = lo4.z; v[i][3] = lo4.w;
-                    v[i][4] = hi4.x; v[i][5] = hi4.y; v[i][6] = hi4.z; v[i][7] = hi4.w;
-                }
+                for (int i = 0; i < LT_TASKS; ++i) v[i] = __ldg(reinterpret_cast<const float4 *>(p + t_src[i]));
             } else {
 #pragma unroll
-                for (int i = 0; i < LT_TASKS; ++i)
-                    dt_load8(a.x, a.ldx, row0 + t_r[i], row0 + t_r[i] < a.rows, kc * LT_KC + 8 * t_kg[i], a.k, mode, v[i]);
+                for (int i = 0; i < LT_TASKS; ++i) {
+                    const long long row = row0 + t_r[i];
+                    const int kcol = kc * LT_KC + t_k[i];
+                    const float *p = a.x + row * a.ldx + kcol;
+                    if (row >= a.rows || kcol >= a.k) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (al16 && kcol + 4 <= a.k) v[i] = __ldg(reinterpret_cast<const float4 *>(p));
+                    else v[i] = make_float4(__ldg(p), kcol + 1 < a.k ? __ldg(p + 1) : 0.0f, kcol + 2 < a.k ? __ldg(p + 2) : 0.0f,
+                                            kcol + 3 < a.k ? __ldg(p + 3) : 0.0f);
+                }
             }
         };
-        auto convert = [&](uint32_t it, float (*v)[8]) {
+        const float2 xs2 = make_float2(xs, xs);
+        auto convert = [&](uint32_t it, const float4 *v) {
             const uint32_t s = it % LT_NST;
             dt_wait(&bar_empty[s], ((it / LT_NST) & 1u) ^ 1u);
             uint8_t *st = s_ring + s * LT_STAGE;
 #pragma unroll
             for (int i = 0; i < LT_TASKS; ++i) {
-                uint4 hi, lo;
-                dt_split8(v[i], xs, hi, lo);
-                *reinterpret_cast<uint4 *>(st + t_off[i]) = hi;
-                *reinterpret_cast<uint4 *>(st + LT_PLANE + t_off[i]) = lo;
+                const float2 p0 = rt_fmul2(make_float2(v[i].x, v[i].y), xs2), p1 = rt_fmul2(make_float2(v[i].z, v[i].w), xs2);
+                uint2 hi, lo;
+                dt_split2(p0.x, p0.y, hi.x, lo.x);
+                dt_split2(p1.x, p1.y, hi.y, lo.y);
+                *reinterpret_cast<uint2 *>(st + t_off[i]) = hi;
+                *reinterpret_cast<uint2 *>(st + LT_PLANE + t_off[i]) = lo;
             }
             rt_fence_proxy_async();
             __syncwarp();
@@ -306,7 +297,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         auto advance = [&](long long &tile, int &kc) {
             if (++kc == nchunks) { kc = 0; tile += tstep; }
         };
-        float va[LT_TASKS][8], vb[LT_TASKS][8];
+        float4 va[LT_TASKS], vb[LT_TASKS];
         long long tile = tile0;
         int kc = 0;
         if (tile < ntiles) issue(tile, kc, va);
@@ -322,7 +313,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     } else {
         // ===== epilogue warps: one thread per row (TMEM lane) =====
         const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-        const float inv = 1.0f / (xs * LT_WSCALE), slope = a.act == 1 ? 0.0f : (a.act == 2 ? 0.1f : 1.0f);
+        const float inv_x = 1.0f / xs, inv_w = 1.0f / ws;   // powers of two: two exact multiplies, no overflow of xs * ws
+        const float slope = a.act == 1 ? 0.0f : (a.act == 2 ? 0.1f : 1.0f);
         const bool st256 = (a.ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && (n0 & 7) == 0;
         uint32_t tcount = 0;
         for (long long tile = tile0; tile < ntiles; tile += tstep, ++tcount) {
@@ -340,7 +332,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float t = fmaf(fmaf(__uint_as_float(cr[i]), 1.0f / LT_LO, __uint_as_float(m[i])), inv, s_bias[c + i]);
+                    const float t = fmaf(fmaf(__uint_as_float(cr[i]), 1.0f / LT_LO, __uint_as_float(m[i])) * inv_x, inv_w, s_bias[c + i]);
                     v[i] = fmaxf(t, t * slope);
                 }
                 if (row < a.rows) {
@@ -381,7 +373,7 @@ struct WgradArgs {
     long long lddy;
     const float *x;
     long long ldx;
-    const float *dy_amax;
+    const float *dy_amax, *x_amax;   // device scalars max |dy|, max |x| (null: unscaled)
     float *part;              // [splits][m_tiles * 128][k_tiles * ktw]
 };
 
@@ -416,7 +408,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
     __syncthreads();
     dt_fence_after();
     const uint32_t tm = *tmem_slot;
-    const float ds = dt_scale_from_amax(a.dy_amax);
+    const float ds = dt_scale_from_amax(a.dy_amax), xsc = dt_scale_from_amax(a.x_amax);
 
     if (warp == WG_LOAD_WARPS) {
         if (lane == 0) {
@@ -491,7 +483,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
                 const bool isa = u < 2;
                 if (!t_live[u] || (!isa && t_c[u] >= a.ktw)) continue;
                 uint4 hi, lo;
-                dt_split8(v[u], isa ? ds : 1.0f, hi, lo);
+                dt_split8(v[u], isa ? ds : xsc, hi, lo);
                 uint8_t *dst = (isa ? sa : sb) + t_off[u];
                 *reinterpret_cast<uint4 *>(dst) = hi;
                 *reinterpret_cast<uint4 *>(dst + (isa ? WG_APLANE : bplane)) = lo;
@@ -505,7 +497,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
             dt_wait(bar_done, 0);
             dt_fence_after();
             const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-            const float inv = 1.0f / ds;
+            const float inv = 1.0f / ds, inv2 = 1.0f / xsc;
             const long long NP = (long long)a.m_tiles * 128, KP = (long long)a.k_tiles * a.ktw;
             float *prow = a.part + ((long long)blockIdx.x * NP + m0 + 32 * warp + lane) * KP + k0;
             for (int c = 0; c < a.ktw; c += 16) {
@@ -516,10 +508,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     float4 o;
-                    o.x = fmaf(__uint_as_float(cr[i + 0]), 1.0f / LT_LO, __uint_as_float(m[i + 0])) * inv;
-                    o.y = fmaf(__uint_as_float(cr[i + 1]), 1.0f / LT_LO, __uint_as_float(m[i + 1])) * inv;
-                    o.z = fmaf(__uint_as_float(cr[i + 2]), 1.0f / LT_LO, __uint_as_float(m[i + 2])) * inv;
-                    o.w = fmaf(__uint_as_float(cr[i + 3]), 1.0f / LT_LO, __uint_as_float(m[i + 3])) * inv;
+                    o.x = fmaf(__uint_as_float(cr[i + 0]), 1.0f / LT_LO, __uint_as_float(m[i + 0])) * inv * inv2;
+                    o.y = fmaf(__uint_as_float(cr[i + 1]), 1.0f / LT_LO, __uint_as_float(m[i + 1])) * inv * inv2;
+                    o.z = fmaf(__uint_as_float(cr[i + 2]), 1.0f / LT_LO, __uint_as_float(m[i + 2])) * inv * inv2;
+                    o.w = fmaf(__uint_as_float(cr[i + 3]), 1.0f / LT_LO, __uint_as_float(m[i + 3])) * inv * inv2;
                     *reinterpret_cast<float4 *>(prow + c + i) = o;
                 }
             }
@@ -580,7 +572,7 @@ RT_API int rt_absmax(const float *x, long long count, float *amax_out, void *str
 }
 
 RT_API int rt_dense_tc_forward(long long rows, int k, int n, const float *x, long long ldx, const float *w, long long w_sn, long long w_sk,
-                               const float *bias, const float *x_amax, int act, float *y, long long ldy, void *stream) {
+                               const float *bias, const float *x_amax, const float *w_amax, int act, float *y, long long ldy, void *stream) {
     RT_REQUIRE(rows >= 0 && k >= 1 && n >= 1 && x && w && y, "rt_dense_tc_forward: bad arguments");
     RT_REQUIRE(ldx >= k && ldy >= n, "rt_dense_tc_forward: leading dimensions smaller than the row width");
     RT_REQUIRE(act >= 0 && act <= 2, "rt_dense_tc_forward: act must be 0 (none), 1 (ReLU) or 2 (LeakyReLU 0.1)");
@@ -610,13 +602,13 @@ RT_API int rt_dense_tc_forward(long long rows, int k, int n, const float *x, lon
     long long grid_rows = dt_sm_count() / n_tiles;
     if (grid_rows < 1) grid_rows = 1;
     if (grid_rows > ntiles) grid_rows = ntiles;
-    LinTcArgs a{rows, k, n, kp, np, n_tiles, x, ldx, w, w_sn, w_sk, bias, x_amax, y, ldy, act};
+    LinTcArgs a{rows, k, n, kp, np, n_tiles, x, ldx, w, w_sn, w_sk, bias, x_amax, w_amax, y, ldy, act};
     lin_tc_kernel<<<(unsigned)(grid_rows * n_tiles), LT_THREADS, smem, (cudaStream_t)stream>>>(a);
     return rt_check_launch("lin_tc_kernel");
 }
 
 RT_API int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long long lddy, const float *x, long long ldx,
-                             const float *dy_amax, float *dw, void *stream) {
+                             const float *dy_amax, const float *x_amax, float *dw, void *stream) {
     RT_REQUIRE(rows >= 0 && k >= 1 && n >= 1 && dy && x && dw, "rt_dense_tc_wgrad: bad arguments");
     RT_REQUIRE(lddy >= n && ldx >= k, "rt_dense_tc_wgrad: leading dimensions smaller than the row width");
     cudaStream_t st = (cudaStream_t)stream;
@@ -659,7 +651,7 @@ RT_API int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long
     float *part = nullptr;
     int rc = rt_scratch_alloc((void **)&part, sizeof(float) * (size_t)(splits * NP * KP), st, "rt_dense_tc_wgrad");
     if (rc != RT_OK) return rc;
-    WgradArgs a{rows, rps, n, k, m_tiles, k_tiles, ktw, dy, lddy, x, ldx, dy_amax, part};
+    WgradArgs a{rows, rps, n, k, m_tiles, k_tiles, ktw, dy, lddy, x, ldx, dy_amax, x_amax, part};
     wgrad_tc_kernel<<<dim3((unsigned)splits, (unsigned)tiles), WG_THREADS, smem, st>>>(a);
     rc = rt_check_launch("wgrad_tc_kernel");
     if (rc == RT_OK) {

@@ -33,22 +33,25 @@ def _rows2d(x):
 
 
 def absmax(x):
-    """max |x| as a 1-element device tensor (no host synchronisation); consumed by the kernels to scale gradients into
-    the fp16 planes' range."""
+    """max |x| as a 1-element device tensor (no host synchronisation); the kernels read it on the device and scale the operand
+    by a power of two into the fp16 planes' range, so any finite fp32 input is valid."""
+    if not x.is_contiguous():
+        return torch.linalg.vector_norm(x.detach(), float("inf")).reshape(1).float()   # strided view: one torch reduction
     out = torch.empty(1, dtype=torch.float32, device=x.device)
     with torch.cuda.device_of(x):
         _cabi.call("rt_absmax", x.data_ptr(), x.numel(), out.data_ptr(), _stream(x))
     return out
 
 
-def forward_raw(x2, ldx, w, w_sn, w_sk, k, n, bias=None, amax=None, act=0):
-    """y (rows, n) = x2 (rows, k; leading dimension ldx) . W'^T + bias, W'[i][j] = w.data_ptr()[i * w_sn + j * w_sk]."""
+def forward_raw(x2, ldx, w, w_sn, w_sk, k, n, bias=None, amax=None, w_amax=None, act=0):
+    """y (rows, n) = act(x2 (rows, k; leading dimension ldx) . W'^T + bias), W'[i][j] = w.data_ptr()[i * w_sn + j * w_sk];
+    amax / w_amax: device scalars max |x2| / max |w| (None: unscaled x2, 2^10 w -- range-limited, see the header)."""
     rows = x2.shape[0]
     y = torch.empty(rows, n, dtype=torch.float32, device=x2.device)
     with torch.cuda.device_of(x2):
         _cabi.call("rt_dense_tc_forward", rows, k, n, x2.data_ptr(), ldx, w.data_ptr(), w_sn, w_sk,
-                   bias.data_ptr() if bias is not None else None, amax.data_ptr() if amax is not None else None, act,
-                   y.data_ptr(), n, _stream(x2))
+                   bias.data_ptr() if bias is not None else None, amax.data_ptr() if amax is not None else None,
+                   w_amax.data_ptr() if w_amax is not None else None, act, y.data_ptr(), n, _stream(x2))
     return y
 
 
@@ -60,28 +63,29 @@ class _LinearTC(torch.autograd.Function):
         ldx = x2.stride(0) if x2.shape[0] > 1 else x2.shape[1]
         w = weight.contiguous()
         n, k = w.shape
-        y = forward_raw(x2, ldx, w, k, 1, k, n, bias.contiguous() if bias is not None else None)
-        ctx.save_for_backward(x2, w)
+        x_amax, w_amax = absmax(x2), absmax(w)          # one extra read of x: no range restriction on the activations
+        y = forward_raw(x2, ldx, w, k, 1, k, n, bias.contiguous() if bias is not None else None, x_amax, w_amax)
+        ctx.save_for_backward(x2, w, x_amax, w_amax)
         ctx.ldx = ldx
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w = ctx.saved_tensors
+        x2, w, x_amax, w_amax = ctx.saved_tensors
         n, k = w.shape
         dy2, lddy = _rows2d(dy)
         rows = dy2.shape[0]
-        amax = absmax(dy2) if lddy == n else absmax(dy2.contiguous())
+        amax = absmax(dy2)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX = dY . W: the same kernel on dY with the transposed view of W (W'[i][j] = W[j][i])
-            dx = forward_raw(dy2, lddy, w, 1, k, n, k, None, amax)
+            dx = forward_raw(dy2, lddy, w, 1, k, n, k, None, amax, w_amax)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(n, k, dtype=torch.float32, device=w.device)
             with torch.cuda.device_of(w):
                 _cabi.call("rt_dense_tc_wgrad", rows, n, k, dy2.data_ptr(), lddy, x2.data_ptr(), ctx.ldx, amax.data_ptr(),
-                           dw.data_ptr(), _stream(w))
+                           x_amax.data_ptr(), dw.data_ptr(), _stream(w))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
         return dx, dw, db

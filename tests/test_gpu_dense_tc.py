@@ -107,10 +107,13 @@ def test_out_of_range_operand_is_loud():
     x = torch.ones(4096, 64, device="cuda")
     x[5, 3] = 1.0e5                                      # beyond fp16: the hi plane holds inf
     w = torch.ones(64, 64, device="cuda") / 64
-    y = dense_tc.forward_raw(x, 64, w, 64, 1, 64, 64)
+    y = dense_tc.forward_raw(x, 64, w, 64, 1, 64, 64)    # raw call without the operands' maxima: range-limited
     assert not bool(torch.isfinite(y[5]).all())          # never a silently saturated value
     assert bool(torch.isfinite(y[6]).all())
     amax = dense_tc.absmax(x)
     assert float(amax) == 1.0e5
-    y2 = dense_tc.forward_raw(x, 64, w, 64, 1, 64, 64, None, amax)   # the scaled form is exact again
+    y2 = dense_tc.forward_raw(x, 64, w, 64, 1, 64, 64, None, amax, dense_tc.absmax(w))   # scaled operands: any finite input
     assert _rel(y2, x.double() @ w.double().t()) < 2e-6
+    # the module-level entry always scales: activations ~1e5 and weights ~1e3 behave like fp32
+    xb, wb = x * 3.0, w * 6.4e4
+    assert _rel(dense_tc.linear(xb, wb), xb.double() @ wb.double().t()) < 2e-6

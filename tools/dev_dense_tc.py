@@ -76,7 +76,7 @@ def check(rows, k, n, gscale=1.0, bias=True, time=False):
             dw = torch.empty(n, k, device="cuda")
             from ratrack_b200 import _cabi
             st = torch.cuda.current_stream().cuda_stream
-            t_dw = timeit(lambda: _cabi.call("rt_dense_tc_wgrad", rows, n, k, dy.data_ptr(), n, x.data_ptr(), k, amax.data_ptr(), dw.data_ptr(), st))
+            t_dw = timeit(lambda: _cabi.call("rt_dense_tc_wgrad", rows, n, k, dy.data_ptr(), n, x.data_ptr(), k, amax.data_ptr(), None, dw.data_ptr(), st))
             t_dwr = timeit(lambda: dy.t() @ x)
             t_am = timeit(lambda: dense_tc.absmax(dy))
         fl = 2.0 * rows * k * n / 1e9

@@ -20,7 +20,7 @@ for _ in range(2):
     y = dense_tc.forward_raw(x, k, w, k, 1, k, n)
     amax = dense_tc.absmax(dy)
     dx = dense_tc.forward_raw(dy, n, w, 1, k, n, k, None, amax)
-    _cabi.call("rt_dense_tc_wgrad", rows, n, k, dy.data_ptr(), n, x.data_ptr(), k, amax.data_ptr(), dw.data_ptr(),
+    _cabi.call("rt_dense_tc_wgrad", rows, n, k, dy.data_ptr(), n, x.data_ptr(), k, amax.data_ptr(), None, dw.data_ptr(),
                torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 print("ok", float(y.abs().max()), float(dx.abs().max()), float(dw.abs().max()))
