@@ -229,6 +229,42 @@ int rt_group_rows(int b, int c, int n, int npoint, int nsample, const float *xyz
 int rt_group_rows_grad(int b, int c, int n, int npoint, int nsample, const float *grad_rows, const int *idx,
                        float *grad_feat_rows, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Section 5 -- cost volume of the training step, channels innermost
+ *
+ * replaces, for FeatureCorrelator.forward and its autograd backward (reference:
+ * src/utils/model_utils/model_utils.py:193-250), the op-by-op chain over (B,256,16,N) tensors by fused kernels
+ * on row-major tensors (point, neighbour, channel).  c = channels (multiple of 32, <= 1024), k <= 32 neighbours.
+ * Every gradient is a fixed-order sum: bit-repeatable.
+ * ------------------------------------------------------------------------------------------ */
+
+/* first layer, project-then-gather (model_utils.py:216-231):
+ * out[p,j,:] = LeakyReLU_0.1(p2[nbr(p,j),:] + p1[p,:] + wd.(xyz2[nbr(p,j)] - xyz1[p]) + bias)
+ * p1 (b,n1,c), p2 (b,n2,c) per-point projections; xyz1 (b,n1,3), xyz2 (b,n2,3); idx (b,n1,k) neighbours in cloud 2;
+ * wd (c,3); bias (c) or NULL -> out (b,n1,k,c), dir_out (b,n1,k,3) [optional]: the direction vectors */
+int rt_cv1_forward(int b, int n1, int n2, int k, int c, const float *p1, const float *p2, const float *xyz1,
+                   const float *xyz2, const int *idx, const float *wd, const float *bias, float *out, float *dir_out,
+                   void *stream);
+
+/* dout, out (b,n1,k,c), dir (b,n1,k,3), idx -> dp1 (b,n1,c), dp2 (b,n2,c), dwd (c,3), dbias (c), all overwritten */
+int rt_cv1_backward(int b, int n1, int n2, int k, int c, const float *dout, const float *out, const float *dir,
+                    const int *idx, float *dp1, float *dp2, float *dwd, float *dbias, void *stream);
+
+/* backward prologue of a dense layer whose activation was fused into the GEMM epilogue (rt_dense_tc_forward act 1 / 2):
+ * g = dy * act'(y) over (rows, n) contiguous, amax_out[0] = max |g|, colsum (n) = column sums of g (the bias gradient) */
+int rt_act_grad(long long rows, int n, int act, const float *y, const float *dy, float *g, float *amax_out,
+                float *colsum, void *stream);
+
+/* WeightNet-weighted neighbour sum (model_utils.py:232-236, 239-248):
+ * out[p,:] = sum_j ReLU(w3.h2[p,j,:] + b3) * X[p,j,:],  X[p,j] = x[p,j] (idx NULL; x (b,n,k,c)) or x[idx[p,j]]
+ * (x (b,n,c) per-point rows, idx (b,n,k)); h2 (b,n,k,8) = WeightNet's hidden rows, w3 (c,8), b3 (c) -> out (b,n,c) */
+int rt_wsum_forward(int b, int n, int k, int c, const float *x, const int *idx, const float *h2, const float *w3,
+                    const float *b3, float *out, void *stream);
+
+/* dout (b,n,c) -> dx (shape of x), dh2 (b,n,k,8), dw3 (c,8), db3 (c), all overwritten */
+int rt_wsum_backward(int b, int n, int k, int c, const float *x, const int *idx, const float *h2, const float *w3,
+                     const float *b3, const float *dout, float *dx, float *dh2, float *dw3, float *db3, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,11 @@ SIGNATURES = {
     "rt_engine_status_async": [_P, _P, _P],
     "rt_group_rows": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rt_group_rows_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "rt_cv1_forward": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "rt_cv1_backward": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "rt_act_grad": [ctypes.c_longlong, _I, _I, _P, _P, _P, _P, _P, _P],
+    "rt_wsum_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "rt_wsum_backward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "rt_absmax": [_P, ctypes.c_longlong, _P, _P],
     "rt_dense_tc_forward": [ctypes.c_longlong, _I, _I, _P, ctypes.c_longlong, _P, ctypes.c_longlong, ctypes.c_longlong, _P, _P, _P, _I, _P,
                             ctypes.c_longlong, _P],

@@ -120,6 +120,8 @@ class FeatureCorrelator(nn.Module):
         K = self.nsample
         if self.bn:
             return self._forward_dense(pc1, pc2, feature1, feature2)
+        if self._rows_path_ok(pc1, feature1):
+            return self._forward_rows(pc1, pc2, feature1, feature2)
         xyz1, xyz2 = pc1.permute(0, 2, 1), pc2.permute(0, 2, 1)
         idx = knn_point(K, xyz2, xyz1).int().contiguous()                                  # (B,N1,K)
         direction = pointnet2_utils.grouping_operation(pc2.contiguous(), idx) - pc1.unsqueeze(-1)      # (B,3,N1,K)
@@ -143,6 +145,52 @@ class FeatureCorrelator(nn.Module):
         weights = self.weightnet2(direction)
         x = pointnet2_utils.grouping_operation(x.contiguous(), idx)
         return torch.sum(weights * x, dim=3).contiguous()
+
+    fused_rows = True   # class-wide switch: False = the op-by-op chain above (A/B runs, parity tests)
+
+    def _rows_path_ok(self, pc1, feature1):
+        wn = self.weightnet1
+        C = self.mlp_convs[-1].out_channels
+        return (FeatureCorrelator.fused_rows and pc1.is_cuda and feature1.dtype == torch.float32 and self.nsample <= 32
+                and not wn.bn and len(wn.mlp_convs) == 3 and wn.mlp_convs[-1].in_channels == 8 and C % 32 == 0 and C <= 1024
+                and all(c.out_channels == C for c in self.mlp_convs) and isinstance(self.relu, nn.LeakyReLU)
+                and abs(self.relu.negative_slope - 0.1) < 1e-12)
+
+    @staticmethod
+    def _wn_hidden(wn, direction_rows):
+        """WeightNet's first two layers on (B,N,K,3) direction rows -> (B,N,K,8) hidden rows (its last layer is evaluated
+        inside the weighted-sum kernel)."""
+        h = direction_rows
+        for conv in wn.mlp_convs[:-1]:
+            h = F.relu(F.linear(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias))
+        return h
+
+    def _forward_rows(self, pc1, pc2, feature1, feature2):
+        """The same function on the fused channels-innermost kernels (lib/costvol_train.py, csrc/costvol_train.cu): the
+        (B,C,N1,K) tensors of the chain below exist only as the three (B,N1,K,C) activations the backward pass needs."""
+        from .lib import costvol_train as cvt
+
+        K = self.nsample
+        xyz1, xyz2 = pc1.permute(0, 2, 1).contiguous(), pc2.permute(0, 2, 1).contiguous()
+        idx12 = knn_point(K, xyz2, xyz1).int().contiguous()
+        conv0 = self.mlp_convs[0]
+        d1, d2 = feature1.shape[1], feature2.shape[1]
+        w = conv0.weight.view(conv0.out_channels, conv0.in_channels)
+        p1 = dense_tc.linear(feature1.permute(0, 2, 1).contiguous(), w[:, :d1])               # (B,N1,C) rows
+        p2 = dense_tc.linear(feature2.permute(0, 2, 1).contiguous(), w[:, d1:d1 + d2])
+        x, direction = cvt.cv_layer1(p1, p2, xyz1, xyz2, idx12, w[:, d1 + d2:], conv0.bias)   # (B,N1,K,C), (B,N1,K,3)
+        for conv in self.mlp_convs[1:]:
+            x = cvt.linear_act(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias, "leaky")
+        wn = self.weightnet1
+        last = wn.mlp_convs[-1]
+        x = cvt.weighted_sum(x, self._wn_hidden(wn, direction), last.weight.view(last.out_channels, 8), last.bias)   # (B,N1,C)
+
+        idx11 = knn_point(K, xyz1, xyz1).int().contiguous()
+        direction = index_points(xyz1, idx11.long()) - xyz1.unsqueeze(2)                      # (B,N1,K,3)
+        wn = self.weightnet2
+        last = wn.mlp_convs[-1]
+        x = cvt.weighted_sum(x, self._wn_hidden(wn, direction), last.weight.view(last.out_channels, 8), last.bias, idx=idx11)
+        return x.permute(0, 2, 1).contiguous()
 
     def _forward_dense(self, pc1, pc2, feature1, feature2):
         """The reference's literal dataflow (needed when the first layer is followed by a BatchNorm: bn=True)."""
