@@ -259,7 +259,7 @@ def train_record(dev, rank, world, B, N, steps, warmup, label="configs[2] geomet
            "ms_per_step": ms / steps, "scaling": "weak", "dtype": "f32",
            "config": {"workload": f"synthetic N={N} pts, batch={B} per GPU, forward+backward multi-task loss ({label})",
                       "batch_per_gpu": B, "points": N, "npoints": 512,
-                      "path": "modular (CUDA pointnet2 ops + deterministic grad kernels under autograd)", "parallelism": f"dp{world}"},
+                      "path": "autograd over the package's own kernels: tcgen05 split-fp16 forward / dgrad / wgrad for the dense layers, fused channels-innermost cost volume and grouping, deterministic gradient kernels; BatchNorm / max-pool / GRU / Adam are torch", "parallelism": f"dp{world}"},
            "collectives": coll, "gpu_launches": _cabi.launch_count, "clocks": clk, "final_loss": float(loss),
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     del net, opt, t
