@@ -493,13 +493,13 @@ def ref_gpu_rate(net, t, h0, steps, B):
     ref = ref_gpu.load()
     if ref is None:
         return {"unavailable": "oracle/_ref/pointnet2_cuda.so not built"}
-    from ratrack_b200.lib.pytorch_utils import PointwiseConv2d
+    from ratrack_b200.model_utils import reference_dataflow
 
     ours, fused = U.pointnet2, net.use_fused
     U.pointnet2, net.use_fused = ref, False
-    PointwiseConv2d.use_gemm = False      # 1x1 convolutions through nn.Conv2d / cuDNN, as the reference's modules run them
     try:
-        with torch.no_grad():
+        # op-by-op dataflow of the reference's modules: nn.Conv2d / cuDNN, torch Linear / BatchNorm, channel-major grouping
+        with torch.no_grad(), reference_dataflow():
             for _ in range(3):
                 net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], h0)
             torch.cuda.synchronize()
@@ -513,7 +513,6 @@ def ref_gpu_rate(net, t, h0, steps, B):
                 "what": "reference CUDA kernels (oracle/_ref) + torch fp32 modules, same B200, same batch"}
     finally:
         U.pointnet2, net.use_fused = ours, fused
-        PointwiseConv2d.use_gemm = True
 
 
 if __name__ == "__main__":

@@ -452,12 +452,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
             const int cb = (t2 >> 3) * 32;
             t_c[u] = c;
             t_g[u] = g;
-            t_live[u] = isa || t2 < nbt;
+            t_live[u] = isa ? m0 + cb < a.n : t2 < nbt;   // a 32-channel block of dy beyond n stays zero (cleared once below)
             const int ch = (isa ? m0 : k0) + c;
             t_ok[u] = t_live[u] && (isa ? ch < a.n : (c < a.ktw && ch < a.k));
             t_full[u] = t_live[u] && (isa ? m0 + cb + 32 <= a.n : (cb + 32 <= a.ktw && k0 + cb + 32 <= a.k));   // warp-uniform
             t_off[u] = g * (isa ? 2048 : a.ktw * 16) + (c >> 3) * 128 + (c & 7) * 16;
             t_src[u] = (isa ? a.dy : a.x) + (long long)(8 * g) * (isa ? a.lddy : a.ldx) + ch;
+        }
+        if (m0 + 128 > a.n) {   // some dy blocks are dead: their planes must read as zeros
+            for (int st_ = 0; st_ < WG_NST; ++st_)
+                for (int i = threadIdx.x; i < 2 * WG_APLANE / 16; i += 32 * WG_LOAD_WARPS)
+                    reinterpret_cast<uint4 *>(smem + st_ * stage_bytes)[i] = make_uint4(0, 0, 0, 0);
+            rt_fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * WG_LOAD_WARPS) : "memory");   // loader warps only
         }
         for (int it = 0; it < nstages; ++it) {
             const uint32_t s = (uint32_t)it % WG_NST;

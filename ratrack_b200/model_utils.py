@@ -15,6 +15,8 @@ created on the inputs' device), `h=None` creates zeros for the actual batch size
 reference checkpoints load with strict=False exactly as the reference itself loads them
 (src/models/model.py:24,37).
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -22,6 +24,21 @@ import torch.nn.functional as F
 from .lib import dense_tc, pointnet2_utils
 from .lib.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 from .lib.pytorch_utils import PointwiseConv2d
+
+
+@contextlib.contextmanager
+def reference_dataflow():
+    """Inside this context the modular path evaluates the network op by op exactly as the reference's own modules do --
+    1x1 convolutions through nn.Conv2d / cuDNN, Linear through torch, QueryAndGroup and the
+    cost volume as chains of channel-major ops -- with only the ten pointnet2 kernels native.  Used where the REFERENCE's
+    arithmetic is the thing measured (bench.py `ref_gpu`, tests/test_gpu_parity_floor.py), never on the product path."""
+    saved = (PointwiseConv2d.use_gemm, dense_tc.enabled, pointnet2_utils.QueryAndGroup.rows_layout, FeatureCorrelator.fused_rows)
+    PointwiseConv2d.use_gemm = dense_tc.enabled = False
+    pointnet2_utils.QueryAndGroup.rows_layout = FeatureCorrelator.fused_rows = False
+    try:
+        yield
+    finally:
+        PointwiseConv2d.use_gemm, dense_tc.enabled, pointnet2_utils.QueryAndGroup.rows_layout, FeatureCorrelator.fused_rows = saved
 
 
 def square_distance(src, dst):

@@ -8,6 +8,7 @@ default engine (tcgen05 split-fp16 products) is then held to the SAME tolerance 
 (tests/test_gpu_backbone.py: TOL_TC is TOL_FP32) and, tensor by tensor, to a small multiple of the floor measured here.
 The numbers of one run are committed in profiles/r2_parity_floor.txt.
 """
+import contextlib
 import json
 import os
 
@@ -18,8 +19,7 @@ import torch
 from oracle import backbone_oracle, ref_gpu
 from ratrack_b200 import synthetic
 from ratrack_b200.lib import pointnet2_utils as U
-from ratrack_b200.lib.pytorch_utils import PointwiseConv2d
-from ratrack_b200.model_utils import Track4DBackbone
+from ratrack_b200.model_utils import Track4DBackbone, reference_dataflow
 from test_gpu_backbone import TOL_FP32, TOL_TC
 
 pytestmark = pytest.mark.gpu
@@ -63,9 +63,10 @@ def _forward(net, d, batch, fused, ref_kernels=False):
     net.use_fused = fused
     if ref_kernels:
         U.pointnet2 = ref_gpu.load()
-        PointwiseConv2d.use_gemm = False      # nn.Conv2d / cuDNN, exactly what the reference's modules run
     try:
-        with torch.no_grad():
+        # ref_kernels: the op-by-op dataflow of the reference's modules (nn.Conv2d / cuDNN, torch Linear / BatchNorm, channel-major
+        # grouping and cost volume) over the reference's own compiled kernels -- nothing of this package's arithmetic
+        with torch.no_grad(), (reference_dataflow() if ref_kernels else contextlib.nullcontext()):
             out = net.backbone(t["pc1"], t["pc2"], t["ft1"], t["ft2"], torch.zeros(5, batch, 128, device="cuda"))
             knn = net.cost_volume_neighbours(t["pc1"], t["pc2"])
         torch.cuda.synchronize()
@@ -73,7 +74,6 @@ def _forward(net, d, batch, fused, ref_kernels=False):
             net._engine.check_status()
     finally:
         U.pointnet2 = ours
-        PointwiseConv2d.use_gemm = True
     return out, knn
 
 
