@@ -529,14 +529,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(WgradArgs a) {
     if (warp == WG_LOAD_WARPS) dt_tmem_dealloc(tm, tmem_cols);
 }
 
-// dw[n][k] = sum over the splits, in split order (bit-repeatable)
-__global__ void wgrad_reduce_kernel(const float *part, int splits, long long NP, long long KP, int n, int k, float *dw) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n * k) return;
-    const int r = (int)(i / k), c = (int)(i % k);
+// dw[n][k] = sum over the splits in a FIXED order (bit-repeatable): a CTA owns 32 consecutive output elements, warp g adds
+// the splits g, g + 8, ... in increasing order (coalesced 128-byte reads), then the 8 warps' sums are added in warp order.
+// (One thread per element walked up to a few hundred partials serially: 23 us per layer, 3.5 % of the training step.)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *part, int splits, long long NP, long long KP, int n, int k, float *dw) {
+    __shared__ float s_sum[8][32];
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * 32 + lane;
     float s = 0.0f;
-    for (int sp = 0; sp < splits; ++sp) s += part[((long long)sp * NP + r) * KP + c];
-    dw[i] = s;
+    if (i < (long long)n * k) {
+        const int r = (int)(i / k), c = (int)(i % k);
+        for (int sp = g; sp < splits; sp += 8) s += part[((long long)sp * NP + r) * KP + c];
+    }
+    s_sum[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && i < (long long)n * k) {
+        float t = s_sum[0][lane];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) t += s_sum[u][lane];
+        dw[i] = t;
+    }
 }
 
 // max |x| as an fp32 bit pattern (non-negative floats order like unsigned integers)
@@ -663,7 +675,7 @@ RT_API int rt_dense_tc_wgrad(long long rows, int n, int k, const float *dy, long
     rc = rt_check_launch("wgrad_tc_kernel");
     if (rc == RT_OK) {
         const long long total = (long long)n * k;
-        wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, (int)splits, NP, KP, n, k, dw);
+        wgrad_reduce_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(part, (int)splits, NP, KP, n, k, dw);
         rc = rt_check_launch("wgrad_reduce_kernel");
     }
     rt_scratch_free(part, st);
