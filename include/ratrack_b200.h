@@ -179,6 +179,13 @@ int rt_backbone_forward_varlen(rt_engine *e, int b, int n, const int *npts1, con
 int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha, int iters, float *scores, long long *indices0,
                       long long *indices1, void *stream);
 
+/* replaces the per-object embedding assembly of Track4D.affinity_module (reference: src/models/track4d.py:202-216)
+ * points (139, p_total) channel-major: the feature columns of nobj objects side by side, object i = columns
+ * [offsets[i], offsets[i+1]) (offsets: nobj + 1 device ints, every object non-empty) -> out (nobj, 141) =
+ * [mean position (3), position variance (3), max feature (128), mean flow (3), mean rrv (2), rrv variance (2)],
+ * variances = population variances, two-pass. */
+int rt_object_embeddings(int nobj, int p_total, const float *points, const int *offsets, float *out, void *stream);
+
 /* replaces the host-side sklearn call of Track4D.clustering (reference: src/models/track4d.py:36,108-126)
  * x (b,n,d) fp32 feature rows -> labels (b,n) int32: exactly sklearn.cluster.DBSCAN(eps, min_samples).fit_predict per set
  * (cluster numbers in order of first core point, border points to the lowest-numbered adjacent cluster, noise = -1).

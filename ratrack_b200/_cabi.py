@@ -27,6 +27,7 @@ SIGNATURES = {
     "rt_knn_expanded": [_I, _I, _I, _I, _P, _P, _P, _P],
     "rt_dbscan": [_I, _I, _I, _P, _F, _I, _P, _P],
     "rt_sinkhorn_match": [_I, _I, _I, _P, _F, _I, _P, _P, _P, _P],
+    "rt_object_embeddings": [_I, _I, _P, _P, _P, _P],
     "rt_engine_create": [ctypes.POINTER(ctypes.c_void_p), _I, ctypes.POINTER(ctypes.c_void_p), _I],
     "rt_engine_set_profile_events": [_P, _P, _P],
     "rt_engine_set_flags": [_P, _I],

@@ -41,6 +41,8 @@ def object_embeddings(points, seg, nseg):
     (nseg, 141) embeddings [centre(3), position variance(3), max feature(128), mean flow(3), mean rrv(2), rrv variance(2)]
     exactly as the reference assembles them per object (track4d.py:202-216; variances are population variances,
     computed two-pass like torch.var)."""
+    if points.is_cuda and not (torch.is_grad_enabled() and points.requires_grad):
+        return object_embeddings_packed(points, torch.bincount(seg, minlength=nseg).tolist())
     cnt = torch.zeros(nseg, device=points.device).index_add_(0, seg, torch.ones_like(seg, dtype=torch.float32))
 
     def seg_mean(x):                       # (C,P) -> (nseg,C)
@@ -55,6 +57,19 @@ def object_embeddings(points, seg, nseg):
     fmax = torch.full((nseg, feat.shape[0]), float("-inf"), device=points.device)
     fmax = fmax.scatter_reduce(0, seg[:, None].expand(-1, feat.shape[0]), feat.t(), reduce="amax", include_self=True)
     return torch.cat([pos_m, seg_var(pos, pos_m), fmax, seg_mean(flow), rrv_m, seg_var(rrv, rrv_m)], dim=1)
+
+
+def object_embeddings_packed(points, counts):
+    """The same embeddings for objects whose columns sit side by side in `points` (139, P) -- object i owns the next counts[i]
+    columns -- in ONE kernel launch (rt_object_embeddings); inference only (no autograd)."""
+    nseg = len(counts)
+    off = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32).to(points.device, non_blocking=True)
+    pts = points.detach().contiguous()
+    out = torch.empty(nseg, 141, dtype=torch.float32, device=points.device)
+    with torch.cuda.device_of(pts):
+        _cabi.call("rt_object_embeddings", nseg, pts.shape[1], pts.data_ptr(), off.data_ptr(), out.data_ptr(),
+                   torch.cuda.current_stream(pts.device).cuda_stream)
+    return out
 
 
 class Track4D(Track4DBackbone):
@@ -117,14 +132,23 @@ class Track4D(Track4DBackbone):
         if pc1_features.shape[2] == 0:
             return []
         f = torch.cat((pc1_features[0, 3:9, :], pc1_features[0, 10:12, :]), dim=0).t().contiguous()
-        labels = association.dbscan_labels(f.detach(), self.eps, self.min_samples).cpu().numpy()
-        order, seen = [], set()
-        for lab in labels.tolist():
-            if lab != -1 and lab not in seen:
-                seen.add(lab)
-                order.append(lab)
-        dev = pc1_features.device
-        return [pc1_features[:, :, torch.from_numpy(np.nonzero(labels == lab)[0]).to(dev)] for lab in order]
+        labels = association.dbscan_labels(f.detach(), self.eps, self.min_samples).cpu().numpy()      # the frame's first host read
+        # clusters in the order they first appear along the point index, points inside a cluster in index order: one stable
+        # sort on the host, ONE gather on the device, the per-cluster tensors are views of its result
+        keep = np.nonzero(labels != -1)[0]
+        if keep.size == 0:
+            return []
+        labs = labels[keep]
+        uniq, first = np.unique(labs, return_index=True)
+        rank = np.empty(int(uniq.max()) + 1, dtype=np.int64)
+        rank[uniq[np.argsort(first, kind="stable")]] = np.arange(uniq.size)
+        order = np.argsort(rank[labs], kind="stable")
+        counts = np.bincount(rank[labs], minlength=uniq.size).tolist()
+        perm = torch.from_numpy(keep[order]).to(pc1_features.device, non_blocking=True)
+        packed = pc1_features.index_select(2, perm)
+        objs = list(torch.split(packed, counts, dim=2))
+        self._packed = (objs, packed, counts)        # affinity_module reuses the side-by-side layout (no cat, no segment ids)
+        return objs
 
     def affinity_module(self, objects_curr, objects_prev):
         """-> (aff_list (m*n,), aff_mat (1,m,n), m, n); empty inputs give ([], (1,0)) as the reference does (:218-222)."""
@@ -134,7 +158,13 @@ class Track4D(Track4DBackbone):
             return [], torch.zeros(1, 0, device=dev), m, n
 
         def embed(objs):
+            packed = getattr(self, "_packed", None)
+            fast = objs[0].is_cuda and not (torch.is_grad_enabled() and any(o.requires_grad for o in objs))
+            if fast and packed is not None and packed[0] is objs:                   # this frame's clusters: already side by side
+                return object_embeddings_packed(packed[1][0], packed[2])
             pts = torch.cat([o[0] for o in objs], dim=1)
+            if fast:
+                return object_embeddings_packed(pts, [o.shape[2] for o in objs])
             seg = torch.cat([torch.full((o.shape[2],), i, dtype=torch.long, device=pts.device) for i, o in enumerate(objs)])
             return object_embeddings(pts, seg, len(objs))
 
@@ -163,7 +193,8 @@ class Track4D(Track4DBackbone):
                 return aff_list, aff_mat, None, confs
             idx = indices1[0]
             conf_all = aff_mat[0, idx.clamp(min=0), torch.arange(n, device=aff_mat.device)]
-            idx_h, conf_h = idx.cpu().tolist(), conf_all.detach().cpu().tolist()      # the frame's one device->host read
+            both = torch.stack((idx.to(torch.float64), conf_all.detach().to(torch.float64))).cpu()   # the frame's second (last) host read
+            idx_h, conf_h = both[0].long().tolist(), both[1].tolist()
             # (an unmatched object has index -1: the reference then reads aff_mat[0, -1, i]; only the sign of the test matters)
             prev_keys = list(objects_prev.keys())
             for i in range(n):
