@@ -204,16 +204,18 @@ __global__ void wsum_bwd_kernel(long long total_pts, int n, int K, int C, const 
             aw[4] = fmaf(dwn, hb.x, aw[4]); aw[5] = fmaf(dwn, hb.y, aw[5]); aw[6] = fmaf(dwn, hb.z, aw[6]); aw[7] = fmaf(dwn, hb.w, aw[7]);
         }
         __syncthreads();
-        // two threads per (k, i): each adds half of the channels in channel order, the halves are added by one shuffle
-        // (the loop bound is uniform over a warp: blockDim and K * 16 are multiples of 32, so partners are always both active)
-        for (int t = threadIdx.x; t < K * CV_H * 2; t += blockDim.x) {
+        // two threads per (k, i): each adds half of the channels in channel order, the halves are added by one shuffle.
+        // Every thread of the CTA runs every trip (the shuffle names the full warp): work beyond K * 16 is predicated off.
+        for (int t0 = 0; t0 < K * CV_H * 2; t0 += blockDim.x) {
+            const int t = t0 + threadIdx.x;
+            const bool live = t < K * CV_H * 2;
             const int pair = t >> 1, half = t & 1;
-            const int k = pair / CV_H, i = pair % CV_H;
-            const int c0 = half * (C / 2), c1 = c0 + C / 2;
+            const int k = live ? pair / CV_H : 0, i = pair % CV_H;
+            const int c0 = half * (C / 2), c1 = live ? c0 + C / 2 : c0;
             float s = 0.0f;
             for (int cc = c0; cc < c1; ++cc) s = fmaf(s_w3[cc * CV_H + i], s_dwn[k * (C + 1) + cc], s);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (half == 0) dh2[(p * K + k) * CV_H + i] = s;
+            if (live && half == 0) dh2[(p * K + k) * CV_H + i] = s;
         }
         __syncthreads();
     }

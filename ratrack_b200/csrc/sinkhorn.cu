@@ -29,8 +29,10 @@ __device__ __forceinline__ float sk_lse(const float *row, const float *add, int 
     return logf(sum) + shift;
 }
 
-template <int LPR>
-__global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n, const float *__restrict__ aff_all, float alpha,
+// THREADS: 256, or 64 for matrices of up to 8 x 8 (two warps hold all rows: the two CTA barriers of an iteration -- the
+// kernel's critical path at the reference's few-objects-per-frame operating point -- synchronise 2 warps instead of 8)
+template <int LPR, int THREADS>
+__global__ void __launch_bounds__(THREADS) sinkhorn_match_kernel(int m, int n, const float *__restrict__ aff_all, float alpha,
                                                                      int iters, float *__restrict__ scores_all,
                                                                      long long *__restrict__ idx0_all, long long *__restrict__ idx1_all,
                                                                      float *__restrict__ zscratch) {
@@ -47,22 +49,22 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
     float *max1v = max0v + M;         // n
     int *max0i = reinterpret_cast<int *>(max1v + N);
     int *max1i = max0i + M;
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = SK_THREADS / 32;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = THREADS / 32;
     const float *aff = aff_all + (size_t)b * m * n;
 
     // couplings = [[scores, alpha], [alpha, alpha]]; log_mu / log_nu as in log_optimal_transport
-    for (int e = t; e < M * N; e += SK_THREADS) {
+    for (int e = t; e < M * N; e += THREADS) {
         const int i = e / N, j = e % N;
         const float z = (i < m && j < n) ? aff[i * n + j] : alpha;
         Z[i * ld + j] = z;
         ZT[j * ldt + i] = z;
     }
     const float norm = -logf((float)m + (float)n);
-    for (int i = t; i < M; i += SK_THREADS) {
+    for (int i = t; i < M; i += THREADS) {
         u[i] = 0.0f;
         log_mu[i] = i < m ? norm : logf((float)n) + norm;
     }
-    for (int j = t; j < N; j += SK_THREADS) {
+    for (int j = t; j < N; j += THREADS) {
         v[j] = 0.0f;
         log_nu[j] = j < n ? norm : logf((float)m) + norm;
     }
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
     }
     }
     // Z + u + v - norm
-    for (int e = t; e < M * N; e += SK_THREADS) {
+    for (int e = t; e < M * N; e += THREADS) {
         const int i = e / N, j = e % N;
         const float s = Z[i * ld + j] + u[i] + v[j] - norm;
         Z[i * ld + j] = s;
@@ -132,12 +134,12 @@ __global__ void __launch_bounds__(SK_THREADS) sinkhorn_match_kernel(int m, int n
     }
     __syncthreads();
     // mutual check and matching threshold (track4d.py:170-180)
-    for (int i = t; i < m; i += SK_THREADS) {
+    for (int i = t; i < m; i += THREADS) {
         const bool mutual0 = max1i[max0i[i]] == i;
         const bool valid0 = mutual0 && expf(max0v[i]) > 0.0f;
         if (idx0_all) idx0_all[(size_t)b * m + i] = valid0 ? max0i[i] : -1;
     }
-    for (int j = t; j < n; j += SK_THREADS) {
+    for (int j = t; j < n; j += THREADS) {
         const int i = max1i[j];
         const bool mutual1 = max0i[i] == j;
         const bool mutual0 = max1i[max0i[i]] == i;
@@ -164,8 +166,8 @@ RT_API int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha,
     static RtPerDevice attr;
     const int dev = rt_current_device();
     if (!attr.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(sinkhorn_match_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(sinkhorn_match_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(sinkhorn_match_kernel<8, SK_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sinkhorn_match_kernel<32, SK_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) {
             rt_set_error("sinkhorn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
@@ -178,10 +180,12 @@ RT_API int rt_sinkhorn_match(int b, int m, int n, const float *aff, float alpha,
         const int ae = rt_scratch_alloc((void **)&zscratch, zbytes * (size_t)b, st, "sinkhorn_match");
         if (ae != RT_OK) return ae;
     }
-    if (M <= 96 && N <= 96)
-        sinkhorn_match_kernel<8><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
+    if (M <= 8 && N <= 8)
+        sinkhorn_match_kernel<8, 64><<<b, 64, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
+    else if (M <= 96 && N <= 96)
+        sinkhorn_match_kernel<8, SK_THREADS><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
     else
-        sinkhorn_match_kernel<32><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
+        sinkhorn_match_kernel<32, SK_THREADS><<<b, SK_THREADS, smem, st>>>(m, n, aff, alpha, iters, scores, indices0, indices1, zscratch);
     const int rc = rt_check_launch("sinkhorn_match_kernel");
     rt_scratch_free(zscratch, st);
     return rc;
