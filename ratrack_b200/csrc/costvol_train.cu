@@ -36,16 +36,21 @@ int cv_sms() {
 }
 
 // ---- cv1 -------------------------------------------------------------------------------------------------------------
-__global__ void cv1_fwd_kernel(long long total_pts, int n1, int n2, int K, int C, const float *__restrict__ p1, const float *__restrict__ p2,
+// KT = 16: the model's neighbour count as a compile-time constant (loops fully unrolled: all of a point's row loads are in flight
+// together -- the runtime-K loops kept ~4 loads per thread in flight and ran at a third of the HBM rate); KT = 0: any K
+template <int KT>
+__global__ void cv1_fwd_kernel(long long total_pts, int n1, int n2, int Krt, int C, const float *__restrict__ p1, const float *__restrict__ p2,
                                const float *__restrict__ xyz1, const float *__restrict__ xyz2, const int *__restrict__ idx,
                                const float *__restrict__ wd, const float *__restrict__ bias, float *__restrict__ out,
                                float *__restrict__ dir_out) {
     const int c = threadIdx.x;
+    const int K = KT ? KT : Krt;
     const float wx = __ldg(wd + c * 3), wy = __ldg(wd + c * 3 + 1), wz = __ldg(wd + c * 3 + 2), bv = bias ? __ldg(bias + c) : 0.0f;
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
         const long long cloud = p / n1;
         const float qx = __ldg(xyz1 + p * 3), qy = __ldg(xyz1 + p * 3 + 1), qz = __ldg(xyz1 + p * 3 + 2);
         const float p1v = __ldg(p1 + p * C + c);
+#pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long g = cloud * n2 + __ldg(idx + p * K + k);
             const float dx = __ldg(xyz2 + g * 3) - qx, dy = __ldg(xyz2 + g * 3 + 1) - qy, dz = __ldg(xyz2 + g * 3 + 2) - qz;
@@ -142,7 +147,8 @@ __global__ void act_grad_kernel(long long rows, int n, int act, const float *__r
 
 // ---- wsum --------------------------------------------------------------------------------------------------------------
 // out[p,c] = sum_k ReLU(W3[c,:].h2[p,k,:] + b3[c]) * X[p,k,c];  X = x[(p*K+k)] (idx == null) or xpts[cloud*n + idx[p,k]]
-__global__ void wsum_fwd_kernel(long long total_pts, int n, int K, int C, const float *__restrict__ x, const int *__restrict__ idx,
+template <int KT>
+__global__ void wsum_fwd_kernel(long long total_pts, int n, int Krt, int C, const float *__restrict__ x, const int *__restrict__ idx,
                                 const float *__restrict__ h2, const float *__restrict__ w3, const float *__restrict__ b3,
                                 float *__restrict__ out) {
     const int c = threadIdx.x;
@@ -150,9 +156,11 @@ __global__ void wsum_fwd_kernel(long long total_pts, int n, int K, int C, const 
 #pragma unroll
     for (int i = 0; i < CV_H; ++i) w[i] = __ldg(w3 + c * CV_H + i);
     const float bv = __ldg(b3 + c);
+    const int K = KT ? KT : Krt;
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
         const long long cloud = p / n;
         float s = 0.0f;
+#pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long r = p * K + k;
             const float4 ha = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H)), hb = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H) + 1);
@@ -169,7 +177,8 @@ __global__ void wsum_fwd_kernel(long long total_pts, int n, int K, int C, const 
 // backward: dx rows (idx == null), dh2 (p,k,8), per-CTA partials of dW3 (C x 8) and db3 (C).  Thread = channel.
 // dh2[p,k,i] = sum_c W3[c,i] * dwn[p,k,c] crosses the threads: the point's dwn (K x C) goes through shared memory and the
 // first K * 8 threads add it over the channels in channel order.
-__global__ void wsum_bwd_kernel(long long total_pts, int n, int K, int C, const float *__restrict__ x, const int *__restrict__ idx,
+template <int KT>
+__global__ void wsum_bwd_kernel(long long total_pts, int n, int Krt, int C, const float *__restrict__ x, const int *__restrict__ idx,
                                 const float *__restrict__ h2, const float *__restrict__ w3, const float *__restrict__ b3,
                                 const float *__restrict__ dout, float *__restrict__ dx, float *__restrict__ dh2, float *__restrict__ part) {
     extern __shared__ float s_mem[];
@@ -184,11 +193,13 @@ __global__ void wsum_bwd_kernel(long long total_pts, int n, int K, int C, const 
         aw[i] = 0.0f;
     }
     const float bv = __ldg(b3 + c);
+    const int K = KT ? KT : Krt;
     float ab = 0.0f;
     __syncthreads();
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
         const long long cloud = p / n;
         const float dv = __ldg(dout + p * C + c);
+#pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long r = p * K + k;
             const float4 ha = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H)), hb = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H) + 1);
@@ -266,7 +277,8 @@ RT_API int rt_cv1_forward(int b, int n1, int n2, int k, int c, const float *p1, 
     const long long pts = (long long)b * n1;
     if (pts == 0) return RT_OK;
     const int grid = (int)min(pts, (long long)cv_sms() * 8);
-    cv1_fwd_kernel<<<grid, c, 0, (cudaStream_t)stream>>>(pts, n1, n2, k, c, p1, p2, xyz1, xyz2, idx, wd, bias, out, dir_out);
+    if (k == 16) cv1_fwd_kernel<16><<<grid, c, 0, (cudaStream_t)stream>>>(pts, n1, n2, k, c, p1, p2, xyz1, xyz2, idx, wd, bias, out, dir_out);
+    else cv1_fwd_kernel<0><<<grid, c, 0, (cudaStream_t)stream>>>(pts, n1, n2, k, c, p1, p2, xyz1, xyz2, idx, wd, bias, out, dir_out);
     return rt_check_launch("cv1_fwd_kernel");
 }
 
@@ -349,7 +361,9 @@ RT_API int rt_wsum_forward(int b, int n, int k, int c, const float *x, const int
     RT_REQUIRE(x && h2 && w3 && b3 && out, "rt_wsum_forward: null pointer");
     const long long pts = (long long)b * n;
     if (pts == 0) return RT_OK;
-    wsum_fwd_kernel<<<(int)min(pts, (long long)cv_sms() * 8), c, 0, (cudaStream_t)stream>>>(pts, n, k, c, x, idx, h2, w3, b3, out);
+    const int grid = (int)min(pts, (long long)cv_sms() * 8);
+    if (k == 16) wsum_fwd_kernel<16><<<grid, c, 0, (cudaStream_t)stream>>>(pts, n, k, c, x, idx, h2, w3, b3, out);
+    else wsum_fwd_kernel<0><<<grid, c, 0, (cudaStream_t)stream>>>(pts, n, k, c, x, idx, h2, w3, b3, out);
     return rt_check_launch("wsum_fwd_kernel");
 }
 
@@ -373,7 +387,8 @@ RT_API int rt_wsum_backward(int b, int n, int k, int c, const float *x, const in
     const size_t smem = sizeof(float) * ((size_t)c * CV_H + (size_t)k * (c + 1));
     static RtPerDevice attr_set;
     if (smem > 48 * 1024 && !attr_set.done(rt_current_device())) {
-        const cudaError_t e = cudaFuncSetAttribute(wsum_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wsum_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wsum_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             rt_set_error("rt_wsum_backward: cannot reserve shared memory: %s", cudaGetErrorString(e));
             rt_scratch_free(part, st);
@@ -381,7 +396,8 @@ RT_API int rt_wsum_backward(int b, int n, int k, int c, const float *x, const in
         }
         attr_set.mark(rt_current_device());
     }
-    wsum_bwd_kernel<<<grid, c, smem, st>>>(pts, n, k, c, x, idx, h2, w3, b3, dout, idx ? nullptr : dx, dh2, part);
+    if (k == 16) wsum_bwd_kernel<16><<<grid, c, smem, st>>>(pts, n, k, c, x, idx, h2, w3, b3, dout, idx ? nullptr : dx, dh2, part);
+    else wsum_bwd_kernel<0><<<grid, c, smem, st>>>(pts, n, k, c, x, idx, h2, w3, b3, dout, idx ? nullptr : dx, dh2, part);
     rc = rt_check_launch("wsum_bwd_kernel");
     if (rc == RT_OK) {
         float *red = part + (size_t)grid * M;
