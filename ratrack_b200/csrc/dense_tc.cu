@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         // The (tile, K chunk) items of this CTA form one flat sequence; the loads of item i+1 are in flight while item i is
         // converted and stored (two register sets).  ncu on the first version (8 warps, generic addressing): 92 % of the
         // kernel's instructions were the loaders', 115 per 32-byte task, two warps per scheduler -> instruction-latency bound
-        // at a third of the HBM rate.  Hence 16 warps and a lean path (whole tile in range, 32-byte aligned rows, full K chunks)
-        // whose per-task cost is one pointer add, one 256-bit load, the split and two 128-bit stores.
+        // at a third of the HBM rate.  Hence 16 warps and a lean path (whole tile in range, 16-byte aligned rows, full K chunks)
+        // whose per-task cost is one pointer add, one 128-bit load, the split of four values and two 64-bit stores.
         const int lw = warp - LT_EPI_WARPS;
         const bool al16 = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
         const bool lean_k = al16 && (a.k % LT_KC) == 0;
