@@ -8,7 +8,7 @@ Functional, driven by a reference-format state_dict (key names of SURVEY.md App.
 fp32 torch-CPU ops for the dense layers (conv1x1 = matmul, BatchNorm, Linear, GRU) and
 the C oracle (oracle/pointnet2_oracle.c) for the native pointnet2 ops.  Each function
 cites the reference lines it restates.  Pinned against the UNMODIFIED reference Python
-(run through oracle/ref_harness.py) by tests/test_oracle_vs_reference.py in the dev
+(run through oracle/ref_harness.py) by tests/test_oracle_golden.py::test_oracle_vs_live_reference_python in the dev
 container and by tests/golden/backbone_*.npz (outputs of that reference run) everywhere.
 
 BatchNorm: `training=False` uses running stats (net.eval()); `training=True` uses batch
