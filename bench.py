@@ -15,9 +15,11 @@ Printed JSON (one line, rank 0):
                micro-batch, copies of neighbouring micro-batches overlapped with compute: infer_host_stream)
   roofline     the dominant kernel of the step, timed live with CUDA events on its launch stream
   cpu_baseline the CPU oracle port (torch-CPU dense layers + C/OpenMP pointnet2 ops) on a bounded sample
-  ref_gpu      (informational) the reference's own CUDA kernels (oracle/_ref) under the same torch modules
-  train        (informational, BASELINE configs[2]) the training step at batch 256 per GPU with the time and bytes of its
-               two collectives (gradient all_reduce, affinity all_gather)
+  ref_gpu      (informational) the reference's own CUDA kernels (oracle/_ref) under torch fp32 modules evaluated op by op as the
+               reference's modules do (model_utils.reference_dataflow: nn.Conv2d / cuDNN, none of this package's dense kernels)
+  train        (informational, BASELINE configs[2]) the training step at batch 256 per GPU -- autograd over the package's tcgen05
+               dense kernels and fused cost-volume / grouping kernels -- with the time and bytes of its two
+               collectives (gradient all_reduce, affinity all_gather)
   train_cfg4   (informational, BASELINE configs[4]) the same step at N=3000 points, 16 pairs per GPU (= batch 128 on 8 GPUs)
 --impl reference times the reference's CPU path (the oracle port: the reference has no CPU implementation of
 its native ops, and its Python cannot travel to the GPU box) on the host cores.
