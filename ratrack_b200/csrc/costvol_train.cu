@@ -157,6 +157,45 @@ __global__ void wsum_fwd_kernel(long long total_pts, int n, int Krt, int C, cons
     for (int i = 0; i < CV_H; ++i) w[i] = __ldg(w3 + c * CV_H + i);
     const float bv = __ldg(b3 + c);
     const int K = KT ? KT : Krt;
+    if constexpr (KT > 0) {
+        // The point's hidden rows (and neighbour indices) are the same for every channel: the CTA stages them in shared memory
+        // one point ahead, so a thread's only global loads are its KT independent x values -- all in flight together -- instead of
+        // KT dependent index -> row chains plus 2 KT broadcast loads that the register budget serialised.
+        __shared__ __align__(16) float s_h2[2][KT * CV_H];
+        __shared__ int s_idx[2][KT];
+        auto stage = [&](long long q, int buf) {
+            for (int i = threadIdx.x; i < KT * (CV_H + 1); i += blockDim.x) {
+                if (i < KT * CV_H) s_h2[buf][i] = __ldg(h2 + q * KT * CV_H + i);
+                else if (idx) s_idx[buf][i - KT * CV_H] = __ldg(idx + q * KT + (i - KT * CV_H));
+            }
+        };
+        long long p = blockIdx.x;
+        int buf = 0;
+        if (p < total_pts) stage(p, 0);
+        __syncthreads();
+        for (; p < total_pts; p += gridDim.x, buf ^= 1) {
+            const long long cloud = p / n;
+            float xv[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const long long xr = idx ? cloud * n + s_idx[buf][k] : p * KT + k;
+                xv[k] = __ldg(x + xr * C + c);
+            }
+            if (p + gridDim.x < total_pts) stage(p + gridDim.x, buf ^ 1);   // the other buffer was last read before the previous barrier
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const float4 ha = *reinterpret_cast<const float4 *>(&s_h2[buf][k * CV_H]), hb = *reinterpret_cast<const float4 *>(&s_h2[buf][k * CV_H + 4]);
+                float wn = bv;
+                wn = fmaf(w[0], ha.x, wn); wn = fmaf(w[1], ha.y, wn); wn = fmaf(w[2], ha.z, wn); wn = fmaf(w[3], ha.w, wn);
+                wn = fmaf(w[4], hb.x, wn); wn = fmaf(w[5], hb.y, wn); wn = fmaf(w[6], hb.z, wn); wn = fmaf(w[7], hb.w, wn);
+                s = fmaf(fmaxf(wn, 0.0f), xv[k], s);
+            }
+            out[p * C + c] = s;
+            __syncthreads();
+        }
+        return;
+    }
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
         const long long cloud = p / n;
         float s = 0.0f;
@@ -196,19 +235,51 @@ __global__ void wsum_bwd_kernel(long long total_pts, int n, int Krt, int C, cons
     const int K = KT ? KT : Krt;
     float ab = 0.0f;
     __syncthreads();
-    for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
+    constexpr int KS = KT > 0 ? KT : 1;
+    __shared__ __align__(16) float s_h2[2][KS * CV_H];   // KT > 0: the point's hidden rows / neighbour indices, staged one point ahead
+    __shared__ int s_idx[2][KS];
+    auto stage = [&](long long q, int buf) {
+        for (int i = threadIdx.x; i < KS * (CV_H + 1); i += blockDim.x) {
+            if (i < KS * CV_H) s_h2[buf][i] = __ldg(h2 + q * KS * CV_H + i);
+            else if (idx) s_idx[buf][i - KS * CV_H] = __ldg(idx + q * KS + (i - KS * CV_H));
+        }
+    };
+    int buf = 0;
+    if (KT > 0 && (long long)blockIdx.x < total_pts) {
+        stage(blockIdx.x, 0);
+        __syncthreads();
+    }
+    for (long long p = blockIdx.x; p < total_pts; p += gridDim.x, buf ^= 1) {
         const long long cloud = p / n;
         const float dv = __ldg(dout + p * C + c);
+        float xv[KS];
+        if constexpr (KT > 0) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const long long xr = idx ? cloud * n + s_idx[buf][k] : p * KT + k;
+                xv[k] = __ldg(x + xr * C + c);     // KT independent loads, all in flight
+            }
+            if (p + gridDim.x < total_pts) stage(p + gridDim.x, buf ^ 1);   // read next after the two barriers below
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long r = p * K + k;
-            const float4 ha = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H)), hb = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H) + 1);
+            float4 ha, hb;
+            if constexpr (KT > 0) {
+                ha = *reinterpret_cast<const float4 *>(&s_h2[buf][k * CV_H]);
+                hb = *reinterpret_cast<const float4 *>(&s_h2[buf][k * CV_H + 4]);
+            } else {
+                ha = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H));
+                hb = __ldg(reinterpret_cast<const float4 *>(h2 + r * CV_H) + 1);
+            }
             float wn = bv;
             wn = fmaf(w[0], ha.x, wn); wn = fmaf(w[1], ha.y, wn); wn = fmaf(w[2], ha.z, wn); wn = fmaf(w[3], ha.w, wn);
             wn = fmaf(w[4], hb.x, wn); wn = fmaf(w[5], hb.y, wn); wn = fmaf(w[6], hb.z, wn); wn = fmaf(w[7], hb.w, wn);
-            const long long xr = idx ? cloud * n + __ldg(idx + r) : r;
+            float xk;
+            if constexpr (KT > 0) xk = xv[k];
+            else xk = __ldg(x + (idx ? cloud * n + __ldg(idx + r) : r) * C + c);
             if (dx) dx[r * C + c] = fmaxf(wn, 0.0f) * dv;
-            const float dwn = wn > 0.0f ? __ldg(x + xr * C + c) * dv : 0.0f;
+            const float dwn = wn > 0.0f ? xk * dv : 0.0f;
             s_dwn[k * (C + 1) + c] = dwn;
             ab += dwn;
             aw[0] = fmaf(dwn, ha.x, aw[0]); aw[1] = fmaf(dwn, ha.y, aw[1]); aw[2] = fmaf(dwn, ha.z, aw[2]); aw[3] = fmaf(dwn, ha.w, aw[3]);
