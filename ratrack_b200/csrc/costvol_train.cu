@@ -25,6 +25,10 @@ namespace {
 constexpr int CV_MAXK = 32;     // neighbours per point (the model uses 16)
 constexpr int CV_H = 8;         // WeightNet hidden width (reference: model_utils.py:359-390, hidden_unit=[8, 8])
 
+// point / destination index -> cloud: a 32-bit division whenever the index fits (the 64-bit one costs ~100 instructions per thread)
+__device__ __forceinline__ long long cv_div(long long a, int b) {
+    return a <= 0xffffffffll ? (long long)((unsigned)a / (unsigned)b) : a / b;
+}
 __device__ __forceinline__ float cv_leaky(float v) { return fmaxf(v, 0.1f * v); }
 __device__ __forceinline__ float cv_slope(float y) { return y > 0.0f ? 1.0f : 0.1f; }
 
@@ -47,7 +51,7 @@ __global__ void cv1_fwd_kernel(long long total_pts, int n1, int n2, int Krt, int
     const int K = KT ? KT : Krt;
     const float wx = __ldg(wd + c * 3), wy = __ldg(wd + c * 3 + 1), wz = __ldg(wd + c * 3 + 2), bv = bias ? __ldg(bias + c) : 0.0f;
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
-        const long long cloud = p / n1;
+        const long long cloud = cv_div(p, n1);
         const float qx = __ldg(xyz1 + p * 3), qy = __ldg(xyz1 + p * 3 + 1), qz = __ldg(xyz1 + p * 3 + 2);
         const float p1v = __ldg(p1 + p * C + c);
 #pragma unroll
@@ -92,8 +96,8 @@ __global__ void cv1_bwd_scatter_kernel(long long total_dst, int n2, long long e_
                                        float *__restrict__ dp2) {
     const int c = threadIdx.x;
     for (long long d = blockIdx.x; d < total_dst; d += gridDim.x) {
-        const long long cloud = d / n2;
-        const int t = (int)(d % n2);
+        const long long cloud = cv_div(d, n2);
+        const int t = (int)(d - cloud * n2);
         const int *sg = seg + cloud * (n2 + 1);
         const int j0 = __ldg(sg + t), j1 = __ldg(sg + t + 1);
         const int *ord = order + cloud * e_total;
@@ -174,7 +178,7 @@ __global__ void wsum_fwd_kernel(long long total_pts, int n, int Krt, int C, cons
         if (p < total_pts) stage(p, 0);
         __syncthreads();
         for (; p < total_pts; p += gridDim.x, buf ^= 1) {
-            const long long cloud = p / n;
+            const long long cloud = cv_div(p, n);
             float xv[KT];
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
@@ -197,7 +201,7 @@ __global__ void wsum_fwd_kernel(long long total_pts, int n, int Krt, int C, cons
         return;
     }
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x) {
-        const long long cloud = p / n;
+        const long long cloud = cv_div(p, n);
         float s = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -250,7 +254,7 @@ __global__ void wsum_bwd_kernel(long long total_pts, int n, int Krt, int C, cons
         __syncthreads();
     }
     for (long long p = blockIdx.x; p < total_pts; p += gridDim.x, buf ^= 1) {
-        const long long cloud = p / n;
+        const long long cloud = cv_div(p, n);
         const float dv = __ldg(dout + p * C + c);
         float xv[KS];
         if constexpr (KT > 0) {
@@ -318,8 +322,8 @@ __global__ void wsum_bwd_scatter_kernel(long long total_dst, int n, int K, int C
     const float bv = __ldg(b3 + c);
     const long long e_total = (long long)n * K;
     for (long long d = blockIdx.x; d < total_dst; d += gridDim.x) {
-        const long long cloud = d / n;
-        const int t = (int)(d % n);
+        const long long cloud = cv_div(d, n);
+        const int t = (int)(d - cloud * n);
         const int *sg = seg + cloud * (n + 1);
         const int j0 = __ldg(sg + t), j1 = __ldg(sg + t + 1);
         const int *ord = order + cloud * e_total;
@@ -330,7 +334,7 @@ __global__ void wsum_bwd_scatter_kernel(long long total_dst, int n, int K, int C
             float wn = bv;
             wn = fmaf(w[0], ha.x, wn); wn = fmaf(w[1], ha.y, wn); wn = fmaf(w[2], ha.z, wn); wn = fmaf(w[3], ha.w, wn);
             wn = fmaf(w[4], hb.x, wn); wn = fmaf(w[5], hb.y, wn); wn = fmaf(w[6], hb.z, wn); wn = fmaf(w[7], hb.w, wn);
-            s = fmaf(fmaxf(wn, 0.0f), __ldg(dout + (r / K) * C + c), s);
+            s = fmaf(fmaxf(wn, 0.0f), __ldg(dout + cv_div(r, K) * C + c), s);
         }
         dxpts[d * C + c] = s;
     }
