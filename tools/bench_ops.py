@@ -44,7 +44,7 @@ def main():
 
     def timed(fn):
         ts = []
-        for _ in range(1 if ONCE else 3):
+        for _ in range(0 if ONCE else 3):   # --once: exactly one launch per op reaches the profiler
             fn()
         for _ in range(REPS):
             flush.zero_()
