@@ -84,13 +84,25 @@ class Track4D(Track4DBackbone):
         self.max_id = 0
 
     # -- reference-shaped methods ----------------------------------------------------------------------------------
-    def forward(self, pc1, pc2, feature1, feature2, h, objects_prev):
+    def forward(self, pc1, pc2, feature1, feature2, h, objects_prev, npts1=None, npts2=None):
         """Batch 1 with `objects_prev` a dict: the reference's call (track4d.py:49-65), same 10-tuple.
-        Batch B with `objects_prev` a list of B dicts (B independent sequences at the same time step): see forward_batch."""
+        Batch B with `objects_prev` a list of B dicts (B independent sequences at the same time step): see forward_batch.
+        npts1 / npts2 (batch 1, beyond the reference's signature): point counts of a zero-padded pair whose two clouds differ
+        in size (main_utils.pair_tensors); the padded columns are dropped again before clustering, so the 10-tuple is that of
+        the unpadded pair."""
         if isinstance(objects_prev, (list, tuple)):
+            if npts1 is not None:
+                raise ValueError("forward_batch takes clouds of one size; variable-size pairs go one pair per call")
             return self.forward_batch(pc1, pc2, feature1, feature2, h, objects_prev)
-        out = self.backbone(pc1, pc2, feature1, feature2, h)
-        return self.track(pc1, feature1, out, objects_prev)
+        if npts1 is None:
+            out = self.backbone(pc1, pc2, feature1, feature2, h)
+            return self.track(pc1, feature1, out, objects_prev)
+        if pc1.shape[0] != 1:
+            raise ValueError("npts1 / npts2 are for a single padded pair (batch 1)")
+        out = self.backbone(pc1, pc2, feature1, feature2, h, npts1=npts1, npts2=npts2)
+        n1 = int(npts1[0])
+        out = tuple(o if (o is None or i == 1) else o[..., :(int(npts2[0]) if i == 5 else n1)] for i, o in enumerate(out))
+        return self.track(pc1[..., :n1], feature1[..., :n1], out, objects_prev)
 
     def forward_batch(self, pc1, pc2, feature1, feature2, h, objects_prev, max_ids=None):
         """B independent sequences per call: ONE batched backbone pass (h is (5,B,128), one recurrent state per sequence),
