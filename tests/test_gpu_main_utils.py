@@ -2,9 +2,10 @@
 files out, the state carried as the reference's epoch loop carries it (src/main_utils.py:44-185).
 
 Written in the last minutes of this round's GPU budget.  The equal-size loop ran on a B200 and passed
-(profiles/r2_main_utils_gpu.txt).  The unequal-size case failed in that run on an assertion of the TEST (it required the
-'50-50 rne' metric to be finite, which it is not when no `cls` probability equals 1 exactly -- the reference's own
-`np.mean([])`); the assertion is corrected below, but the corrected test has not run on hardware, hence its non-strict xfail:
+(profiles/r2_main_utils_gpu.txt).  The unequal-size case did not pass in that run; the xfail mark it ran under hid the traceback.
+One defect was found afterwards, in the TEST: it required the '50-50 rne' metric to be finite, which it is not when no `cls`
+probability equals 1 exactly (the reference's own `np.mean([])`; reproduced on the CPU).  That assertion is corrected below; whether
+it was the only cause is not known, the corrected test has not run on hardware, hence its non-strict xfail:
 a pass is reported as XPASS, a failure cannot mask the rest of the suite."""
 import os
 
@@ -74,7 +75,7 @@ def test_eval_epoch_equals_the_hand_written_loop(tmp_path):
     assert out["objects"] == n_obj
 
 
-@pytest.mark.xfail(strict=False, reason="corrected after its only hardware run (test-side assertion on a NaN-by-definition metric); not re-run: GPU budget of the round spent")
+@pytest.mark.xfail(strict=False, reason="did not pass in its only hardware run; a test-side assertion on a NaN-by-definition metric was corrected afterwards, not re-run: GPU budget of the round spent")
 def test_eval_epoch_with_clouds_of_unequal_sizes(tmp_path):
     d = synthetic.make_batch(3, 320, seed=32)
     frames = {7: _records(d, 0, 301), 8: _records(d, 1, 320), 9: _records(d, 2, 277)}
