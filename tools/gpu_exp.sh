@@ -1,4 +1,5 @@
 #!/bin/bash
+# hardware probe of the TMA gather4 instruction + A/B of the wide (16 worker warps) mlp_tc variant (RT_MLP_WIDE)
 timeout 120 tools/tma_gather_probe
 echo "--- wide mlp_tc A/B"
 timeout 600 python -m pytest tests/test_gpu_backbone.py -m gpu -q --tb=short -x 2>&1 | tail -n 2
