@@ -14,7 +14,8 @@ Printed JSON (one line, rank 0):
   e2e          same metric through the public host-buffer API (pinned host -> H2D -> backbone -> D2H flow+cls per
                micro-batch, copies of neighbouring micro-batches overlapped with compute: infer_host_stream)
   roofline     the dominant kernel of the step, timed live with CUDA events on its launch stream
-  cpu_baseline the CPU oracle port (torch-CPU dense layers + C/OpenMP pointnet2 ops) on a bounded sample
+  cpu_baseline the CPU oracle port (torch-CPU dense layers + C/OpenMP pointnet2 ops) on a bounded sample: micro-batches of 8 pairs
+               of the same workload for about 12 s (at most 1024 pairs); the sample is named in the record
   ref_gpu      (informational) the reference's own CUDA kernels (oracle/_ref) under torch fp32 modules evaluated op by op as the
                reference's modules do (model_utils.reference_dataflow: nn.Conv2d / cuDNN, none of this package's dense kernels)
   train        (informational, BASELINE configs[2]) the training step at batch 256 per GPU -- autograd over the package's tcgen05
@@ -112,8 +113,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_rate(pairs, micro, points, threads=None):
-    """Oracle port of the reference path on the host cores: returns (frames/s, cores, seconds)."""
+def cpu_reference_rate(pairs, micro, points, threads=None, min_seconds=0.0, max_pairs=None):
+    """Oracle port of the reference path on the host cores: at least `pairs` pairs and `min_seconds` of work (bounded by
+    `max_pairs`); returns (frames/s, cores, seconds, pairs done)."""
     import torch
 
     from oracle import backbone_oracle
@@ -130,11 +132,11 @@ def cpu_reference_rate(pairs, micro, points, threads=None):
     backbone_oracle.backbone(sd, c["pc1"], c["pc2"], c["ft1"], c["ft2"], h)  # warm-up (thread pools, mkldnn primitives)
     t0 = time.perf_counter()
     done = 0
-    while done < pairs:
+    while done < pairs or (time.perf_counter() - t0 < min_seconds and (max_pairs is None or done < max_pairs)):
         backbone_oracle.backbone(sd, c["pc1"], c["pc2"], c["ft1"], c["ft2"], h)
         done += micro
     dt = time.perf_counter() - t0
-    return done / dt, cores, dt
+    return done / dt, cores, dt, done
 
 
 def run_reference(a):
@@ -471,9 +473,9 @@ def main():
     if train4 is not None:
         out["train_cfg4"] = train4
     if world == 1 and not a.no_cpu:
-        v, cores, dt = cpu_reference_rate(pairs=32, micro=8, points=N)
+        v, cores, dt, done = cpu_reference_rate(pairs=32, micro=8, points=N, min_seconds=12.0, max_pairs=1024)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"32 pairs (4 micro-batches of 8) of the same N={N} workload, {dt:.1f} s"}
+                               "sample": f"{done} pairs ({done // 8} micro-batches of 8) of the same N={N} workload, {dt:.1f} s"}
         try:
             t1 = {k: v[:B].to(dev) for k, v in host.items()}
             out["ref_gpu"] = ref_gpu_rate(net, t1, torch.zeros(5, t1["pc1"].size(0), 128, device=dev), 5, t1["pc1"].size(0))
