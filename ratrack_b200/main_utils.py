@@ -11,6 +11,9 @@ Host code only.
                         carried state detached (:160-165), the per-frame result file (:167-184), metrics if ground truth is
                         supplied (:132-150).  The label pipeline that produces the ground truth (3-D boxes -> moving points,
                         per-point flow) is the dataset's business and stays outside; `gt_fn` is where it plugs in.
+* `clips_of_rank`,   -- more than one GPU: the recurrent state and the tracked objects belong to a sequence, so
+  `reduce_summary`      whole clips are dealt to the ranks (a sequence never changes rank, no data-path collective) and the per-rank
+                        summaries are summed with one small all_reduce at the end.
 
 Differences from the reference, on purpose: the two clouds of a real pair differ in size (242-352 points in the example set);
 the reference feeds them as they are, one pair per call.  Here a pair of unequal sizes goes through the variable-size entry
@@ -23,6 +26,35 @@ import numpy as np
 import torch
 
 from . import data_io, metrics
+
+FLOW_KEYS = ("rne", "50-50 rne", "mov_rne", "stat_rne", "sas", "ras", "epe")      # eval_scene_flow, main_utils.py:342-374
+SEG_KEYS = ("acc", "miou", "sen")                                                 # eval_motion_seg, main_utils.py:377-389
+
+
+def clips_of_rank(clips, rank, world):
+    """The clips rank `rank` of `world` evaluates: dealt round-robin in list order, every clip to exactly one rank."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside a world of {world}")
+    return list(clips[rank::world])
+
+
+def reduce_summary(summary, group=None, device=None):
+    """Sum what eval_epoch returned over the ranks of `group` (torch.distributed, already initialised): counts and metric sums
+    add up, as the reference's single loop would have accumulated them.  One all_reduce of 13 doubles; `device` = where the
+    collective's buffer lives (a CUDA device for NCCL; default CPU for gloo).  Without an initialised process group: a copy."""
+    import torch.distributed as dist
+
+    vals = [summary["frames"], summary["objects"], summary["examples"]]
+    vals += [summary["flow"].get(k, 0.0) for k in FLOW_KEYS] + [summary["seg"].get(k, 0.0) for k in SEG_KEYS]
+    t = torch.tensor(vals, dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, group=group)
+    v = t.cpu().tolist()
+    out = {"frames": int(round(v[0])), "objects": int(round(v[1])), "examples": int(round(v[2])), "flow": {}, "seg": {}}
+    if out["examples"]:
+        out["flow"] = dict(zip(FLOW_KEYS, v[3:3 + len(FLOW_KEYS)]))
+        out["seg"] = dict(zip(SEG_KEYS, v[3 + len(FLOW_KEYS):]))
+    return out
 
 
 def clip_frame_pairs(radar_dir, clips_dir, clips, reader=data_io.read_radar_bin):

@@ -2,10 +2,12 @@
 (src/dataset_classes/track_vod_3d.py:49-122) and the evaluation branch of its epoch loop (src/main_utils.py:44-185) --
 driven with a recording stand-in for the network."""
 import os
+import socket
 
 import numpy as np
 import pytest
 import torch
+import torch.multiprocessing as mp
 
 from ratrack_b200 import main_utils, metrics
 
@@ -166,3 +168,65 @@ def test_track4d_forward_drops_the_padded_columns_before_tracking():
     assert seen["npts"] == (None, None) and seen["track"][0] == (1, 3, 24)
     with pytest.raises(ValueError):
         net(torch.zeros(2, 3, 24), torch.zeros(2, 3, 24), torch.zeros(2, 2, 24), torch.zeros(2, 2, 24), None, {}, npts1=n1, npts2=n2)
+
+
+def test_clips_are_dealt_whole_and_summaries_add_up_without_a_process_group():
+    clips = ["delft_1", "delft_10", "delft_14", "delft_22", "delft_7"]
+    parts = [main_utils.clips_of_rank(clips, r, 3) for r in range(3)]
+    assert parts == [["delft_1", "delft_22"], ["delft_10", "delft_7"], ["delft_14"]]
+    assert sorted(sum(parts, [])) == sorted(clips)
+    with pytest.raises(ValueError):
+        main_utils.clips_of_rank(clips, 3, 3)
+    s = {"frames": 4, "objects": 8, "examples": 3, "flow": {k: float(i) for i, k in enumerate(main_utils.FLOW_KEYS)},
+         "seg": {"acc": 3.0, "miou": 1.5, "sen": 2.0}}
+    assert main_utils.reduce_summary(s) == s                                        # no process group: a copy
+    empty = {"frames": 2, "objects": 0, "examples": 0, "flow": {}, "seg": {}}
+    assert main_utils.reduce_summary(empty) == empty
+
+
+def _gt(clip, index, pc1):
+    return torch.full_like(pc1, 0.5), (torch.arange(pc1.shape[-1]) % 2).float().reshape(1, -1)
+
+
+def _eval_worker(rank, world, port, root, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clips = main_utils.clips_of_rank(["a", "b", "c"], rank, world)
+    pairs = main_utils.clip_frame_pairs(os.path.join(root, "radar"), os.path.join(root, "clips"), clips)
+    local = main_utils.eval_epoch(_RecordingNet(), pairs, results_dir=os.path.join(root, "results"), gt_fn=_gt)
+    total = main_utils.reduce_summary(local)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, local["frames"], total))
+
+
+def test_two_rank_gloo_evaluation_over_whole_clips(tmp_path):
+    """a sequence stays on one rank; the summed summary equals the single-process loop over all clips."""
+    rng = np.random.default_rng(4)
+    root = str(tmp_path)
+    _write_frames(os.path.join(root, "radar"), list(range(1, 5)) + list(range(10, 13)) + list(range(20, 26)), rng)
+    for name, r in (("a", range(1, 5)), ("b", range(10, 13)), ("c", range(20, 26))):
+        _write_clip(os.path.join(root, "clips"), name, r)
+    want = main_utils.eval_epoch(_RecordingNet(), main_utils.clip_frame_pairs(os.path.join(root, "radar"), os.path.join(root, "clips"),
+                                                                             ["a", "b", "c"]), gt_fn=_gt)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, root, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [3 + 5, 2]                                        # rank 0: clips a, c; rank 1: clip b
+    for _, _, total in res:
+        assert total["frames"] == want["frames"] == 10 and total["objects"] == want["objects"] and total["examples"] == 10
+        assert total["seg"] == pytest.approx(want["seg"])
+        assert total["flow"] == pytest.approx(want["flow"], nan_ok=True)
+    written = sorted(os.path.join(c, f) for c in os.listdir(os.path.join(root, "results")) for f in os.listdir(os.path.join(root, "results", c)))
+    assert len(written) == 10 and written[0] == os.path.join("a", "00002.txt")
