@@ -57,12 +57,17 @@ def reduce_summary(summary, group=None, device=None):
     return out
 
 
-def clip_frame_pairs(radar_dir, clips_dir, clips, reader=data_io.read_radar_bin):
+def clip_frame_pairs(radar_dir, clips_dir, clips, reader=data_io.read_radar_bin, need_previous=True):
     """Yield (frame_a (Na,7), frame_b (Nb,7), index, clip, is_new_seq) in the reference's order.
 
     radar_dir: directory of `<frame:05d>.bin` radar records (VodTrackLocations.radar_dir); clips_dir: directory of `<clip>.txt`
     files listing a clip's frame numbers, first and last line = its range (track_vod_3d.py:56-63); clips: clip names in order
-    (the reference's train / val / test lists, :33-35)."""
+    (the reference's train / val / test lists, :33-35).
+    need_previous: the reference also loads frame `current - 1` (its lidar sweep, for the visualisation, :75-76,89) inside the
+    same try block, so a pair whose previous frame does not exist is dropped -- in practice the pair at frame 0 of the data set.
+    True mirrors that (the previous frame's radar record must exist); False yields every readable pair.
+    One deliberate difference: past the end of a clip whose last frames are unreadable the reference keeps counting up into the
+    next clip's numbers (its `while True` never re-checks the range); here a clip ends at its last line."""
     for clip in clips:
         with open(os.path.join(clips_dir, clip + ".txt")) as f:
             lines = f.read().splitlines()
@@ -72,6 +77,8 @@ def clip_frame_pairs(radar_dir, clips_dir, clips, reader=data_io.read_radar_bin)
             try:
                 a = reader(os.path.join(radar_dir, str(current + 1).zfill(5) + ".bin"))
                 b = reader(os.path.join(radar_dir, str(current).zfill(5) + ".bin"))
+                if need_previous and not os.path.exists(os.path.join(radar_dir, str(current - 1).zfill(5) + ".bin")):
+                    raise OSError("no previous frame")
             except (OSError, ValueError):
                 current += 1                       # the reference's `except: self.current_frame += 1`
                 continue

@@ -54,7 +54,7 @@ def test_eval_epoch_equals_the_hand_written_loop(tmp_path):
     radar, clips = _write(tmp_path, frames)
     results = str(tmp_path / "results")
     net = _net()
-    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["clip"]), results_dir=results, device="cuda")
+    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["clip"], need_previous=False), results_dir=results, device="cuda")
     assert out["frames"] == 4 and sorted(os.listdir(os.path.join(results, "clip"))) == [f"{n:05d}.txt" for n in range(41, 45)]
     # the same frames through the reference-shaped calls by hand
     net2 = _net()
@@ -87,7 +87,7 @@ def test_eval_epoch_with_clouds_of_unequal_sizes(tmp_path):
         seen.append((index, pc1.shape[-1]))
         return torch.zeros_like(pc1), torch.zeros(1, pc1.shape[-1], device=pc1.device)
 
-    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["clip"]), results_dir=str(tmp_path / "r"), device="cuda", gt_fn=gt_fn)
+    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["clip"], need_previous=False), results_dir=str(tmp_path / "r"), device="cuda", gt_fn=gt_fn)
     assert out["frames"] == 2 and seen == [(8, 320), (9, 277)] and out["examples"] == 2
     # 'stat_rne' averages over the points whose probability equals 1 exactly: none here -> nan, as the reference's np.mean([])
     assert all(np.isfinite(v) for k, v in out["flow"].items() if k not in ("stat_rne", "50-50 rne")) and 0.0 <= out["seg"]["acc"] <= 2.0

@@ -31,15 +31,18 @@ def _write_clip(d, name, numbers):
 def test_clip_frame_pairs_follow_the_reference_order(tmp_path):
     rng = np.random.default_rng(0)
     radar, clips = str(tmp_path / "radar"), str(tmp_path / "clips")
-    frames = _write_frames(radar, [10, 11, 12, 14, 15, 30, 31, 32], rng)           # 13 is missing
+    frames = _write_frames(radar, [9, 10, 11, 12, 14, 15, 29, 30, 31, 32], rng)    # 13 is missing
     with open(os.path.join(radar, "00033.bin"), "wb") as f:
         f.write(b"\0" * 40)                                                        # not a whole number of records
     _write_clip(clips, "delft_1", range(10, 16))
     _write_clip(clips, "delft_10", range(30, 35))                                  # 34 is missing too
     got = list(main_utils.clip_frame_pairs(radar, clips, ["delft_1", "delft_10"]))
-    # (first cloud = frame current + 1, second = frame current, index = current + 1); pairs touching 13 / 33 / 34 are skipped
-    assert [(g[2], g[3], g[4]) for g in got] == [(11, "delft_1", True), (12, "delft_1", False), (15, "delft_1", False),
+    # (first cloud = frame current + 1, second = frame current, index = current + 1); pairs touching 13 / 33 / 34 are skipped --
+    # as first, second or PREVIOUS frame (the reference loads frame current - 1 too): (15, 14) goes with them
+    assert [(g[2], g[3], g[4]) for g in got] == [(11, "delft_1", True), (12, "delft_1", False),
                                                  (31, "delft_10", True), (32, "delft_10", False)]
+    loose = list(main_utils.clip_frame_pairs(radar, clips, ["delft_1"], need_previous=False))
+    assert [g[2] for g in loose] == [11, 12, 15]
     for a, b, index, _, _ in got:
         assert np.array_equal(a, frames[index]) and np.array_equal(b, frames[index - 1])
 
@@ -49,8 +52,10 @@ def test_new_sequence_flag_survives_skipped_leading_frames(tmp_path):
     radar, clips = str(tmp_path / "radar"), str(tmp_path / "clips")
     _write_frames(radar, [5, 6, 7], rng)                                            # the clip starts at 3: 3, 4 do not exist
     _write_clip(clips, "c", range(3, 8))
-    got = [(g[2], g[4]) for g in main_utils.clip_frame_pairs(radar, clips, ["c"])]
+    got = [(g[2], g[4]) for g in main_utils.clip_frame_pairs(radar, clips, ["c"], need_previous=False)]
     assert got == [(6, True), (7, False)]
+    # the reference also needs frame current - 1 (its lidar sweep): the pair (6, 5) goes too, 4 does not exist
+    assert [(g[2], g[4]) for g in main_utils.clip_frame_pairs(radar, clips, ["c"])] == [(7, True)]
 
 
 def test_pair_tensors_equal_and_unequal_sizes():
@@ -102,7 +107,7 @@ def test_eval_epoch_carries_state_writes_results_and_accumulates_metrics(tmp_pat
             return None
         return torch.full_like(pc1, 0.5), (torch.arange(pc1.shape[-1]) % 2).float().reshape(1, -1)
 
-    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["a", "b"]), results_dir=results, gt_fn=gt_fn)
+    out = main_utils.eval_epoch(net, main_utils.clip_frame_pairs(radar, clips, ["a", "b"], need_previous=False), results_dir=results, gt_fn=gt_fn)
     assert out["frames"] == 4 and out["objects"] == 8 and out["examples"] == 3
     c = net.calls
     # state: reset at each new sequence, carried (detached) inside one
@@ -194,7 +199,7 @@ def _eval_worker(rank, world, port, root, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     clips = main_utils.clips_of_rank(["a", "b", "c"], rank, world)
-    pairs = main_utils.clip_frame_pairs(os.path.join(root, "radar"), os.path.join(root, "clips"), clips)
+    pairs = main_utils.clip_frame_pairs(os.path.join(root, "radar"), os.path.join(root, "clips"), clips, need_previous=False)
     local = main_utils.eval_epoch(_RecordingNet(), pairs, results_dir=os.path.join(root, "results"), gt_fn=_gt)
     total = main_utils.reduce_summary(local)
     dist.barrier()
@@ -210,7 +215,7 @@ def test_two_rank_gloo_evaluation_over_whole_clips(tmp_path):
     for name, r in (("a", range(1, 5)), ("b", range(10, 13)), ("c", range(20, 26))):
         _write_clip(os.path.join(root, "clips"), name, r)
     want = main_utils.eval_epoch(_RecordingNet(), main_utils.clip_frame_pairs(os.path.join(root, "radar"), os.path.join(root, "clips"),
-                                                                             ["a", "b", "c"]), gt_fn=_gt)
+                                                                             ["a", "b", "c"], need_previous=False), gt_fn=_gt)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -230,3 +235,35 @@ def test_two_rank_gloo_evaluation_over_whole_clips(tmp_path):
         assert total["flow"] == pytest.approx(want["flow"], nan_ok=True)
     written = sorted(os.path.join(c, f) for c in os.listdir(os.path.join(root, "results")) for f in os.listdir(os.path.join(root, "results", c)))
     assert len(written) == 10 and written[0] == os.path.join("a", "00002.txt")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree only exists in the dev container")
+def test_frame_order_equals_the_unmodified_reference_dataset_class(tmp_path):
+    """oracle/ref_frame_order.py drives the reference's own TrackingDataVOD.__getitem__ (file layer substituted, control flow
+    untouched) over the same directory: same pairs, indices, clips and new-sequence flags -- including the pair it drops at
+    the first frame of the data set (no frame -1) and around a missing frame."""
+    import json
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    rng = np.random.default_rng(6)
+    radar, clips = str(tmp_path / "radar"), str(tmp_path / "clips")
+    numbers = [n for n in range(0, 8) if n != 4] + list(range(20, 24)) + list(range(40, 43)) + list(range(60, 64))
+    frames = _write_frames(radar, numbers, rng)
+    val = ["delft_1", "delft_10", "delft_14", "delft_22"]                           # track_vod_3d.py:34, args.eval = True
+    for name, r in zip(val, (range(0, 8), range(20, 24), range(40, 43), range(60, 64))):
+        _write_clip(clips, name, r)
+    mine = list(main_utils.clip_frame_pairs(radar, clips, val))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_frame_order.py"), radar, str(len(mine))],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(ref) == len(mine) and len(mine) >= 8
+    for (a, b, index, clip, new_seq), want in zip(mine, ref):
+        assert (index, clip, new_seq, a.shape[0], b.shape[0]) == (want["index"], want["clip"], want["new_seq"], want["n0"], want["n1"])
+        assert float(np.float64(a[:, :5]).sum()) == pytest.approx(want["sum0"], rel=1e-12)
+        assert float(np.float64(b[:, :5]).sum()) == pytest.approx(want["sum1"], rel=1e-12)
+        assert np.array_equal(a, frames[index]) and np.array_equal(b, frames[index - 1])
+    assert [m[2] for m in mine][:4] == [2, 3, 7, 22] and mine[0][4] and mine[3][4]   # (1,0), (4,3), (5,4), (6,5) dropped
