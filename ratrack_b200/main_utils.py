@@ -19,6 +19,9 @@ Differences from the reference, on purpose: the two clouds of a real pair differ
 the reference feeds them as they are, one pair per call.  Here a pair of unequal sizes goes through the variable-size entry
 (`Track4D.forward(..., npts1=, npts2=)`, zero padding + point counts: data_io.PaddedBatcher's convention), equal sizes through
 the plain one.  Metrics stay on the device until the end (metrics.py); the reference reads them back every frame.
+The reference loads the tracking labels of both frames before it calls the model and skips the frame when that fails (`except:
+continue`, :96-108), so its loop cannot run on unlabelled data at all; here every pair goes through the model and ground truth only
+gates the metrics.
 """
 import os
 
