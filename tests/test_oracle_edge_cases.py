@@ -142,3 +142,55 @@ def test_three_interpolate_rounding_order_and_grad():
 def test_opt_n_threads(n, bs):
     """cuda_utils.h:10-14: the largest power of two <= n, clamped to [1, 1024] -- it fixes the FPS tie rule (A.1)."""
     assert P.opt_n_threads(n) == bs
+
+
+def _d2(p, q):
+    """A.0 on the host: t = dy*dy (rounded to fp32), t = fma(dx, dx, t), d2 = fma(dz, dz, t).  Products of fp32 values are exact
+    in fp64, so rounding each step's fp64 sum to fp32 reproduces the fused operation (up to double rounding, which the fixed seeds
+    below do not hit)."""
+    d = (p - q).astype(np.float32)
+    dx, dy, dz = (d[..., i].astype(np.float64) for i in range(3))
+    t = (dy * dy).astype(np.float32)
+    t = (dx * dx + t).astype(np.float32)
+    return (dz * dz + t).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,m", [(7, 7), (100, 40), (322, 64), (1024, 48), (1500, 32)])
+def test_fps_random_clouds_against_a_numpy_statement(n, m):
+    """Random float clouds (no ties to speak of) with 1 % duplicated points (ties on purpose, as in the VoD frames): running
+    minimum, arg-max with the tree's tie rule, A.0 distance arithmetic."""
+    rng = np.random.default_rng(n)
+    xyz = rng.normal(scale=10.0, size=(2, n, 3)).astype(np.float32)
+    dup = rng.integers(0, n, size=(2, max(1, n // 100), 2))
+    for b in range(2):
+        xyz[b, dup[b, :, 0]] = xyz[b, dup[b, :, 1]]
+    got, temp_got = P.furthest_point_sample(xyz, m, return_temp=True)
+    bs = P.opt_n_threads(n)
+    bits = bs.bit_length() - 1
+    rank = np.array([(_bitrev(k % bs, bits), k // bs) for k in range(n)])
+    order = np.lexsort((rank[:, 1], rank[:, 0]))                          # positions in the tree's priority order
+    for b in range(2):
+        temp = np.full(n, 1e10, np.float32)
+        old = 0
+        for j in range(1, m):
+            temp = np.minimum(temp, _d2(xyz[b], xyz[b, old]))
+            cands = temp[order]
+            old = int(order[int(np.argmax(cands))])                      # first maximum in priority order
+            assert got[b, j] == old, (b, j)
+        assert np.array_equal(temp_got[b], temp)
+
+
+def test_three_nn_and_knn_against_a_stable_sort():
+    """A.3 / A.4: ascending distances, ties to the lower index -- a stable argsort of the A.0 distances."""
+    rng = np.random.default_rng(21)
+    known = rng.normal(scale=3.0, size=(2, 60, 3)).astype(np.float32)
+    known[:, 30:40] = known[:, 10:20]                                    # duplicates: exact ties
+    unknown = rng.normal(scale=3.0, size=(2, 25, 3)).astype(np.float32)
+    d2_3, i3 = P.three_nn_raw(unknown, known)
+    d2_k, ik = P.knn_raw(9, unknown, known)
+    for b in range(2):
+        for q in range(25):
+            d = _d2(known[b], unknown[b, q])
+            o = np.argsort(d, kind="stable")
+            assert i3[b, q].tolist() == o[:3].tolist() and np.array_equal(d2_3[b, q], d[o[:3]])
+            assert ik[b, q].tolist() == o[:9].tolist() and np.array_equal(d2_k[b, q], d[o[:9]])
